@@ -1,0 +1,194 @@
+/* b200als.h -- C ABI of libb200als.so, the Blackwell-native WRMF / ALS half-iteration engine.
+ *
+ * This is the drop-in boundary for rsparse's matrix-factorization hot path.  Every entry point
+ * is `extern "C"`, takes plain pointers and sizes (no R, Rcpp, Armadillo or torch types) and
+ * returns an integer status (0 = ok); `b200als_last_error()` gives the message.  The library's
+ * only compute is hand-written sm_100a CUDA; there is no CPU fallback -- without a CUDA device
+ * every compute call fails with B200ALS_ECUDA.
+ *
+ * Citations are relative to the reference tree (dselivanov/rsparse @ 54f7e6a):
+ *   - `.Call` targets being replaced: src/RcppExports.cpp:329-416, registered :456-490,
+ *     R stubs R/RcppExports.R:88-102, callers R/model_WRMF.R:493-495, :514
+ *   - argument meaning:              src/wrmf_implicit.cpp:5-31, src/wrmf_explicit.cpp:5-27
+ *   - sparse input layout:           inst/include/mapped_csc.hpp:8-29, src/utils.cpp:69-78
+ *   - solver codes:                  inst/include/wrmf.hpp:16-18
+ *
+ * Dense layout: a factor matrix is `rank x n` column-major (R / Armadillo layout), i.e. n
+ * contiguous rows of `rank` values.  Sparse layout: CSC whose COLUMNS are the rows being solved
+ * for (R passes the CSC of users x items for the item half-iteration and the row-major copy
+ * re-labelled as CSC for the user half-iteration, R/model_WRMF.R:184-189); 32-bit 0-based
+ * indices exactly as in R's `@i` / `@p` slots; values either double (R's `@x`) or float.
+ */
+#ifndef B200ALS_H
+#define B200ALS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ALS_VERSION 100
+
+/* status codes */
+#define B200ALS_OK 0
+#define B200ALS_EINVAL 1       /* bad argument (null pointer, negative size, unknown code)       */
+#define B200ALS_ECUDA 2        /* CUDA runtime error / no device                                 */
+#define B200ALS_ENCCL 3        /* NCCL error                                                     */
+#define B200ALS_ENOTSPD 4      /* a per-row system was not positive definite (Cholesky pivot<=0)  */
+#define B200ALS_EUNSUPPORTED 5 /* valid in the reference but not implemented by this engine yet   */
+
+/* inst/include/wrmf.hpp:16-18 */
+#define B200ALS_CHOLESKY 0
+#define B200ALS_CONJUGATE_GRADIENT 1
+#define B200ALS_NNLS 2
+
+#define B200ALS_IMPLICIT 0
+#define B200ALS_EXPLICIT 1
+
+/* which factor matrix a session call refers to */
+#define B200ALS_ITEMS 0
+#define B200ALS_USERS 1
+
+/* Zero-copy view of a dgCMatrix, field for field the reference's MappedCSC<double>
+ * (inst/include/mapped_csc.hpp:8-29) plus an optional float copy of the values. */
+typedef struct b200als_csc {
+  int32_t n_rows;        /* length of the dimension `idx` indexes (= rows of the fixed factor matrix X) */
+  int32_t n_cols;        /* number of columns = number of rows of Y being solved for                   */
+  int64_t nnz;
+  const int32_t* ptr;    /* [n_cols + 1]  R slot @p                                                    */
+  const int32_t* idx;    /* [nnz]         R slot @i, ascending within a column                          */
+  const double* val_f64; /* [nnz]         R slot @x, or NULL                                           */
+  const float* val_f32;  /* [nnz]         optional float values (used when val_f64 is NULL)            */
+} b200als_csc;
+
+const char* b200als_last_error(void);
+int b200als_version(void);
+/* Number of visible CUDA devices (0 and B200ALS_ECUDA when there is none). */
+int b200als_device_count(int* count);
+int b200als_set_device(int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * 1. Stateless half-iteration calls -- same argument lists as the reference's Rcpp exports
+ *    (src/wrmf_implicit.cpp:5-31, src/wrmf_explicit.cpp:5-27) with the S4/SEXP objects flattened:
+ *    `X` is rank x m_csc->n_rows (read-only), `Y` is rank x m_csc->n_cols (updated IN PLACE, as the
+ *    reference does, R/model_WRMF.R:492), `XtX` is rank x rank and already contains +lambda*I
+ *    (R/model_WRMF.R:476-484); pass XtX = NULL to have the engine compute XX^T + lambda*I on the GPU.
+ *    All pointers are HOST pointers; the call copies in, computes on the current device, copies Y
+ *    back and retains nothing.  `*loss` receives the reference's return value (loss / nnz).
+ *    `n_threads` is accepted for signature compatibility and ignored.
+ *    with_biases / global_bias are not implemented: a non-zero value returns
+ *    B200ALS_EUNSUPPORTED.  solver = B200ALS_NNLS likewise (section 8f-4).
+ * ---------------------------------------------------------------------------------------------- */
+int b200als_als_implicit_float(const b200als_csc* m_csc, int rank, const float* X, float* Y,
+                               const float* XtX, double lambda, int n_threads, unsigned solver,
+                               unsigned cg_steps, int with_biases, int is_x_bias_last_row,
+                               double global_bias, float* global_bias_base,
+                               int initialize_bias_base, double* loss);
+int b200als_als_implicit_double(const b200als_csc* m_csc, int rank, const double* X, double* Y,
+                                const double* XtX, double lambda, int n_threads, unsigned solver,
+                                unsigned cg_steps, int with_biases, int is_x_bias_last_row,
+                                double global_bias, double* global_bias_base,
+                                int initialize_bias_base, double* loss);
+int b200als_als_explicit_float(const b200als_csc* m_csc, int rank, const float* X, float* Y,
+                               const float* cnt_X, double lambda, unsigned n_threads,
+                               unsigned solver, unsigned cg_steps, int dynamic_lambda,
+                               int with_biases, int is_x_bias_last_row, double* loss);
+int b200als_als_explicit_double(const b200als_csc* m_csc, int rank, const double* X, double* Y,
+                                const double* cnt_X, double lambda, unsigned n_threads,
+                                unsigned solver, unsigned cg_steps, int dynamic_lambda,
+                                int with_biases, int is_x_bias_last_row, double* loss);
+
+/* XtX = tcrossprod(X) + lambda*I  (R/model_WRMF.R:474-486, :347-353); X is rank x n host memory. */
+int b200als_gram_float(const float* X, int rank, int64_t n, double lambda, float* XtX);
+
+/* ------------------------------------------------------------------------------------------------
+ * 2. Session API -- the device-resident form of WRMF$fit_transform (R/model_WRMF.R:173-360).
+ *    The sparse matrix is uploaded once in both orientations, both factor matrices stay in HBM,
+ *    and the ALS loop (item half, user half, convergence test of R/model_WRMF.R:318-338) runs
+ *    without touching the host.  fp32 only (north star).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct b200als_session b200als_session;
+
+typedef struct b200als_options {
+  int feedback;        /* B200ALS_IMPLICIT / B200ALS_EXPLICIT                                     */
+  int solver;          /* wrmf.hpp:16-18                                                         */
+  int cg_steps;        /* R default 3                                                            */
+  int dynamic_lambda;  /* explicit feedback only (wrmf_explicit.hpp:78)                          */
+  double lambda;
+  int kernel;          /* CG kernel choice: 0 = auto; 1 = generic streaming kernel; 2 = register-resident
+                          kernel with the full XtX (rank 128 only); 3 = register-resident kernel in the
+                          eigenbasis of XtX even for small inputs (implicit, rank 128 only)       */
+  int reserved[7];
+} b200als_options;
+
+void b200als_default_options(b200als_options* o);
+
+/* c_ui: CSC of users x items (columns = items, idx = users)  -> item half-iteration
+ * c_iu: CSC of items x users (columns = users, idx = items)  -> user half-iteration
+ * Either may be NULL if that half-iteration is never run.  Host pointers; copied to the device.
+ * With a communicator (section 3) each rank passes only ITS block of columns for each
+ * orientation plus the global offset of that block, and holds full copies of both factor matrices. */
+int b200als_create(b200als_session** out, const b200als_csc* c_ui, const b200als_csc* c_iu,
+                   int32_t n_user, int32_t n_item, int rank, const b200als_options* opts);
+int b200als_destroy(b200als_session* s);
+
+/* Copy a full factor matrix (rank x n, host memory) to / from the session. */
+int b200als_set_factors(b200als_session* s, int which, const float* host);
+int b200als_get_factors(b200als_session* s, int which, float* host);
+/* Initialise like R/model_WRMF.R:203-244: users ~ N(0,1)/100, items zero for CG / N(0,1)/100 else. */
+int b200als_init_factors(b200als_session* s, uint64_t seed);
+
+/* One half-iteration solving for `which` (B200ALS_ITEMS / B200ALS_USERS); solver_override < 0
+ * keeps the session's solver, otherwise uses the given code (the avoid_cg path of
+ * R/model_WRMF.R:112,:412-452 passes B200ALS_CHOLESKY).  `*loss` may be NULL. */
+int b200als_half_iteration(b200als_session* s, int which, int solver_override, double* loss);
+
+/* The loop of R/model_WRMF.R:318-338: up to n_iter (items, users) pairs, stopping when
+ * loss_prev / loss - 1 < convergence_tol.  loss_trace (may be NULL) receives 2 values per
+ * iteration run; *n_iter_done the count of iterations run. */
+int b200als_fit(b200als_session* s, int n_iter, double convergence_tol, double* loss_trace,
+                int* n_iter_done);
+
+/* transform_ (R/model_WRMF.R:412-452): solve the user half with Y = 0 and CG replaced by
+ * Cholesky against the session's item factors; writes rank x n_user to `host_out` without
+ * disturbing the session's user factors. */
+int b200als_transform(b200als_session* s, float* host_out, double* loss);
+
+/* Device time (ms, CUDA events on the engine's stream) of the last half-iteration, split into
+ * gram (XtX), prepare (basis change) and solve; any pointer may be NULL. */
+int b200als_last_timing(b200als_session* s, float* gram_ms, float* prep_ms, float* solve_ms,
+                        float* comm_ms);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3. Multi-GPU: one process per GPU.  Rank 0 creates an id, the host program distributes the
+ *    128 bytes (torch.distributed / MPI / a file), every rank calls b200als_comm_init.  A session
+ *    created afterwards shards the solved rows by contiguous blocks and all-gathers the updated
+ *    factor slices over NCCL once per half-iteration.
+ * ---------------------------------------------------------------------------------------------- */
+#define B200ALS_UNIQUE_ID_BYTES 128
+int b200als_comm_unique_id(void* id_out /* 128 bytes */);
+int b200als_comm_init(const void* id, int rank, int world_size);
+int b200als_comm_destroy(void);
+int b200als_comm_info(int* rank, int* world_size);
+/* Tell a session which global column range [begin, end) of each orientation this rank owns. */
+int b200als_set_shard(b200als_session* s, int which, int32_t begin, int32_t end);
+
+/* ------------------------------------------------------------------------------------------------
+ * 4. Synthetic workload generator used by bench.py and the tests: every
+ *    row draws exactly nnz_per_row distinct ascending column ids (counter-based hash, seed) and a
+ *    positive confidence (implicit) or a rating in 1..5 (explicit).  Fills a session's c_iu
+ *    orientation directly in HBM, or host arrays when the *_host pointers are given.
+ * ---------------------------------------------------------------------------------------------- */
+int b200als_synth_csr_host(int32_t n_rows, int32_t n_cols, int32_t nnz_per_row, uint64_t seed,
+                           int explicit_values, int64_t row_offset, int32_t* ptr, int32_t* idx,
+                           float* val_f32, double* val_f64);
+int b200als_create_synthetic(b200als_session** out, int32_t n_user_local, int64_t user_offset,
+                             int32_t n_user_global, int32_t n_item, int32_t nnz_per_row,
+                             uint64_t seed, int rank, const b200als_options* opts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ALS_H */

@@ -1,0 +1,339 @@
+// als_resident.cuh -- the hot kernel: fixed-step CG half-iteration with the row's gathered factor
+// tile RESIDENT IN REGISTERS for the whole solve (rank 128, fp32, rows with 1..80 non-zeros).
+//
+// Reference semantics: cg_solver_implicit (inst/include/wrmf_implicit.hpp:8-32), cg_solver_explicit
+// (inst/include/wrmf_explicit.hpp:8-31) and the surrounding column loop (wrmf_implicit.hpp:175-282,
+// wrmf_explicit.hpp:71-146).  What is different from the reference's shape:
+//   * one CTA of 4 warps owns a row; warp w holds gathered rows j = w, w+4, ... (<= 20 of them), lane l
+//     holds features 4l..4l+3 of each as one float4 => the 40 KB tile X_nnz is read from HBM exactly
+//     once per row and then lives in 80 registers/thread for all 2(s+1) mat-vecs;
+//   * the two mat-vecs of a CG step are fused into one sweep over the registers:
+//       u_j = x_j . p   (4 FMA/lane + one transposing halving reduction per warp: 21 SHFL for 20 rows)
+//       w_j = (c_j - 1) u_j ;  acc += w_j x_j   (80 FMA/lane), then a 4-way cross-warp sum in smem;
+//   * the NEXT row's tile (and its warm-start y) is prefetched while this row computes: warp 0 issues
+//     one 512-byte cp.async.bulk (TMA engine, SASS UBLKCP) per gathered row into a 40.5 KB shared
+//     memory slot, completion by mbarrier complete_tx; the CSR indices for the row after that are
+//     software-pipelined through registers => no thread ever waits on a dependent HBM load chain;
+//   * XtX p: either the session has rotated both factor matrices into the eigenbasis of XtX (kDiag:
+//     XtX p = d (.) p, 4 FMA/lane -- see eig.cuh), or (kFullG) each warp multiplies a 32-column slab
+//     of XtX from L1/L2 and the slabs are summed by the same cross-warp reduction;
+//   * the loss term X_nnz' y is obtained from the u vectors already computed
+//     (X_nnz' y = X_nnz' x0 + sum_k alpha_k X_nnz' p_k) instead of a fifth sweep;
+//   * alpha = rsold / p'Ap and beta are formed by fp32 division (the reference divides in double and
+//     rounds to T, wrmf_implicit.hpp:18,23,28); rounding-level difference, covered by the fp32 tolerance.
+// Algorithmic HBM bytes per row: 4nk + 8n + 4 + 4k + 4k  (42,628 B at n = 80, k = 128).
+#pragma once
+#include "common.cuh"
+
+namespace b200als {
+
+constexpr int kResK = 128;       // rank handled by this kernel
+constexpr int kResWarps = 4;
+constexpr int kResThreads = kResWarps * 32;
+constexpr int kResIPW = 20;      // gathered rows per warp
+constexpr int kResMaxN = kResWarps * kResIPW;  // 80
+constexpr int kResRowBytes = kResK * 4;        // 512
+
+struct ResidentParams {
+  const int32_t* ptr;
+  const int32_t* idx;
+  const float* val;
+  const float* X;      // 128 x n_src
+  float* Y;            // 128 x n_targets
+  const float* diag;   // [128]  eigenvalues of XtX (+lambda)          (kDiag)
+  const float* G;      // 128 x 128 XtX + lambda I                      (kFullG)
+  int feedback;
+  int cg_steps;
+  int dynamic_lambda;
+  float lambda;
+  const int32_t* row_list;  // rows with 1 <= nnz <= kResMaxN (nullptr: all rows 0..n_list-1 qualify)
+  int n_list;
+  double* loss_partials;    // [gridDim.x]
+};
+
+struct __align__(128) ResidentSmem {
+  float tile[(kResMaxN + 1) * kResK];      // gathered rows + the warm-start y in row kResMaxN
+  float vbuf[2][kResWarps][kResK];         // cross-warp partial sums (double buffered per sweep)
+  float wbuf[kResWarps][32];               // per-warp w_j broadcast
+  int meta_idx[2][kResMaxN];               // CSR indices of the row after next / next
+  float meta_val[2][kResMaxN];
+  int meta_n[2];
+  uint64_t bar;                            // mbarrier for the tile slot
+  double red[32];
+};
+
+// Transposing halving reduction: on entry lane L holds t[0..N) partial dot products, on exit the lane
+// whose bits select slot q holds the full 32-lane sum of t[q]; returns it (0 for padding lanes).
+template <int N>
+struct Halver {
+  template <int M>
+  static __device__ __forceinline__ float run(float (&t)[N], int lane) {
+    constexpr int H = (N + 1) / 2;
+    const bool upper = (lane & M) != 0;
+    float o[H];
+#pragma unroll
+    for (int v = 0; v < H; v++) {
+      const float lo = t[v];
+      const float hi = (v + H < N) ? t[v + H] : 0.0f;
+      const float send = upper ? lo : hi;
+      const float keep = upper ? hi : lo;
+      o[v] = keep + __shfl_xor_sync(kFull, send, M);
+    }
+    if constexpr (M == 1) {
+      return o[0];
+    } else {
+      return Halver<H>::template run<M / 2>(o, lane);
+    }
+  }
+};
+// slot owned by a lane after Halver<20>::run<16>: 20 -> 10 -> 5 -> 3 -> 2 -> 1
+__device__ __forceinline__ int resident_owner_slot(int lane) {
+  const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1, b0 = lane & 1;
+  const int in3 = 2 * b1 + b0;          // index within the group of 3 (valid < 3)
+  const int in5 = 3 * b2 + in3;         // index within the group of 5 (valid < 5)
+  if (in3 >= 3 || in5 >= 5) return -1;
+  return 10 * b4 + 5 * b3 + in5;
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+
+// mode: 0 r0-implicit  w = c - (c-1)u ; 1 Ap-implicit  w = (c-1)u ; 2 r0-explicit  w = c - u ; 3 Ap-explicit  w = u
+template <bool kFullG>
+__device__ __forceinline__ float4 resident_sweep(const float4 (&xt)[kResIPW], const float4& vec, float cq, int mode,
+                                                 int slot, ResidentSmem& S, int sweep, const float* __restrict__ G,
+                                                 float& u_own) {
+  const int lane = lane_id(), w = warp_id();
+  float t[kResIPW];
+#pragma unroll
+  for (int q = 0; q < kResIPW; q++) t[q] = dot4(xt[q], vec);
+  const float u = Halver<kResIPW>::template run<16>(t, lane);
+  u_own = u;
+  float wq;
+  switch (mode) {
+    case 0: wq = cq - (cq - 1.0f) * u; break;
+    case 1: wq = (cq - 1.0f) * u; break;
+    case 2: wq = cq - u; break;
+    default: wq = u; break;
+  }
+  if (slot >= 0) S.wbuf[w][slot] = wq;
+  __syncwarp();
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int q4 = 0; q4 < kResIPW / 4; q4++) {
+    const float4 wv = *reinterpret_cast<const float4*>(&S.wbuf[w][q4 * 4]);
+    const float ws[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float4& x = xt[q4 * 4 + i];
+      acc.x = fmaf(ws[i], x.x, acc.x);
+      acc.y = fmaf(ws[i], x.y, acc.y);
+      acc.z = fmaf(ws[i], x.z, acc.z);
+      acc.w = fmaf(ws[i], x.w, acc.w);
+    }
+  }
+  __syncwarp();
+  if constexpr (kFullG) {
+    // (mode 0/1 only) this warp's slab of XtX * vec: columns j in [32w, 32w+32); vec_j lives in lane j/4 of
+    // every warp (component j%4).  The slabs are summed with the tile partials below.
+    if (mode <= 1) {
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+      for (int g4 = 0; g4 < 8; g4++) {
+        const int src = w * 8 + g4;  // lane holding vec[4*src .. 4*src+3]
+        const float vj[4] = {__shfl_sync(kFull, vec.x, src), __shfl_sync(kFull, vec.y, src),
+                             __shfl_sync(kFull, vec.z, src), __shfl_sync(kFull, vec.w, src)};
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const float4 gr = ldg_f4(G + (size_t)(src * 4 + c) * kResK + lane * 4);
+          g.x = fmaf(gr.x, vj[c], g.x);
+          g.y = fmaf(gr.y, vj[c], g.y);
+          g.z = fmaf(gr.z, vj[c], g.z);
+          g.w = fmaf(gr.w, vj[c], g.w);
+        }
+      }
+      // r0: acc - G x ; Ap: acc + G p
+      const float sgn = (mode == 0) ? -1.0f : 1.0f;
+      acc.x = fmaf(sgn, g.x, acc.x);
+      acc.y = fmaf(sgn, g.y, acc.y);
+      acc.z = fmaf(sgn, g.z, acc.z);
+      acc.w = fmaf(sgn, g.w, acc.w);
+    }
+  }
+  float* vb = &S.vbuf[sweep & 1][0][0];
+  *reinterpret_cast<float4*>(vb + w * kResK + lane * 4) = acc;
+  __syncthreads();
+  float4 v = *reinterpret_cast<const float4*>(vb + lane * 4);
+#pragma unroll
+  for (int ww = 1; ww < kResWarps; ww++) {
+    const float4 o = *reinterpret_cast<const float4*>(vb + ww * kResK + lane * 4);
+    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+  }
+  return v;
+}
+
+template <bool kFullG>
+__global__ void __launch_bounds__(kResThreads, 3) als_cg_resident_kernel(ResidentParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ResidentSmem& S = *reinterpret_cast<ResidentSmem*>(smem_raw);
+  const int lane = lane_id(), w = warp_id(), tid = threadIdx.x;
+  const bool implicit = (P.feedback == 0);
+  const int stride = gridDim.x;
+  const int slot = resident_owner_slot(lane);
+
+  auto valid = [&](int i) -> bool { return (long long)blockIdx.x + (long long)i * stride < (long long)P.n_list; };
+  auto row_of = [&](int i) -> int {  // i-th row of this CTA (caller checks valid(i))
+    const long long t = (long long)blockIdx.x + (long long)i * stride;
+    return P.row_list ? __ldg(P.row_list + t) : (int)t;
+  };
+  // warp 0: issue the bulk copies of row `r` whose indices sit in meta buffer b
+  auto issue_tile = [&](int r, int b) {
+    const int n = S.meta_n[b];
+    if (lane == 0) mbar_expect_tx(&S.bar, (uint32_t)(n + 1) * kResRowBytes);
+    __syncwarp();
+    for (int j = lane; j < n; j += 32)
+      bulk_g2s(&S.tile[j * kResK], P.X + (size_t)S.meta_idx[b][j] * kResK, kResRowBytes, &S.bar);
+    if (lane == 0) bulk_g2s(&S.tile[kResMaxN * kResK], P.Y + (size_t)r * kResK, kResRowBytes, &S.bar);
+  };
+  // warp 0: blocking fetch of the CSR slice of row r into meta buffer b (prologue only)
+  auto fetch_meta_blocking = [&](int r, int b) {
+    const int p1 = P.ptr[r], n = P.ptr[r + 1] - p1;
+    for (int j = lane; j < n; j += 32) {
+      S.meta_idx[b][j] = __ldg(P.idx + p1 + j);
+      S.meta_val[b][j] = __ldg(P.val + p1 + j);
+    }
+    if (lane == 0) S.meta_n[b] = n;
+  };
+
+  if (tid == 0) {
+    mbar_init(&S.bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  // ---- prologue (warp 0): row 0 tile in flight, row 1 indices in smem, row 2 CSR range and row 3 id in
+  //      registers.  From then on every global load warp 0 issues is consumed one row later. -------------
+  int rid0 = -1, rid1 = -1, rid2 = -1, rid3 = -1;  // warp 0: ids of rows i .. i+3
+  int pf_p1 = 0, pf_n = 0;                          // warp 0: CSR range of row i+2
+  if (w == 0) {
+    if (valid(0)) {
+      rid0 = row_of(0);
+      fetch_meta_blocking(rid0, 0);
+      __syncwarp();
+      issue_tile(rid0, 0);
+    }
+    if (valid(1)) { rid1 = row_of(1); fetch_meta_blocking(rid1, 1); }
+    if (valid(2)) { rid2 = row_of(2); pf_p1 = P.ptr[rid2]; pf_n = P.ptr[rid2 + 1] - pf_p1; }
+    if (valid(3)) rid3 = row_of(3);
+  }
+  __syncthreads();
+
+  float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!kFullG && implicit) dg = ldg_f4(P.diag + lane * 4);
+  double warp_loss = 0.0;
+  int sweep = 0;
+
+  for (int i = 0; valid(i); i++) {
+    const int b = i & 1;
+    const int n = S.meta_n[b];
+    // ---- tile -> registers ------------------------------------------------------------------------
+    mbar_wait(&S.bar, (uint32_t)(i & 1));
+    float4 xt[kResIPW];
+#pragma unroll
+    for (int q = 0; q < kResIPW; q++) {
+      const int j = w + kResWarps * q;
+      xt[q] = (j < n) ? *reinterpret_cast<const float4*>(&S.tile[j * kResK + lane * 4]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4 x = *reinterpret_cast<const float4*>(&S.tile[kResMaxN * kResK + lane * 4]);
+    float cq = 0.0f;
+    if (slot >= 0) {
+      const int j = w + kResWarps * slot;
+      if (j < n) cq = S.meta_val[b][j];
+    }
+    __syncthreads();  // slot and meta[b] are free from here on
+    // ---- producer duties (warp 0; nothing here waits on memory) -------------------------------------
+    int pf_idx[3] = {0, 0, 0};
+    float pf_val[3] = {0.f, 0.f, 0.f};
+    int nx_p1 = 0, nx_p2 = 0, rid4 = -1;
+    if (w == 0) {
+      if (valid(i + 1)) issue_tile(rid1, b ^ 1);
+      if (valid(i + 2)) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const int j = lane + 32 * c;
+          if (j < pf_n) {
+            pf_idx[c] = __ldg(P.idx + pf_p1 + j);
+            pf_val[c] = __ldg(P.val + pf_p1 + j);
+          }
+        }
+      }
+      if (valid(i + 3)) { nx_p1 = __ldg(P.ptr + rid3); nx_p2 = __ldg(P.ptr + rid3 + 1); }
+      if (valid(i + 4)) rid4 = row_of(i + 4);
+    }
+    // ---- CG -------------------------------------------------------------------------------------
+    const float lam_use = implicit ? P.lambda : (P.lambda * (P.dynamic_lambda ? (float)n : 1.0f));
+    float u_own;
+    float4 v = resident_sweep<kFullG>(xt, x, cq, implicit ? 0 : 2, slot, S, sweep++, P.G, u_own);
+    float uy = u_own;  // running X_nnz' y for the loss
+    float4 r;
+    if (implicit) {
+      if (kFullG) r = v;
+      else r = make_float4(fmaf(-dg.x, x.x, v.x), fmaf(-dg.y, x.y, v.y), fmaf(-dg.z, x.z, v.z), fmaf(-dg.w, x.w, v.w));
+    } else {
+      r = make_float4(fmaf(-lam_use, x.x, v.x), fmaf(-lam_use, x.y, v.y), fmaf(-lam_use, x.z, v.z), fmaf(-lam_use, x.w, v.w));
+    }
+    float4 p = r;
+    float rsold = warp_sum(dot4(r, r));
+    for (int it = 0; it < P.cg_steps; it++) {
+      v = resident_sweep<kFullG>(xt, p, cq, implicit ? 1 : 3, slot, S, sweep++, P.G, u_own);
+      float4 Ap;
+      if (implicit) {
+        if (kFullG) Ap = v;
+        else Ap = make_float4(fmaf(dg.x, p.x, v.x), fmaf(dg.y, p.y, v.y), fmaf(dg.z, p.z, v.z), fmaf(dg.w, p.w, v.w));
+      } else {
+        Ap = make_float4(fmaf(lam_use, p.x, v.x), fmaf(lam_use, p.y, v.y), fmaf(lam_use, p.z, v.z), fmaf(lam_use, p.w, v.w));
+      }
+      const float pAp = warp_sum(dot4(p, Ap));
+      const float a = __fdiv_rn(rsold, pAp);
+      x.x = fmaf(a, p.x, x.x); x.y = fmaf(a, p.y, x.y); x.z = fmaf(a, p.z, x.z); x.w = fmaf(a, p.w, x.w);
+      r.x = fmaf(-a, Ap.x, r.x); r.y = fmaf(-a, Ap.y, r.y); r.z = fmaf(-a, Ap.z, r.z); r.w = fmaf(-a, Ap.w, r.w);
+      uy = fmaf(a, u_own, uy);
+      const float rsnew = warp_sum(dot4(r, r));
+      if (rsnew < (float)B200ALS_CG_TOL) break;
+      const float bt = __fdiv_rn(rsnew, rsold);
+      p.x = fmaf(p.x, bt, r.x); p.y = fmaf(p.y, bt, r.y); p.z = fmaf(p.z, bt, r.z); p.w = fmaf(p.w, bt, r.w);
+      rsold = rsnew;
+    }
+    if (w == 0) *reinterpret_cast<float4*>(P.Y + (size_t)rid0 * kResK + lane * 4) = x;
+    // ---- loss ------------------------------------------------------------------------------------
+    {
+      float l = 0.0f;
+      if (slot >= 0 && (w + kResWarps * slot) < n) {
+        const float d = implicit ? (1.0f - uy) : (cq - uy);
+        l = implicit ? d * d * cq : d * d;
+      }
+      l = warp_sum(l);
+      if (w == 0) l = fmaf(lam_use, warp_sum(dot4(x, x)), l);
+      warp_loss += (double)l;
+    }
+    // ---- retire the software pipeline stage: indices of row i+2 -> meta[b] -------------------------------
+    if (w == 0) {
+      if (valid(i + 2)) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const int j = lane + 32 * c;
+          if (j < pf_n) { S.meta_idx[b][j] = pf_idx[c]; S.meta_val[b][j] = pf_val[c]; }
+        }
+        if (lane == 0) S.meta_n[b] = pf_n;
+      }
+      pf_p1 = nx_p1;
+      pf_n = nx_p2 - nx_p1;
+      rid0 = rid1; rid1 = rid2; rid2 = rid3; rid3 = rid4;
+    }
+    __syncthreads();  // meta[b] visible to all before it is read as "row i+2"
+  }
+  const double tot = block_sum_double((lane == 0) ? warp_loss : 0.0, S.red);
+  if (tid == 0) P.loss_partials[blockIdx.x] = tot;
+}
+
+}  // namespace b200als

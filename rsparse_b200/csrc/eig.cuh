@@ -1,0 +1,184 @@
+// eig.cuh -- change of basis that turns the k x k product XtX * p of the implicit-feedback CG
+// (reference: inst/include/wrmf_implicit.hpp:16,22 -- `XtX * x`, `XtX * p`, 2k^2 flop per CG step and
+// 44 % of the arithmetic at k = 128) into a 4-FMA diagonal scale.
+//
+// XtX = Q diag(d) Q' (symmetric eigendecomposition).  With X~ = X Q and y~ = Q' y the per-row system
+//   (XtX + X_nnz D X_nnz') y = X_nnz c      becomes      (diag(d) + X~_nnz D X~_nnz') y~ = X~_nnz c
+// and every CG iterate of the rotated system is Q' times the iterate of the original one (r~ = Q' r,
+// p~ = Q' p; alpha, beta, the rsnew < CG_TOL test and the loss are rotation invariant), so the solver
+// can run entirely in the rotated coordinates.  The engine therefore keeps both factor matrices in a
+// common orthonormal basis B (true = stored * B'), re-diagonalises once per implicit CG half-iteration
+// and rotates back only when factors leave the device.
+//
+//   jacobi_eig_kernel   one CTA, parallel cyclic two-sided Jacobi in fp64 on the k x k Gram (k <= 256)
+//   rotate_rows_kernel  Z = X * R for n x 128 row blocks (fp32 FMA, R in shared memory), in place
+#pragma once
+#include "common.cuh"
+
+namespace b200als {
+
+constexpr int kJacobiThreads = 1024;
+
+// A: k x k symmetric (row-major, overwritten: ends diagonal), Vt: k x k, row e = eigenvector e.
+// Outputs: Qf[f*k + e] = V[f][e] (fp32), df[e] = eigenvalue (fp32), Q64 likewise in double.
+__global__ void __launch_bounds__(kJacobiThreads) jacobi_eig_kernel(double* __restrict__ A, double* __restrict__ Vt,
+                                                                    int k, float* __restrict__ Qf,
+                                                                    float* __restrict__ df, double* __restrict__ Q64,
+                                                                    int max_sweeps) {
+  __shared__ double s_c[128], s_s[128];
+  __shared__ int s_p[128], s_q[128];
+  __shared__ double s_red[32];
+  __shared__ double s_off, s_diag;
+  const int tid = threadIdx.x;
+  const int np = (k + 1) / 2;       // pairs per step
+  const int npad = 2 * np;          // even number of players
+  for (int e = tid; e < k * k; e += kJacobiThreads) Vt[e] = ((e / k) == (e % k)) ? 1.0 : 0.0;
+  __syncthreads();
+  for (int sweep = 0; sweep < max_sweeps; sweep++) {
+    // convergence: off(A)^2 <= 1e-30 * diag(A)^2
+    double off = 0.0, dg = 0.0;
+    for (int e = tid; e < k * k; e += kJacobiThreads) {
+      const double v = A[e];
+      if ((e / k) == (e % k)) dg += v * v; else off += v * v;
+    }
+    const double toff = block_sum_double(off, s_red);
+    const double tdg = block_sum_double(dg, s_red);
+    if (tid == 0) { s_off = toff; s_diag = tdg; }
+    __syncthreads();
+    if (s_off <= 1e-30 * s_diag) break;
+    for (int step = 0; step < npad - 1; step++) {
+      // rotation parameters for the np disjoint pairs of this step (round-robin tournament)
+      if (tid < np) {
+        int p, q;
+        if (tid == 0) { p = npad - 1; q = step; }
+        else { p = (step + tid) % (npad - 1); q = (step - tid + (npad - 1)) % (npad - 1); }
+        if (p > q) { const int t = p; p = q; q = t; }
+        double c = 1.0, s = 0.0;
+        if (q < k) {
+          const double apq = A[p * k + q];
+          if (apq != 0.0) {
+            const double tau = (A[q * k + q] - A[p * k + p]) / (2.0 * apq);
+            const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+            c = 1.0 / sqrt(1.0 + t * t);
+            s = t * c;
+          }
+        } else {
+          q = -1;  // padding player
+        }
+        s_p[tid] = p; s_q[tid] = q; s_c[tid] = c; s_s[tid] = s;
+      }
+      __syncthreads();
+      // A <- A J  (columns p, q of every row)
+      for (int item = tid; item < np * k; item += kJacobiThreads) {
+        const int pr = item / k, i = item - pr * k;
+        const int p = s_p[pr], q = s_q[pr];
+        if (q < 0) continue;
+        const double c = s_c[pr], s = s_s[pr];
+        const double ap = A[i * k + p], aq = A[i * k + q];
+        A[i * k + p] = c * ap - s * aq;
+        A[i * k + q] = s * ap + c * aq;
+      }
+      __syncthreads();
+      // A <- J' A (rows p, q) ;  Vt <- J' Vt  (i.e. V <- V J)
+      for (int item = tid; item < np * k; item += kJacobiThreads) {
+        const int pr = item / k, j = item - pr * k;
+        const int p = s_p[pr], q = s_q[pr];
+        if (q < 0) continue;
+        const double c = s_c[pr], s = s_s[pr];
+        const double ap = A[p * k + j], aq = A[q * k + j];
+        A[p * k + j] = c * ap - s * aq;
+        A[q * k + j] = s * ap + c * aq;
+        const double vp = Vt[p * k + j], vq = Vt[q * k + j];
+        Vt[p * k + j] = c * vp - s * vq;
+        Vt[q * k + j] = s * vp + c * vq;
+      }
+      __syncthreads();
+    }
+  }
+  for (int e = tid; e < k * k; e += kJacobiThreads) {
+    const int f = e / k, ev = e % k;
+    const double v = Vt[ev * k + f];
+    Qf[e] = (float)v;
+    if (Q64) Q64[e] = v;
+  }
+  for (int e = tid; e < k; e += kJacobiThreads) df[e] = (float)A[e * k + e];
+}
+
+// C = A * B (k x k, row-major, double) -- basis bookkeeping B <- B Q ; trivially small.
+__global__ void matmul_kk_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, int k) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= k * k) return;
+  const int i = e / k, j = e % k;
+  double s = 0.0;
+  for (int l = 0; l < k; l++) s += A[i * k + l] * B[l * k + j];
+  C[e] = s;
+}
+// out(fp32)[i][j] = transpose ? in[j][i] : in[i][j]
+__global__ void convert_kk_kernel(const double* __restrict__ in, float* __restrict__ out, int k, int transpose) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= k * k) return;
+  const int i = e / k, j = e % k;
+  out[e] = (float)(transpose ? in[j * k + i] : in[e]);
+}
+__global__ void set_identity_kernel(double* __restrict__ B, int k) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= k * k) return;
+  B[e] = ((e / k) == (e % k)) ? 1.0 : 0.0;
+}
+
+// Z[r][e] = sum_f X[r][f] R[f][e] for rows [0, n), k = 128, in place allowed (Z == X): each CTA stages its
+// 64-row block in shared memory before writing.  256 threads, thread tile 4 rows x 8 columns.
+constexpr int kRotK = 128;
+constexpr int kRotRows = 64;
+struct RotSmem {
+  float R[kRotK][kRotK];      // 64 KB
+  float Xs[kRotRows][kRotK + 4];  // padded: conflict-free column-broadcast reads
+};
+__global__ void __launch_bounds__(256) rotate_rows_kernel(const float* __restrict__ X, float* __restrict__ Z,
+                                                          const float* __restrict__ R, long long n) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RotSmem& S = *reinterpret_cast<RotSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  for (int t = tid; t < kRotK * kRotK / 4; t += 256)
+    reinterpret_cast<float4*>(&S.R[0][0])[t] = __ldg(reinterpret_cast<const float4*>(R) + t);
+  const int tx = tid & 15, ty = tid >> 4;  // columns {4tx..4tx+3} u {64+4tx..}, rows ty*4 .. ty*4+3
+  const long long n_blocks = (n + kRotRows - 1) / kRotRows;
+  for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+    const long long r0 = blk * kRotRows;
+    __syncthreads();
+    for (int t = tid; t < kRotRows * (kRotK / 4); t += 256) {
+      const int rr = t / (kRotK / 4), c4 = t % (kRotK / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + rr < n) v = __ldg(reinterpret_cast<const float4*>(X + (size_t)(r0 + rr) * kRotK) + c4);
+      *reinterpret_cast<float4*>(&S.Xs[rr][c4 * 4]) = v;
+    }
+    __syncthreads();
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+#pragma unroll 4
+    for (int f = 0; f < kRotK; f++) {
+      const float4 b0 = *reinterpret_cast<const float4*>(&S.R[f][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&S.R[f][64 + tx * 4]);
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const float a = S.Xs[ty * 4 + i][f];
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = fmaf(a, bv[j], acc[i][j]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const long long r = r0 + ty * 4 + i;
+      if (r < n) {
+        *reinterpret_cast<float4*>(Z + (size_t)r * kRotK + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        *reinterpret_cast<float4*>(Z + (size_t)r * kRotK + 64 + tx * 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+      }
+    }
+  }
+}
+
+}  // namespace b200als

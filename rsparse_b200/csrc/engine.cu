@@ -1,0 +1,1012 @@
+// engine.cu -- host side of libb200als.so: the C ABI of include/b200als.h, device memory, kernel
+// selection and the ALS outer loop.  Reference counterparts (relative to /root/reference):
+//   stateless calls   src/wrmf_implicit.cpp:5-31, src/wrmf_explicit.cpp:5-27 (+ src/RcppExports.cpp:329-416)
+//   XtX               R/model_WRMF.R:474-486
+//   session / fit     R/model_WRMF.R:173-360 (outer loop :318-338, final transform_ :412-452)
+// No CPU fallback anywhere: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/b200als.h"
+#include "als_generic.cuh"
+#include "als_resident.cuh"
+#include "eig.cuh"
+#include "gram.cuh"
+
+using namespace b200als;
+
+// ------------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(B200ALS_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__) + " @" +      \
+                                     __FILE__ + ":" + std::to_string(__LINE__));                   \
+  } while (0)
+#define NC(expr)                                                                                   \
+  do {                                                                                             \
+    ncclResult_t e__ = (expr);                                                                     \
+    if (e__ != ncclSuccess)                                                                        \
+      return fail(B200ALS_ENCCL, std::string(#expr) + ": " + ncclGetErrorString(e__) + " @" +      \
+                                     __FILE__ + ":" + std::to_string(__LINE__));                   \
+  } while (0)
+#define TRY(expr)                \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != B200ALS_OK) return rc__; \
+  } while (0)
+
+extern "C" const char* b200als_last_error(void) { return g_err.c_str(); }
+extern "C" int b200als_version(void) { return B200ALS_VERSION; }
+extern "C" int b200als_device_count(int* count) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (count) *count = (e == cudaSuccess) ? n : 0;
+  if (e != cudaSuccess || n == 0) return fail(B200ALS_ECUDA, "no CUDA device visible (this engine has no CPU fallback)");
+  return B200ALS_OK;
+}
+extern "C" int b200als_set_device(int device) {
+  CU(cudaSetDevice(device));
+  return B200ALS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  cudaError_t ensure(size_t n) {
+    if (n <= bytes) return cudaSuccess;
+    release();
+    cudaError_t e = cudaMalloc(&p, n ? n : 1);
+    if (e == cudaSuccess) bytes = n;
+    return e;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+  int32_t* i32() const { return reinterpret_cast<int32_t*>(p); }
+  float* f32() const { return reinterpret_cast<float*>(p); }
+  double* f64() const { return reinterpret_cast<double*>(p); }
+  unsigned long long* u64() const { return reinterpret_cast<unsigned long long*>(p); }
+};
+
+template <typename TI, typename TO>
+__global__ void convert_kernel(const TI* __restrict__ in, TO* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (TO)in[i];
+}
+__global__ void sum_partials_kernel(const double* __restrict__ partials, int n, double* __restrict__ out, int accumulate) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n; i++) s += partials[i];
+    out[0] = accumulate ? out[0] + s : s;
+  }
+}
+// regulariser: sum_j w_j ||x_j||^2 (w_j = cnt_X[j] or 1), per-block partials in double
+template <typename T>
+__global__ void __launch_bounds__(256) sqnorm_kernel(const T* __restrict__ X, int k, long long n, const T* __restrict__ cnt,
+                                                     double* __restrict__ partials) {
+  __shared__ double s_red[32];
+  double acc = 0.0;
+  const long long total = n * (long long)k;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const double v = (double)X[e];
+    const double w = cnt ? (double)cnt[e / k] : 1.0;
+    acc += v * v * w;
+  }
+  const double tot = block_sum_double(acc, s_red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = tot;
+}
+// rows by length class: 0 -> empty (Y row zeroed here), 1..max_short -> short list, else long list
+__global__ void classify_rows_kernel(const int32_t* __restrict__ ptr, int n_rows, int max_short, int32_t* __restrict__ short_list,
+                                     int32_t* __restrict__ long_list, int* __restrict__ counts /* [3]: short, long, empty */) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const int n = ptr[r + 1] - ptr[r];
+  if (n <= 0) atomicAdd(&counts[2], 1);
+  else if (n <= max_short) short_list[atomicAdd(&counts[0], 1)] = r;
+  else long_list[atomicAdd(&counts[1], 1)] = r;
+}
+template <typename T>
+__global__ void zero_empty_rows_kernel(const int32_t* __restrict__ ptr, int n_rows, int k, T* __restrict__ Y) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)n_rows * k) return;
+  const int r = (int)(e / k);
+  if (ptr[r + 1] - ptr[r] <= 0) Y[e] = T(0);
+}
+
+// synthetic CSR: row r draws exactly nnz_per_row distinct ascending ids -- one per
+// equal-width stratum of [0, n_cols) -- from a counter-based hash; values 1 + floor(10 u^2) (implicit
+// confidences) or 1..5 (explicit ratings).
+__host__ __device__ inline uint64_t synth_hash(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__host__ __device__ inline void synth_entry(int64_t row, int j, int32_t n_cols, int32_t nnz_per_row, uint64_t seed,
+                                            int explicit_values, int32_t* col, float* val) {
+  const uint64_t h = synth_hash(seed * 0x100000001B3ull + (uint64_t)row * (uint64_t)nnz_per_row + (uint64_t)j);
+  const int64_t lo = ((int64_t)j * n_cols) / nnz_per_row, hi = ((int64_t)(j + 1) * n_cols) / nnz_per_row;
+  *col = (int32_t)(lo + (int64_t)(h % (uint64_t)(hi - lo)));
+  const float u = (float)((h >> 40) & 0xFFFFFF) / 16777216.0f;
+  *val = explicit_values ? (1.0f + floorf(u * 5.0f)) : (1.0f + floorf(10.0f * u * u));
+}
+__global__ void synth_csr_kernel(int32_t n_rows, int32_t n_cols, int32_t nnz_per_row, uint64_t seed, int explicit_values,
+                                 int64_t row_offset, int32_t* __restrict__ ptr, int32_t* __restrict__ idx,
+                                 float* __restrict__ val) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)n_rows * nnz_per_row;
+  if (e <= n_rows) ptr[e] = (int32_t)(e * nnz_per_row);
+  if (e >= total) return;
+  const int64_t r = e / nnz_per_row;
+  const int j = (int)(e - r * nnz_per_row);
+  synth_entry(r + row_offset, j, n_cols, nnz_per_row, seed, explicit_values, &idx[e], &val[e]);
+}
+// factor init: N(0,1)/100 from a counter-based Box-Muller (R/model_WRMF.R:203-215, src/utils.cpp:131-143)
+__global__ void init_normal_kernel(float* __restrict__ out, long long n, uint64_t seed, float scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t h1 = synth_hash(seed ^ (uint64_t)(2 * i)), h2 = synth_hash(seed ^ (uint64_t)(2 * i + 1));
+  const float u1 = ((float)((h1 >> 40) & 0xFFFFFF) + 1.0f) / 16777217.0f;
+  const float u2 = (float)((h2 >> 40) & 0xFFFFFF) / 16777216.0f;
+  out[i] = scale * sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// device context shared by the stateless calls and sessions
+// ------------------------------------------------------------------------------------------------------
+struct Ctx {
+  int device = -1;
+  int sm_count = 148;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  DevBuf ticket, loss_partials, loss_acc, status, gram_partials, reg_partials;
+  bool attrs_set = false;
+  int init() {
+    if (stream) return B200ALS_OK;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+      return fail(B200ALS_ECUDA, "no CUDA device visible (this engine has no CPU fallback)");
+    CU(cudaGetDevice(&device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    sm_count = prop.multiProcessorCount;
+    smem_optin = prop.sharedMemPerBlockOptin;
+    CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CU(ticket.ensure(sizeof(unsigned long long)));
+    CU(loss_acc.ensure(4 * sizeof(double)));
+    CU(status.ensure(sizeof(int)));
+    return B200ALS_OK;
+  }
+};
+static Ctx& ctx() {
+  static thread_local Ctx c;
+  return c;
+}
+
+template <typename T>
+struct CscDev {
+  int32_t n_rows = 0, n_cols = 0;
+  int64_t nnz = 0;
+  DevBuf ptr, idx, val;
+  // row classes for the resident kernel (built lazily)
+  DevBuf short_list, long_list;
+  int n_short = -1, n_long = 0, n_empty = 0;
+  bool all_short = false;
+};
+
+template <typename T>
+static int upload_csc(const b200als_csc* A, CscDev<T>& D, cudaStream_t st) {
+  if (!A || !A->ptr || (A->nnz > 0 && (!A->idx || (!A->val_f64 && !A->val_f32))))
+    return fail(B200ALS_EINVAL, "b200als_csc: null ptr/idx/val");
+  if (A->n_cols < 0 || A->n_rows < 0 || A->nnz < 0) return fail(B200ALS_EINVAL, "b200als_csc: negative size");
+  D.n_rows = A->n_rows;
+  D.n_cols = A->n_cols;
+  D.nnz = A->nnz;
+  CU(D.ptr.ensure(sizeof(int32_t) * ((size_t)A->n_cols + 1)));
+  CU(D.idx.ensure(sizeof(int32_t) * (size_t)A->nnz));
+  CU(D.val.ensure(sizeof(T) * (size_t)A->nnz));
+  CU(cudaMemcpyAsync(D.ptr.p, A->ptr, sizeof(int32_t) * ((size_t)A->n_cols + 1), cudaMemcpyHostToDevice, st));
+  if (A->nnz) {
+    CU(cudaMemcpyAsync(D.idx.p, A->idx, sizeof(int32_t) * (size_t)A->nnz, cudaMemcpyHostToDevice, st));
+    const bool same_f64 = A->val_f64 && sizeof(T) == 8, same_f32 = !A->val_f64 && sizeof(T) == 4;
+    if (same_f64 || same_f32) {
+      CU(cudaMemcpyAsync(D.val.p, A->val_f64 ? (const void*)A->val_f64 : (const void*)A->val_f32,
+                         sizeof(T) * (size_t)A->nnz, cudaMemcpyHostToDevice, st));
+    } else {
+      // double -> float (or float -> double) once at upload; the reference converts per visit
+      // (wrmf_implicit.hpp:182-183), same rounding
+      DevBuf tmp;
+      const size_t eb = A->val_f64 ? 8 : 4;
+      CU(tmp.ensure(eb * (size_t)A->nnz));
+      CU(cudaMemcpyAsync(tmp.p, A->val_f64 ? (const void*)A->val_f64 : (const void*)A->val_f32, eb * (size_t)A->nnz,
+                         cudaMemcpyHostToDevice, st));
+      const int bs = 256;
+      const unsigned gs = (unsigned)((A->nnz + bs - 1) / bs);
+      if (A->val_f64) convert_kernel<double, T><<<gs, bs, 0, st>>>(tmp.f64(), D.val.template as<T>(), A->nnz);
+      else convert_kernel<float, T><<<gs, bs, 0, st>>>(tmp.f32(), D.val.template as<T>(), A->nnz);
+      CU(cudaGetLastError());
+      CU(cudaStreamSynchronize(st));
+    }
+  }
+  D.n_short = -1;
+  return B200ALS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Gram
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+static int run_gram(Ctx& c, const T* X, int k, long long n, double lambda, T* G, double* G64) {
+  const int nt1 = (k + kGramTile - 1) / kGramTile, n_tiles = nt1 * (nt1 + 1) / 2;
+  long long n_cta = std::min<long long>((long long)c.sm_count * 2 / std::max(1, n_tiles) + 1, (n + 255) / 256);
+  n_cta = std::max<long long>(1, n_cta);
+  long long rows_per = (n + n_cta - 1) / n_cta;
+  rows_per = ((rows_per + kGramRows - 1) / kGramRows) * kGramRows;
+  n_cta = std::max<long long>(1, (n + rows_per - 1) / rows_per);
+  CU(c.gram_partials.ensure(sizeof(double) * (size_t)n_cta * n_tiles * kGramTile * kGramTile));
+  gram_partial_kernel<T><<<dim3((unsigned)n_cta, (unsigned)n_tiles), 256, 0, c.stream>>>(X, k, n, rows_per,
+                                                                                         c.gram_partials.f64(), nt1);
+  CU(cudaGetLastError());
+  gram_reduce_kernel<T><<<(k * k + 255) / 256, 256, 0, c.stream>>>(c.gram_partials.f64(), (int)n_cta, n_tiles, k,
+                                                                   lambda, G, G64);
+  CU(cudaGetLastError());
+  return B200ALS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// half-iteration dispatch
+// ------------------------------------------------------------------------------------------------------
+struct HalfOpts {
+  int feedback, solver, cg_steps, dynamic_lambda, kernel;
+  double lambda;
+};
+
+template <typename T>
+static int classify_rows(Ctx& c, CscDev<T>& A) {
+  if (A.n_short >= 0) return B200ALS_OK;
+  CU(A.short_list.ensure(sizeof(int32_t) * (size_t)std::max(1, A.n_cols)));
+  CU(A.long_list.ensure(sizeof(int32_t) * (size_t)std::max(1, A.n_cols)));
+  DevBuf counts;
+  CU(counts.ensure(3 * sizeof(int)));
+  CU(cudaMemsetAsync(counts.p, 0, 3 * sizeof(int), c.stream));
+  if (A.n_cols > 0) {
+    classify_rows_kernel<<<(A.n_cols + 255) / 256, 256, 0, c.stream>>>(A.ptr.i32(), A.n_cols, kResMaxN,
+                                                                      A.short_list.i32(), A.long_list.i32(),
+                                                                      counts.i32());
+    CU(cudaGetLastError());
+  }
+  int h[3];
+  CU(cudaMemcpyAsync(h, counts.p, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaStreamSynchronize(c.stream));
+  A.n_short = h[0];
+  A.n_long = h[1];
+  A.n_empty = h[2];
+  A.all_short = (h[0] == A.n_cols);
+  return B200ALS_OK;
+}
+
+template <typename T, int KPL>
+static int launch_cg_generic(Ctx& c, const SolveParams<T>& P, int n_work, int* grid_out) {
+  const int grid = (int)std::min<long long>((long long)c.sm_count * 4, std::max(1, (n_work + 7) / 8));
+  als_cg_generic_kernel<T, KPL><<<grid, 256, 0, c.stream>>>(P);
+  CU(cudaGetLastError());
+  *grid_out = grid;
+  return B200ALS_OK;
+}
+
+// Runs one half-iteration on device data.  `diag`/`rotated`: the caller has put X and Y in the eigenbasis of
+// G (implicit CG, rank 128, resident kernel) and passes the eigenvalues.  Accumulates the loss numerator
+// (sum over solved rows) into c.loss_acc[0].
+template <typename T>
+static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const float* diag, int k, const HalfOpts& o) {
+  if (o.solver == B200ALS_NNLS) return fail(B200ALS_EUNSUPPORTED, "solver = nnls is not implemented (SURVEY 8f-4)");
+  if (o.solver != B200ALS_CHOLESKY && o.solver != B200ALS_CONJUGATE_GRADIENT) return fail(B200ALS_EINVAL, "unknown solver code");
+  if (o.feedback == B200ALS_IMPLICIT && !G && !diag) return fail(B200ALS_EINVAL, "implicit feedback needs XtX");
+  CU(cudaMemsetAsync(c.loss_acc.p, 0, sizeof(double), c.stream));
+  CU(cudaMemsetAsync(c.status.p, 0, sizeof(int), c.stream));
+  if (A.n_cols == 0) return B200ALS_OK;
+  SolveParams<T> P;
+  P.ptr = A.ptr.i32();
+  P.idx = A.idx.i32();
+  P.val = A.val.template as<T>();
+  P.X = X;
+  P.Y = Y;
+  P.G = (o.feedback == B200ALS_IMPLICIT) ? G : nullptr;
+  P.k = k;
+  P.n_targets = A.n_cols;
+  P.feedback = o.feedback;
+  P.cg_steps = o.cg_steps;
+  P.dynamic_lambda = o.dynamic_lambda;
+  P.lambda = o.lambda;
+  P.row_list = nullptr;
+  P.n_list = 0;
+  P.ticket = c.ticket.u64();
+  P.status = c.status.i32();
+  const int max_grid = c.sm_count * 8;
+  CU(c.loss_partials.ensure(sizeof(double) * (size_t)max_grid));
+  P.loss_partials = c.loss_partials.f64();
+
+  auto run_generic_cg = [&](const int32_t* list, int n_list) -> int {
+    P.row_list = list;
+    P.n_list = n_list;
+    const int n_work = list ? n_list : A.n_cols;
+    if (n_work == 0) return B200ALS_OK;
+    CU(cudaMemsetAsync(c.ticket.p, 0, sizeof(unsigned long long), c.stream));
+    int grid = 0;
+    if (k <= 32) TRY((launch_cg_generic<T, 1>(c, P, n_work, &grid)));
+    else if (k <= 64) TRY((launch_cg_generic<T, 2>(c, P, n_work, &grid)));
+    else if (k <= 128) TRY((launch_cg_generic<T, 4>(c, P, n_work, &grid)));
+    else if (k <= 256) TRY((launch_cg_generic<T, 8>(c, P, n_work, &grid)));
+    else return fail(B200ALS_EUNSUPPORTED, "rank > 256 is not supported");
+    sum_partials_kernel<<<1, 32, 0, c.stream>>>(P.loss_partials, grid, c.loss_acc.f64(), 1);
+    CU(cudaGetLastError());
+    return B200ALS_OK;
+  };
+
+  if (o.solver == B200ALS_CHOLESKY) {
+    const size_t smem = chol_generic_smem_bytes<T>(k);
+    if (smem > c.smem_optin)
+      return fail(B200ALS_EUNSUPPORTED, "cholesky: rank too large for the shared-memory factorisation (needs " +
+                                           std::to_string(smem) + " B)");
+    CU(cudaFuncSetAttribute(als_chol_generic_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (smem + 1024)));
+    const int grid = std::min(c.sm_count * per_sm, std::max(1, A.n_cols));
+    CU(cudaMemsetAsync(c.ticket.p, 0, sizeof(unsigned long long), c.stream));
+    als_chol_generic_kernel<T><<<grid, 256, smem, c.stream>>>(P);
+    CU(cudaGetLastError());
+    sum_partials_kernel<<<1, 32, 0, c.stream>>>(P.loss_partials, grid, c.loss_acc.f64(), 1);
+    CU(cudaGetLastError());
+    return B200ALS_OK;
+  }
+
+  // ---- conjugate gradient ----
+  bool resident = false;
+  if constexpr (sizeof(T) == 4) {
+    resident = (k == kResK) && (o.kernel != 1) && (o.feedback == B200ALS_EXPLICIT || G || diag);
+    if (o.kernel == 2 && !resident) return fail(B200ALS_EUNSUPPORTED, "resident kernel requires rank 128 fp32");
+  }
+  if (!resident) {
+    if (diag && !G) return fail(B200ALS_EINVAL, "generic CG needs the full XtX");
+    return run_generic_cg(nullptr, 0);
+  }
+  if constexpr (sizeof(T) == 4) {
+    TRY(classify_rows(c, A));
+    zero_empty_rows_kernel<T><<<(unsigned)(((long long)A.n_cols * k + 255) / 256), 256, 0, c.stream>>>(P.ptr, A.n_cols, k, Y);
+    CU(cudaGetLastError());
+    if (A.n_short > 0) {
+      ResidentParams R;
+      R.ptr = P.ptr;
+      R.idx = P.idx;
+      R.val = (const float*)P.val;
+      R.X = (const float*)X;
+      R.Y = (float*)Y;
+      R.diag = diag;
+      R.G = (const float*)G;
+      R.feedback = o.feedback;
+      R.cg_steps = o.cg_steps;
+      R.dynamic_lambda = o.dynamic_lambda;
+      R.lambda = (float)o.lambda;
+      R.row_list = A.all_short ? nullptr : A.short_list.i32();
+      R.n_list = A.n_short;
+      R.loss_partials = P.loss_partials;
+      const int grid = std::min(c.sm_count * 3, A.n_short);
+      const size_t smem = sizeof(ResidentSmem);
+      const bool full_g = (o.feedback == B200ALS_IMPLICIT) && !diag;
+      if (full_g) {
+        CU(cudaFuncSetAttribute(als_cg_resident_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        als_cg_resident_kernel<true><<<grid, kResThreads, smem, c.stream>>>(R);
+      } else {
+        CU(cudaFuncSetAttribute(als_cg_resident_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        als_cg_resident_kernel<false><<<grid, kResThreads, smem, c.stream>>>(R);
+      }
+      CU(cudaGetLastError());
+      sum_partials_kernel<<<1, 32, 0, c.stream>>>(P.loss_partials, grid, c.loss_acc.f64(), 1);
+      CU(cudaGetLastError());
+    }
+    if (A.n_long > 0) {
+      if (diag && !G) return fail(B200ALS_EINVAL, "rows longer than 80 need the full XtX for the streaming kernel");
+      TRY(run_generic_cg(A.long_list.i32(), A.n_long));
+    }
+  }
+  return B200ALS_OK;
+}
+
+// loss = (sum_rows + lambda * regulariser) / nnz, rounded through T like the reference's return type
+// (wrmf_implicit.hpp:286-304, wrmf_explicit.hpp:147-173)
+template <typename T>
+static int finish_loss(Ctx& c, const T* X, int k, long long n_src, const T* cnt_X, const HalfOpts& o, int64_t nnz,
+                       double rows_sum, bool rows_sum_given, double* loss_out) {
+  double reg = 0.0;
+  if (o.lambda > 0) {
+    const bool weighted = (o.feedback == B200ALS_EXPLICIT) && o.dynamic_lambda;
+    const int grid = c.sm_count * 2;
+    CU(c.reg_partials.ensure(sizeof(double) * (size_t)grid));
+    sqnorm_kernel<T><<<grid, 256, 0, c.stream>>>(X, k, n_src, weighted ? cnt_X : nullptr, c.reg_partials.f64());
+    CU(cudaGetLastError());
+    sum_partials_kernel<<<1, 32, 0, c.stream>>>(c.reg_partials.f64(), grid, c.loss_acc.f64() + 1, 0);
+    CU(cudaGetLastError());
+  }
+  double h[2] = {0, 0};
+  int st = 0;
+  CU(cudaMemcpyAsync(h, c.loss_acc.p, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaMemcpyAsync(&st, c.status.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaStreamSynchronize(c.stream));
+  if (st != 0) return fail(B200ALS_ENOTSPD, "a per-row system was not positive definite (Cholesky pivot <= 0)");
+  if (o.lambda > 0) reg = h[1];
+  const double rows = rows_sum_given ? rows_sum : h[0];
+  if (loss_out) *loss_out = (double)(T)((rows + o.lambda * reg) / (double)nnz);
+  return B200ALS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// 1. stateless calls
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+static int stateless_half(const b200als_csc* A, int rank, const T* X, T* Y, const T* XtX, const T* cnt_X, const HalfOpts& o,
+                          double* loss) {
+  Ctx& c = ctx();
+  TRY(c.init());
+  if (!A || !X || !Y) return fail(B200ALS_EINVAL, "null argument");
+  if (rank <= 0) return fail(B200ALS_EINVAL, "rank must be positive");
+  CscDev<T> D;
+  TRY(upload_csc<T>(A, D, c.stream));
+  const size_t k = (size_t)rank;
+  DevBuf dX, dY, dG, dCnt;
+  CU(dX.ensure(sizeof(T) * k * (size_t)A->n_rows));
+  CU(dY.ensure(sizeof(T) * k * (size_t)A->n_cols));
+  CU(cudaMemcpyAsync(dX.p, X, sizeof(T) * k * (size_t)A->n_rows, cudaMemcpyHostToDevice, c.stream));
+  CU(cudaMemcpyAsync(dY.p, Y, sizeof(T) * k * (size_t)A->n_cols, cudaMemcpyHostToDevice, c.stream));
+  const T* G = nullptr;
+  if (o.feedback == B200ALS_IMPLICIT) {
+    CU(dG.ensure(sizeof(T) * k * k));
+    if (XtX) CU(cudaMemcpyAsync(dG.p, XtX, sizeof(T) * k * k, cudaMemcpyHostToDevice, c.stream));
+    else TRY(run_gram<T>(c, dX.template as<T>(), rank, A->n_rows, o.lambda, dG.template as<T>(), nullptr));
+    G = dG.template as<T>();
+  }
+  const T* dcnt = nullptr;
+  if (o.feedback == B200ALS_EXPLICIT && o.dynamic_lambda && o.lambda > 0) {
+    if (!cnt_X) return fail(B200ALS_EINVAL, "explicit feedback with dynamic_lambda needs cnt_X");
+    CU(dCnt.ensure(sizeof(T) * (size_t)A->n_rows));
+    CU(cudaMemcpyAsync(dCnt.p, cnt_X, sizeof(T) * (size_t)A->n_rows, cudaMemcpyHostToDevice, c.stream));
+    dcnt = dCnt.template as<T>();
+  }
+  TRY(solve_rows<T>(c, D, dX.template as<T>(), dY.template as<T>(), G, nullptr, rank, o));
+  CU(cudaMemcpyAsync(Y, dY.p, sizeof(T) * k * (size_t)A->n_cols, cudaMemcpyDeviceToHost, c.stream));
+  TRY(finish_loss<T>(c, dX.template as<T>(), rank, A->n_rows, dcnt, o, A->nnz, 0.0, false, loss));
+  return B200ALS_OK;
+}
+
+static int check_bias_args(int with_biases, double global_bias) {
+  if (with_biases) return fail(B200ALS_EUNSUPPORTED, "with_user_item_bias is not implemented (SURVEY 8f-3)");
+  if (global_bias != 0.0) return fail(B200ALS_EUNSUPPORTED, "with_global_bias is not implemented (SURVEY 8f-3)");
+  return B200ALS_OK;
+}
+
+extern "C" int b200als_als_implicit_float(const b200als_csc* m, int rank, const float* X, float* Y, const float* XtX,
+                                          double lambda, int, unsigned solver, unsigned cg_steps, int with_biases, int,
+                                          double global_bias, float*, int, double* loss) {
+  TRY(check_bias_args(with_biases, global_bias));
+  HalfOpts o{B200ALS_IMPLICIT, (int)solver, (int)cg_steps, 0, 0, lambda};
+  return stateless_half<float>(m, rank, X, Y, XtX, nullptr, o, loss);
+}
+extern "C" int b200als_als_implicit_double(const b200als_csc* m, int rank, const double* X, double* Y, const double* XtX,
+                                           double lambda, int, unsigned solver, unsigned cg_steps, int with_biases, int,
+                                           double global_bias, double*, int, double* loss) {
+  TRY(check_bias_args(with_biases, global_bias));
+  HalfOpts o{B200ALS_IMPLICIT, (int)solver, (int)cg_steps, 0, 0, lambda};
+  return stateless_half<double>(m, rank, X, Y, XtX, nullptr, o, loss);
+}
+extern "C" int b200als_als_explicit_float(const b200als_csc* m, int rank, const float* X, float* Y, const float* cnt_X,
+                                          double lambda, unsigned, unsigned solver, unsigned cg_steps, int dynamic_lambda,
+                                          int with_biases, int, double* loss) {
+  TRY(check_bias_args(with_biases, 0.0));
+  HalfOpts o{B200ALS_EXPLICIT, (int)solver, (int)cg_steps, dynamic_lambda != 0, 0, lambda};
+  return stateless_half<float>(m, rank, X, Y, nullptr, cnt_X, o, loss);
+}
+extern "C" int b200als_als_explicit_double(const b200als_csc* m, int rank, const double* X, double* Y, const double* cnt_X,
+                                           double lambda, unsigned, unsigned solver, unsigned cg_steps, int dynamic_lambda,
+                                           int with_biases, int, double* loss) {
+  TRY(check_bias_args(with_biases, 0.0));
+  HalfOpts o{B200ALS_EXPLICIT, (int)solver, (int)cg_steps, dynamic_lambda != 0, 0, lambda};
+  return stateless_half<double>(m, rank, X, Y, nullptr, cnt_X, o, loss);
+}
+
+extern "C" int b200als_gram_float(const float* X, int rank, int64_t n, double lambda, float* XtX) {
+  Ctx& c = ctx();
+  TRY(c.init());
+  if (!X || !XtX || rank <= 0 || n < 0) return fail(B200ALS_EINVAL, "bad argument");
+  DevBuf dX, dG;
+  CU(dX.ensure(sizeof(float) * (size_t)rank * (size_t)n));
+  CU(dG.ensure(sizeof(float) * (size_t)rank * rank));
+  CU(cudaMemcpyAsync(dX.p, X, sizeof(float) * (size_t)rank * (size_t)n, cudaMemcpyHostToDevice, c.stream));
+  TRY(run_gram<float>(c, dX.f32(), rank, n, lambda, dG.f32(), nullptr));
+  CU(cudaMemcpyAsync(XtX, dG.p, sizeof(float) * (size_t)rank * rank, cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaStreamSynchronize(c.stream));
+  return B200ALS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// 3. communicator (one process per GPU)
+// ------------------------------------------------------------------------------------------------------
+struct Comm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+};
+static Comm g_comm;
+
+extern "C" int b200als_comm_unique_id(void* id_out) {
+  static_assert(sizeof(ncclUniqueId) == B200ALS_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  if (!id_out) return fail(B200ALS_EINVAL, "null id");
+  ncclUniqueId id;
+  NC(ncclGetUniqueId(&id));
+  std::memcpy(id_out, &id, sizeof(id));
+  return B200ALS_OK;
+}
+extern "C" int b200als_comm_init(const void* id, int rank, int world_size) {
+  if (!id || world_size < 1 || rank < 0 || rank >= world_size) return fail(B200ALS_EINVAL, "bad communicator arguments");
+  TRY(ctx().init());
+  if (g_comm.comm) return fail(B200ALS_EINVAL, "communicator already initialised");
+  ncclUniqueId uid;
+  std::memcpy(&uid, id, sizeof(uid));
+  NC(ncclCommInitRank(&g_comm.comm, world_size, uid, rank));
+  g_comm.rank = rank;
+  g_comm.world = world_size;
+  return B200ALS_OK;
+}
+extern "C" int b200als_comm_destroy(void) {
+  if (g_comm.comm) {
+    ncclCommDestroy(g_comm.comm);
+    g_comm.comm = nullptr;
+  }
+  g_comm.rank = 0;
+  g_comm.world = 1;
+  return B200ALS_OK;
+}
+extern "C" int b200als_comm_info(int* rank, int* world_size) {
+  if (rank) *rank = g_comm.rank;
+  if (world_size) *world_size = g_comm.world;
+  return B200ALS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// 2. session
+// ------------------------------------------------------------------------------------------------------
+struct b200als_session {
+  b200als_options opt;
+  int k = 0;
+  int32_t n_user = 0, n_item = 0;
+  // orientation [B200ALS_ITEMS]: columns = items (local block), idx = users ; [B200ALS_USERS]: columns = users
+  CscDev<float> csc[2];
+  bool has[2] = {false, false};
+  int32_t shard_begin[2] = {0, 0}, shard_end[2] = {0, 0};
+  int64_t nnz_global[2] = {0, 0};
+  DevBuf fac[2];   // full factor matrices (stored in basis B): [ITEMS] k x n_item, [USERS] k x n_user
+  DevBuf cnt[2];   // cnt[w][j] = nnz of row j of factor matrix w (global), for the dynamic-lambda regulariser
+  DevBuf G, G64, Vt, Q, Qt, diag, B64, Btmp, Bf, scratch;
+  bool basis_identity = true;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  float t_gram = 0, t_prep = 0, t_solve = 0, t_comm = 0;
+};
+
+extern "C" void b200als_default_options(b200als_options* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->feedback = B200ALS_IMPLICIT;
+  o->solver = B200ALS_CONJUGATE_GRADIENT;
+  o->cg_steps = 3;
+  o->dynamic_lambda = 1;
+  o->lambda = 0.0;
+  o->kernel = 0;
+}
+
+static int session_alloc(b200als_session* s) {
+  Ctx& c = ctx();
+  const size_t k = (size_t)s->k;
+  CU(s->fac[B200ALS_ITEMS].ensure(sizeof(float) * k * (size_t)s->n_item));
+  CU(s->fac[B200ALS_USERS].ensure(sizeof(float) * k * (size_t)s->n_user));
+  CU(cudaMemsetAsync(s->fac[0].p, 0, s->fac[0].bytes, c.stream));
+  CU(cudaMemsetAsync(s->fac[1].p, 0, s->fac[1].bytes, c.stream));
+  CU(s->G.ensure(sizeof(float) * k * k));
+  CU(s->G64.ensure(sizeof(double) * k * k));
+  CU(s->Vt.ensure(sizeof(double) * k * k));
+  CU(s->Q.ensure(sizeof(float) * k * k));
+  CU(s->Qt.ensure(sizeof(float) * k * k));
+  CU(s->diag.ensure(sizeof(float) * k));
+  CU(s->B64.ensure(sizeof(double) * k * k));
+  CU(s->Btmp.ensure(sizeof(double) * k * k));
+  CU(s->Bf.ensure(sizeof(float) * k * k));
+  set_identity_kernel<<<(unsigned)((k * k + 255) / 256), 256, 0, c.stream>>>(s->B64.f64(), (int)k);
+  CU(cudaGetLastError());
+  s->basis_identity = true;
+  for (auto& e : s->ev) CU(cudaEventCreate(&e));
+  return B200ALS_OK;
+}
+
+// cnt[which][j] += number of entries of row j seen in the local block of the *other* orientation
+__global__ void count_idx_kernel(const int32_t* __restrict__ idx, long long nnz, float* __restrict__ cnt) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < nnz) atomicAdd(&cnt[idx[e]], 1.0f);
+}
+
+static int session_counts(b200als_session* s) {
+  // cnt_X for the dynamic-lambda regulariser (R/model_WRMF.R:305-315): nnz per row of the FIXED matrix, i.e. for
+  // the user half (X = items) the nnz per item.  Counted from whichever orientation is present.
+  Ctx& c = ctx();
+  for (int w = 0; w < 2; w++) {
+    const int32_t n = (w == B200ALS_ITEMS) ? s->n_item : s->n_user;
+    CU(s->cnt[w].ensure(sizeof(float) * (size_t)std::max(1, n)));
+    CU(cudaMemsetAsync(s->cnt[w].p, 0, sizeof(float) * (size_t)n, c.stream));
+  }
+  // orientation USERS has idx = items -> counts per item ; orientation ITEMS has idx = users -> counts per user
+  for (int w = 0; w < 2; w++) {
+    if (!s->has[w] || s->csc[w].nnz == 0) continue;
+    const int other = 1 - w;
+    count_idx_kernel<<<(unsigned)((s->csc[w].nnz + 255) / 256), 256, 0, c.stream>>>(s->csc[w].idx.i32(), s->csc[w].nnz,
+                                                                                   s->cnt[other].f32());
+    CU(cudaGetLastError());
+  }
+  if (g_comm.world > 1) {
+    for (int w = 0; w < 2; w++) {
+      const int32_t n = (w == B200ALS_ITEMS) ? s->n_item : s->n_user;
+      if (s->has[1 - w]) NC(ncclAllReduce(s->cnt[w].p, s->cnt[w].p, (size_t)n, ncclFloat, ncclSum, g_comm.comm, c.stream));
+    }
+  }
+  return B200ALS_OK;
+}
+
+extern "C" int b200als_create(b200als_session** out, const b200als_csc* c_ui, const b200als_csc* c_iu, int32_t n_user,
+                              int32_t n_item, int rank, const b200als_options* opts) {
+  Ctx& c = ctx();
+  TRY(c.init());
+  if (!out || rank <= 0 || n_user < 0 || n_item < 0) return fail(B200ALS_EINVAL, "bad argument");
+  if (rank > 256) return fail(B200ALS_EUNSUPPORTED, "rank > 256 is not supported");
+  b200als_session* s = new b200als_session();
+  if (opts) s->opt = *opts; else b200als_default_options(&s->opt);
+  s->k = rank;
+  s->n_user = n_user;
+  s->n_item = n_item;
+  int rc = session_alloc(s);
+  if (rc == B200ALS_OK && c_ui) {
+    rc = upload_csc<float>(c_ui, s->csc[B200ALS_ITEMS], c.stream);
+    s->has[B200ALS_ITEMS] = true;
+    s->shard_begin[B200ALS_ITEMS] = 0;
+    s->shard_end[B200ALS_ITEMS] = c_ui->n_cols;
+  }
+  if (rc == B200ALS_OK && c_iu) {
+    rc = upload_csc<float>(c_iu, s->csc[B200ALS_USERS], c.stream);
+    s->has[B200ALS_USERS] = true;
+    s->shard_begin[B200ALS_USERS] = 0;
+    s->shard_end[B200ALS_USERS] = c_iu->n_cols;
+  }
+  if (rc == B200ALS_OK) rc = session_counts(s);
+  for (int w = 0; w < 2 && rc == B200ALS_OK; w++) {
+    long long nnz = s->has[w] ? s->csc[w].nnz : 0;
+    if (g_comm.world > 1) {
+      DevBuf t;
+      if (t.ensure(sizeof(long long)) != cudaSuccess) { rc = fail(B200ALS_ECUDA, "alloc"); break; }
+      cudaMemcpyAsync(t.p, &nnz, sizeof(nnz), cudaMemcpyHostToDevice, c.stream);
+      if (ncclAllReduce(t.p, t.p, 1, ncclInt64, ncclSum, g_comm.comm, c.stream) != ncclSuccess) { rc = fail(B200ALS_ENCCL, "allreduce nnz"); break; }
+      cudaMemcpyAsync(&nnz, t.p, sizeof(nnz), cudaMemcpyDeviceToHost, c.stream);
+      cudaStreamSynchronize(c.stream);
+    }
+    s->nnz_global[w] = nnz;
+  }
+  if (rc == B200ALS_OK && cudaStreamSynchronize(c.stream) != cudaSuccess) rc = fail(B200ALS_ECUDA, "sync after upload");
+  if (rc != B200ALS_OK) {
+    b200als_destroy(s);
+    return rc;
+  }
+  *out = s;
+  return B200ALS_OK;
+}
+
+extern "C" int b200als_destroy(b200als_session* s) {
+  if (!s) return B200ALS_OK;
+  for (auto& e : s->ev)
+    if (e) cudaEventDestroy(e);
+  delete s;
+  return B200ALS_OK;
+}
+
+extern "C" int b200als_set_shard(b200als_session* s, int which, int32_t begin, int32_t end) {
+  if (!s || which < 0 || which > 1) return fail(B200ALS_EINVAL, "bad argument");
+  const int32_t n = (which == B200ALS_ITEMS) ? s->n_item : s->n_user;
+  if (begin < 0 || end < begin || end > n || (s->has[which] && end - begin != s->csc[which].n_cols))
+    return fail(B200ALS_EINVAL, "shard range does not match the uploaded block");
+  s->shard_begin[which] = begin;
+  s->shard_end[which] = end;
+  return B200ALS_OK;
+}
+
+static int rotate_matrix(Ctx& c, float* M, long long n, const float* R) {
+  if (n <= 0) return B200ALS_OK;
+  const size_t smem = sizeof(RotSmem);
+  CU(cudaFuncSetAttribute(rotate_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long blocks = (n + kRotRows - 1) / kRotRows;
+  const int grid = (int)std::min<long long>(blocks, c.sm_count * 2);
+  rotate_rows_kernel<<<grid, 256, smem, c.stream>>>(M, M, R, n);
+  CU(cudaGetLastError());
+  return B200ALS_OK;
+}
+
+// true = stored * B'  <=> stored = true * B.  Export / import copies through a scratch buffer.
+extern "C" int b200als_set_factors(b200als_session* s, int which, const float* host) {
+  Ctx& c = ctx();
+  if (!s || !host || which < 0 || which > 1) return fail(B200ALS_EINVAL, "bad argument");
+  const long long n = (which == B200ALS_ITEMS) ? s->n_item : s->n_user;
+  CU(cudaMemcpyAsync(s->fac[which].p, host, sizeof(float) * (size_t)s->k * (size_t)n, cudaMemcpyHostToDevice, c.stream));
+  if (!s->basis_identity) {
+    convert_kk_kernel<<<(s->k * s->k + 255) / 256, 256, 0, c.stream>>>(s->B64.f64(), s->Bf.f32(), s->k, 0);
+    CU(cudaGetLastError());
+    TRY(rotate_matrix(c, s->fac[which].f32(), n, s->Bf.f32()));
+  }
+  CU(cudaStreamSynchronize(c.stream));
+  return B200ALS_OK;
+}
+static int export_rotated(b200als_session* s, const float* dev, long long n, float* host) {
+  Ctx& c = ctx();
+  const size_t bytes = sizeof(float) * (size_t)s->k * (size_t)n;
+  if (s->basis_identity) {
+    CU(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c.stream));
+  } else {
+    CU(s->scratch.ensure(bytes));
+    CU(cudaMemcpyAsync(s->scratch.p, dev, bytes, cudaMemcpyDeviceToDevice, c.stream));
+    convert_kk_kernel<<<(s->k * s->k + 255) / 256, 256, 0, c.stream>>>(s->B64.f64(), s->Bf.f32(), s->k, 1);
+    CU(cudaGetLastError());
+    TRY(rotate_matrix(c, s->scratch.f32(), n, s->Bf.f32()));
+    CU(cudaMemcpyAsync(host, s->scratch.p, bytes, cudaMemcpyDeviceToHost, c.stream));
+  }
+  CU(cudaStreamSynchronize(c.stream));
+  return B200ALS_OK;
+}
+extern "C" int b200als_get_factors(b200als_session* s, int which, float* host) {
+  if (!s || !host || which < 0 || which > 1) return fail(B200ALS_EINVAL, "bad argument");
+  const long long n = (which == B200ALS_ITEMS) ? s->n_item : s->n_user;
+  return export_rotated(s, s->fac[which].f32(), n, host);
+}
+
+extern "C" int b200als_init_factors(b200als_session* s, uint64_t seed) {
+  Ctx& c = ctx();
+  if (!s) return fail(B200ALS_EINVAL, "null session");
+  const long long nu = (long long)s->k * s->n_user, ni = (long long)s->k * s->n_item;
+  if (nu) init_normal_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, c.stream>>>(s->fac[B200ALS_USERS].f32(), nu, seed, 0.01f);
+  CU(cudaGetLastError());
+  if (s->opt.solver == B200ALS_CONJUGATE_GRADIENT) {
+    CU(cudaMemsetAsync(s->fac[B200ALS_ITEMS].p, 0, sizeof(float) * (size_t)ni, c.stream));  // R/model_WRMF.R:217-230
+  } else if (ni) {
+    init_normal_kernel<<<(unsigned)((ni + 255) / 256), 256, 0, c.stream>>>(s->fac[B200ALS_ITEMS].f32(), ni,
+                                                                           seed ^ 0xA5A5A5A5ull, 0.01f);
+    CU(cudaGetLastError());
+  }
+  set_identity_kernel<<<(s->k * s->k + 255) / 256, 256, 0, c.stream>>>(s->B64.f64(), s->k);
+  CU(cudaGetLastError());
+  s->basis_identity = true;
+  CU(cudaStreamSynchronize(c.stream));
+  return B200ALS_OK;
+}
+
+// all-gather of the freshly solved slices (unequal block sizes => one broadcast per owner, grouped)
+static int exchange_slices(b200als_session* s, int which) {
+  if (g_comm.world <= 1) return B200ALS_OK;
+  Ctx& c = ctx();
+  // every rank learns every rank's [begin, end)
+  std::vector<int32_t> ranges(2 * g_comm.world);
+  DevBuf d;
+  CU(d.ensure(sizeof(int32_t) * 2 * g_comm.world));
+  int32_t mine[2] = {s->shard_begin[which], s->shard_end[which]};
+  CU(cudaMemcpyAsync(d.i32() + 2 * g_comm.rank, mine, sizeof(mine), cudaMemcpyHostToDevice, c.stream));
+  NC(ncclAllGather(d.i32() + 2 * g_comm.rank, d.p, 2, ncclInt32, g_comm.comm, c.stream));
+  CU(cudaMemcpyAsync(ranges.data(), d.p, sizeof(int32_t) * 2 * g_comm.world, cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaStreamSynchronize(c.stream));
+  float* M = s->fac[which].f32();
+  NC(ncclGroupStart());
+  for (int r = 0; r < g_comm.world; r++) {
+    const size_t cnt = (size_t)(ranges[2 * r + 1] - ranges[2 * r]) * (size_t)s->k;
+    if (cnt == 0) continue;
+    float* p = M + (size_t)ranges[2 * r] * s->k;
+    NC(ncclBroadcast(p, p, cnt, ncclFloat, r, g_comm.comm, c.stream));
+  }
+  NC(ncclGroupEnd());
+  return B200ALS_OK;
+}
+
+// solve for `which`; Yout == nullptr: in place into the session's factors.  Yout != nullptr (transform_):
+// solve into Yout (device, local block) starting from zeros.
+static int session_half(b200als_session* s, int which, int solver, float* Yout, double* loss) {
+  Ctx& c = ctx();
+  if (!s->has[which]) return fail(B200ALS_EINVAL, "the orientation needed for this half-iteration was not supplied");
+  const int fixed = 1 - which;
+  const long long n_fixed = (fixed == B200ALS_ITEMS) ? s->n_item : s->n_user;
+  float* X = s->fac[fixed].f32();
+  float* Yfull = s->fac[which].f32();
+  float* Y = Yout ? Yout : (Yfull + (size_t)s->shard_begin[which] * s->k);
+  HalfOpts o{s->opt.feedback, solver, s->opt.cg_steps, s->opt.dynamic_lambda, s->opt.kernel, s->opt.lambda};
+  CscDev<float>& A = s->csc[which];
+  const bool implicit = (o.feedback == B200ALS_IMPLICIT);
+  CU(cudaEventRecord(s->ev[0], c.stream));
+  const float* G = nullptr;
+  const float* diag = nullptr;
+  if (implicit) {
+    TRY(run_gram<float>(c, X, s->k, n_fixed, o.lambda, s->G.f32(), s->G64.f64()));
+    G = s->G.f32();
+  }
+  CU(cudaEventRecord(s->ev[1], c.stream));
+  // eigenbasis path: implicit CG, rank 128, resident kernel, enough rows to amortise the rotation
+  bool use_diag = implicit && solver == B200ALS_CONJUGATE_GRADIENT && s->k == kResK && o.kernel != 1 && o.kernel != 2 && !Yout;
+  if (use_diag) {
+    TRY(classify_rows(c, A));
+    if (o.kernel != 3 && (A.n_long > 0 || (long long)A.n_cols * g_comm.world < 50000)) use_diag = false;
+  }
+  if (use_diag) {
+    jacobi_eig_kernel<<<1, kJacobiThreads, 0, c.stream>>>(s->G64.f64(), s->Vt.f64(), s->k, s->Q.f32(),
+                                                          s->diag.f32(), s->Btmp.f64(), 30);
+    CU(cudaGetLastError());
+    // fixed <- fixed Q (whole matrix), solved slice <- slice Q, B <- B Q
+    TRY(rotate_matrix(c, X, n_fixed, s->Q.f32()));
+    TRY(rotate_matrix(c, Y, A.n_cols, s->Q.f32()));
+    matmul_kk_kernel<<<(s->k * s->k + 255) / 256, 256, 0, c.stream>>>(s->B64.f64(), s->Btmp.f64(),
+                                                                     s->Vt.f64(), s->k);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(s->B64.p, s->Vt.p, sizeof(double) * (size_t)s->k * s->k, cudaMemcpyDeviceToDevice, c.stream));
+    s->basis_identity = false;
+    diag = s->diag.f32();
+    G = nullptr;
+  }
+  CU(cudaEventRecord(s->ev[2], c.stream));
+  TRY(solve_rows<float>(c, A, X, Y, G, diag, s->k, o));
+  CU(cudaEventRecord(s->ev[3], c.stream));
+  if (!Yout) TRY(exchange_slices(s, which));
+  CU(cudaEventRecord(s->ev[4], c.stream));
+  // loss: local row sums -> global
+  double rows_sum = 0.0;
+  {
+    double h = 0.0;
+    if (g_comm.world > 1) NC(ncclAllReduce(c.loss_acc.p, c.loss_acc.p, 1, ncclDouble, ncclSum, g_comm.comm, c.stream));
+    CU(cudaMemcpyAsync(&h, c.loss_acc.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    CU(cudaStreamSynchronize(c.stream));
+    rows_sum = h;
+  }
+  TRY(finish_loss<float>(c, X, s->k, n_fixed, s->cnt[fixed].f32(), o, s->nnz_global[which], rows_sum, true, loss));
+  cudaEventElapsedTime(&s->t_gram, s->ev[0], s->ev[1]);
+  cudaEventElapsedTime(&s->t_prep, s->ev[1], s->ev[2]);
+  cudaEventElapsedTime(&s->t_solve, s->ev[2], s->ev[3]);
+  cudaEventElapsedTime(&s->t_comm, s->ev[3], s->ev[4]);
+  return B200ALS_OK;
+}
+
+extern "C" int b200als_half_iteration(b200als_session* s, int which, int solver_override, double* loss) {
+  if (!s || which < 0 || which > 1) return fail(B200ALS_EINVAL, "bad argument");
+  return session_half(s, which, solver_override >= 0 ? solver_override : s->opt.solver, nullptr, loss);
+}
+
+extern "C" int b200als_fit(b200als_session* s, int n_iter, double convergence_tol, double* loss_trace, int* n_iter_done) {
+  if (!s || n_iter < 0) return fail(B200ALS_EINVAL, "bad argument");
+  double loss_prev = INFINITY;
+  int done = 0;
+  for (int i = 0; i < n_iter; i++) {  // R/model_WRMF.R:318-338
+    double li = 0, lu = 0;
+    TRY(session_half(s, B200ALS_ITEMS, s->opt.solver, nullptr, &li));
+    TRY(session_half(s, B200ALS_USERS, s->opt.solver, nullptr, &lu));
+    if (loss_trace) { loss_trace[2 * i] = li; loss_trace[2 * i + 1] = lu; }
+    done = i + 1;
+    if (loss_prev / lu - 1 < convergence_tol) break;
+    loss_prev = lu;
+  }
+  if (n_iter_done) *n_iter_done = done;
+  return B200ALS_OK;
+}
+
+extern "C" int b200als_transform(b200als_session* s, float* host_out, double* loss) {
+  Ctx& c = ctx();
+  if (!s || !host_out) return fail(B200ALS_EINVAL, "bad argument");
+  if (!s->has[B200ALS_USERS]) return fail(B200ALS_EINVAL, "transform needs the users orientation");
+  CscDev<float>& A = s->csc[B200ALS_USERS];
+  DevBuf res;
+  const size_t bytes = sizeof(float) * (size_t)s->k * (size_t)A.n_cols;
+  CU(res.ensure(bytes));
+  CU(cudaMemsetAsync(res.p, 0, bytes, c.stream));  // res = zeros (R/model_WRMF.R:423-427)
+  const int solver = (s->opt.solver == B200ALS_CONJUGATE_GRADIENT) ? B200ALS_CHOLESKY : s->opt.solver;  // avoid_cg (:112)
+  TRY(session_half(s, B200ALS_USERS, solver, res.f32(), loss));
+  return export_rotated(s, res.f32(), A.n_cols, host_out);
+}
+
+extern "C" int b200als_last_timing(b200als_session* s, float* gram_ms, float* prep_ms, float* solve_ms, float* comm_ms) {
+  if (!s) return fail(B200ALS_EINVAL, "null session");
+  if (gram_ms) *gram_ms = s->t_gram;
+  if (prep_ms) *prep_ms = s->t_prep;
+  if (solve_ms) *solve_ms = s->t_solve;
+  if (comm_ms) *comm_ms = s->t_comm;
+  return B200ALS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// 4. synthetic workloads
+// ------------------------------------------------------------------------------------------------------
+extern "C" int b200als_synth_csr_host(int32_t n_rows, int32_t n_cols, int32_t nnz_per_row, uint64_t seed, int explicit_values,
+                                      int64_t row_offset, int32_t* ptr, int32_t* idx, float* val_f32, double* val_f64) {
+  if (n_rows < 0 || n_cols <= 0 || nnz_per_row <= 0 || nnz_per_row > n_cols || !ptr || !idx)
+    return fail(B200ALS_EINVAL, "bad synthetic shape");
+  if ((long long)n_rows * nnz_per_row > 2147483647LL) return fail(B200ALS_EINVAL, "nnz exceeds 32-bit row pointers");
+  const unsigned nt = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; t++)
+    th.emplace_back([=]() {
+      const int64_t r0 = (int64_t)n_rows * t / nt, r1 = (int64_t)n_rows * (t + 1) / nt;
+      for (int64_t r = r0; r < r1; r++) {
+        ptr[r] = (int32_t)(r * nnz_per_row);
+        for (int j = 0; j < nnz_per_row; j++) {
+          int32_t col; float v;
+          synth_entry(r + row_offset, j, n_cols, nnz_per_row, seed, explicit_values, &col, &v);
+          const int64_t e = r * nnz_per_row + j;
+          idx[e] = col;
+          if (val_f32) val_f32[e] = v;
+          if (val_f64) val_f64[e] = (double)v;
+        }
+      }
+    });
+  for (auto& x : th) x.join();
+  ptr[n_rows] = (int32_t)((int64_t)n_rows * nnz_per_row);
+  return B200ALS_OK;
+}
+
+extern "C" int b200als_create_synthetic(b200als_session** out, int32_t n_user_local, int64_t user_offset, int32_t n_user_global,
+                                        int32_t n_item, int32_t nnz_per_row, uint64_t seed, int rank,
+                                        const b200als_options* opts) {
+  Ctx& c = ctx();
+  TRY(c.init());
+  if (!out || rank <= 0 || n_user_local < 0 || n_item <= 0 || nnz_per_row <= 0 || nnz_per_row > n_item)
+    return fail(B200ALS_EINVAL, "bad argument");
+  if ((long long)n_user_local * nnz_per_row > 2147483647LL) return fail(B200ALS_EINVAL, "local nnz exceeds 32-bit row pointers");
+  b200als_session* s = new b200als_session();
+  if (opts) s->opt = *opts; else b200als_default_options(&s->opt);
+  s->k = rank;
+  s->n_user = n_user_global;
+  s->n_item = n_item;
+  int rc = session_alloc(s);
+  if (rc != B200ALS_OK) { b200als_destroy(s); return rc; }
+  CscDev<float>& A = s->csc[B200ALS_USERS];
+  A.n_rows = n_item;
+  A.n_cols = n_user_local;
+  A.nnz = (int64_t)n_user_local * nnz_per_row;
+  auto bail = [&](int code, const char* m) { b200als_destroy(s); return fail(code, m); };
+  if (A.ptr.ensure(sizeof(int32_t) * ((size_t)n_user_local + 1)) != cudaSuccess) return bail(B200ALS_ECUDA, "alloc ptr");
+  if (A.idx.ensure(sizeof(int32_t) * (size_t)A.nnz) != cudaSuccess) return bail(B200ALS_ECUDA, "alloc idx");
+  if (A.val.ensure(sizeof(float) * (size_t)A.nnz) != cudaSuccess) return bail(B200ALS_ECUDA, "alloc val");
+  const long long total = std::max<long long>(A.nnz, n_user_local + 1);
+  synth_csr_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c.stream>>>(n_user_local, n_item, nnz_per_row, seed,
+                                                                         s->opt.feedback == B200ALS_EXPLICIT, user_offset,
+                                                                         A.ptr.i32(), A.idx.i32(), A.val.f32());
+  if (cudaGetLastError() != cudaSuccess) return bail(B200ALS_ECUDA, "synth kernel launch");
+  s->has[B200ALS_USERS] = true;
+  s->shard_begin[B200ALS_USERS] = (int32_t)user_offset;
+  s->shard_end[B200ALS_USERS] = (int32_t)user_offset + n_user_local;
+  s->nnz_global[B200ALS_USERS] = (int64_t)n_user_global * nnz_per_row;
+  rc = session_counts(s);
+  if (rc == B200ALS_OK && cudaStreamSynchronize(c.stream) != cudaSuccess) rc = fail(B200ALS_ECUDA, "sync");
+  if (rc != B200ALS_OK) { b200als_destroy(s); return rc; }
+  *out = s;
+  return B200ALS_OK;
+}

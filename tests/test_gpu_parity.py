@@ -1,0 +1,222 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against
+  (1) the committed golden vectors generated from the reference's own source,
+  (2) the CPU oracle on seeded inputs at sizes the oracle finishes in seconds,
+  (3) size-independent properties at larger sizes.
+Stated tolerances: fp32 engine vs fp64 reference: relative Frobenius error of the
+updated factor matrix <= 1e-5 per half-iteration, loss relative error <= 1e-5; fp64 kernels: <= 1e-9
+(summation order only).  CSR indexing is exact: every row's result depends only on its own indices."""
+import numpy as np
+import pytest
+
+import oracle
+import wrmf_cases as wc
+from rsparse_b200 import WRMF, Session, als_explicit, als_implicit, gram
+from rsparse_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+CASES = sorted(wc.half_iteration_cases().keys())
+TOL_F32 = 1e-5
+TOL_F64 = 1e-9
+
+
+def relF(a, b):
+    a = a.astype(np.float64)
+    b = b.astype(np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def run_stateless(c, dt, XtX="engine"):
+    X = c["X"].astype(dt)
+    Y = c["Y0"].astype(dt).copy()
+    if c["feedback"] == "implicit":
+        G = None
+        if XtX == "host":  # what R does: tcrossprod(X) + lambda*I in the working precision (R/model_WRMF.R:474-486)
+            G = (X.T @ X + c["lam"] * np.eye(X.shape[1], dtype=dt)).astype(dt)
+        loss = als_implicit(c["ptr"], c["idx"], c["val"], X, Y, c["lam"], c["solver"], c["cg_steps"], XtX=G)
+    else:
+        loss = als_explicit(c["ptr"], c["idx"], c["val"], X, Y, c["cnt_X"], c["lam"], c["solver"], c["cg_steps"],
+                            c["dynamic_lambda"])
+    return Y, loss
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_f64_kernels_vs_reference_golden(name, cases, golden_half):
+    Y, loss = run_stateless(cases[name], np.float64, XtX="host")
+    assert relF(Y, golden_half[name + "/Y_f64"]) < TOL_F64
+    assert abs(loss - float(golden_half[name + "/loss_f64"])) <= TOL_F64 * abs(loss)
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("xtx", ["host", "engine"])
+def test_f32_engine_vs_reference_golden(name, xtx, cases, golden_half):
+    Y, loss = run_stateless(cases[name], np.float32, XtX=xtx)
+    ref = golden_half[name + "/Y_f64"]
+    assert relF(Y, ref) < TOL_F32, (relF(Y, ref), relF(golden_half[name + "/Y_f32"], ref))
+    assert abs(loss - float(golden_half[name + "/loss_f64"])) <= TOL_F32 * abs(loss)
+    empty = np.diff(cases[name]["ptr"]) == 0
+    assert np.all(Y[empty] == 0)
+
+
+def _session_for(c, kernel, solver=None):
+    n_src, k = c["X"].shape
+    n_tgt = c["Y0"].shape[0]
+    s = Session(None, (c["ptr"], c["idx"], c["val"]), n_tgt, n_src, k, c["feedback"], c["solver"] if solver is None else solver,
+                c["cg_steps"], c["dynamic_lambda"], c["lam"], kernel)
+    s.set_factors(L.ITEMS, c["X"])
+    s.set_factors(L.USERS, c["Y0"])
+    return s
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if "k128" in n and "_cg_" in n])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
+def test_cg_kernel_variants_agree_with_reference(name, kernel, cases, golden_half):
+    """generic streaming (1), register-resident with full XtX (2), register-resident in the eigenbasis (3)."""
+    c = cases[name]
+    if kernel == 3 and (c["feedback"] != "implicit" or np.diff(c["ptr"]).max() > 80):
+        pytest.skip("eigenbasis path: implicit feedback, rows <= 80 nnz")
+    s = _session_for(c, kernel)
+    loss = s.half_iteration(L.USERS)
+    Y = s.get_factors(L.USERS)
+    X = s.get_factors(L.ITEMS)
+    s.close()
+    ref = golden_half[name + "/Y_f64"]
+    assert relF(Y, ref) < TOL_F32
+    assert abs(loss - float(golden_half[name + "/loss_f64"])) <= TOL_F32 * abs(loss)
+    assert relF(X, c["X"]) < 2e-6   # the fixed matrix comes back unchanged (rotated out of the eigenbasis for kernel 3)
+
+
+def test_row_results_depend_only_on_their_own_indices(cases):
+    """Bit-exact CSR indexing: permuting the order rows are presented in permutes the result rows bitwise."""
+    c = cases["synth_ragged_implicit_cg_k128"]
+    n = c["Y0"].shape[0]
+    perm = np.argsort(wc.splitmix64(np.arange(n, dtype=np.uint64)))
+    lens = np.diff(c["ptr"])
+    ptr2 = np.zeros(n + 1, np.int32)
+    ptr2[1:] = np.cumsum(lens[perm])
+    idx2 = np.concatenate([c["idx"][c["ptr"][r]:c["ptr"][r + 1]] for r in perm]).astype(np.int32)
+    val2 = np.concatenate([c["val"][c["ptr"][r]:c["ptr"][r + 1]] for r in perm])
+    X = c["X"]
+    G = gram(X, c["lam"])
+    Y1 = c["Y0"].copy()
+    als_implicit(c["ptr"], c["idx"], c["val"], X, Y1, c["lam"], wc.CG, 3, XtX=G)
+    Y2 = np.ascontiguousarray(c["Y0"][perm])
+    als_implicit(ptr2, idx2, val2, X, Y2, c["lam"], wc.CG, 3, XtX=G)
+    assert np.array_equal(Y1[perm], Y2)
+
+
+def test_gram_kernel_vs_oracle():
+    for (n, k) in ((5000, 128), (777, 16), (3000, 200)):
+        X = wc.det_factors(n, k, 5 + k)
+        G = gram(X, 0.3)
+        ref = X.astype(np.float64).T @ X.astype(np.float64) + 0.3 * np.eye(k)
+        assert np.allclose(G, ref, rtol=3e-6, atol=1e-7)
+        assert np.array_equal(G, G.T)
+        assert np.array_equal(G, gram(X, 0.3))   # fixed-order reduction => reproducible
+
+
+@pytest.mark.parametrize("name", ["ml100k_implicit_cg_k16", "ml100k_implicit_chol_k8", "ml100k_explicit_cg_k8"])
+def test_session_fit_matches_reference_trace(name, golden_traces):
+    """b200als_fit (the loop of R/model_WRMF.R:318-338) + transform_ vs the reference-generated trace."""
+    M = wc.load_movielens()
+    users, items = wc.targets_csc(M), wc.targets_csc(M.T)
+    U0, I0 = golden_traces[name + "/U0"], golden_traces[name + "/I0"]
+    k = U0.shape[1]
+    s = Session(items, users, M.shape[0], M.shape[1], k, str(golden_traces[name + "/feedback"]),
+                int(golden_traces[name + "/solver"]), 3, True, float(golden_traces[name + "/lam"]))
+    s.set_factors(L.USERS, U0)
+    s.set_factors(L.ITEMS, I0)
+    trace, done = s.fit(3, -1.0)
+    assert done == 3
+    ref_losses = golden_traces[name + "/losses_f64"]
+    assert np.allclose(trace, ref_losses, rtol=5e-5)
+    comp = s.get_factors(L.ITEMS)
+    emb, _ = s.transform()
+    s.close()
+    # three full ALS iterations compound the per-half-iteration fp32 error
+    assert relF(comp, golden_traces[name + "/components_f64"]) < 2e-4
+    assert relF(emb, golden_traces[name + "/user_emb_f64"]) < 2e-4
+
+
+@pytest.mark.parametrize("precision", ["float", "double"])
+@pytest.mark.parametrize("feedback,solver", [("implicit", "conjugate_gradient"), ("implicit", "cholesky"),
+                                             ("explicit", "conjugate_gradient"), ("explicit", "cholesky")])
+def test_wrmf_class_like_reference_tests(precision, feedback, solver):
+    """tests/testthat/test-wrmf.R:29-64: shapes, fit_transform(train) == transform(train), transform(cv) shape."""
+    M = wc.load_movielens()
+    train, cv = M[:900], M[900:]
+    model = WRMF(rank=8, lambda_=0.1, feedback=feedback, solver=solver, precision=precision, seed=1)
+    emb = model.fit_transform(train, n_iter=5, convergence_tol=-1)
+    assert emb.shape == (900, 8)
+    assert model.components.shape == (8, M.shape[1])
+    emb2 = model.transform(train)
+    assert relF(emb2, emb) < (3e-5 if precision == "float" else 1e-9)
+    assert model.transform(cv).shape == (cv.shape[0], 8)
+    assert np.all(np.isfinite(emb))
+
+
+def test_wrmf_rejects_what_the_reference_rejects():
+    M = wc.load_movielens()
+    with pytest.raises(ValueError):
+        WRMF(solver="lbfgs")
+    with pytest.raises(TypeError):
+        WRMF(cg_steps=3.0)
+    neg = M.copy().astype(np.float64)
+    neg.data[0] = -1.0
+    with pytest.raises(ValueError):
+        WRMF(rank=4, feedback="implicit", precision="float").fit_transform(neg, n_iter=1)
+    m = WRMF(rank=4, precision="float")
+    m.fit_transform(M[:50], n_iter=1)
+    with pytest.raises(ValueError):
+        m.transform(M[:10, :100])
+
+
+def test_larger_synthetic_vs_oracle_all_cg_paths():
+    """60k x 20k, 80 nnz/row, rank 128 (a C3-shaped slice): eigenbasis kernel, full-XtX kernel and the
+    streaming kernel against the fp32 oracle on the same generator output."""
+    n_user, n_item, nnz, k, lam = 60000, 20000, 80, 128, 0.1
+    ptr = np.zeros(n_user + 1, np.int32)
+    idx = np.zeros(n_user * nnz, np.int32)
+    v64 = np.zeros(n_user * nnz, np.float64)
+    L.check(L.lib().b200als_synth_csr_host(n_user, n_item, nnz, 42, 0, 0, L.vp(ptr), L.vp(idx), None, L.vp(v64)))
+    X = wc.det_factors(n_item, k, 901)
+    Y0 = wc.det_factors(n_user, k, 902)
+    G = oracle.gram(X, lam)
+    Yo = Y0.copy()
+    lo = oracle.als_implicit(ptr, idx, v64, X, Yo, G, lam, wc.CG, 3, oracle.max_threads())
+    for kernel in (1, 2, 3):
+        s = Session.synthetic(n_user, 0, n_user, n_item, nnz, 42, k, "implicit", L.CONJUGATE_GRADIENT, 3, True, lam, kernel)
+        s.set_factors(L.ITEMS, X)
+        s.set_factors(L.USERS, Y0)
+        loss = s.half_iteration(L.USERS)
+        Y = s.get_factors(L.USERS)
+        s.close()
+        assert relF(Y, Yo) < TOL_F32, kernel
+        assert abs(loss - lo) <= TOL_F32 * abs(lo), kernel
+
+
+def test_explicit_larger_synthetic_vs_oracle():
+    n_user, n_item, nnz, k, lam = 30000, 8000, 80, 128, 0.1
+    ptr = np.zeros(n_user + 1, np.int32)
+    idx = np.zeros(n_user * nnz, np.int32)
+    v64 = np.zeros(n_user * nnz, np.float64)
+    L.check(L.lib().b200als_synth_csr_host(n_user, n_item, nnz, 7, 1, 0, L.vp(ptr), L.vp(idx), None, L.vp(v64)))
+    X = wc.det_factors(n_item, k, 911)
+    Y0 = wc.det_factors(n_user, k, 912)
+    cnt = np.bincount(idx, minlength=n_item).astype(np.float32)
+    Yo = Y0.copy()
+    lo = oracle.als_explicit(ptr, idx, v64, X, Yo, cnt, lam, wc.CG, 3, True, oracle.max_threads())
+    Y = Y0.copy()
+    loss = als_explicit(ptr, idx, v64, X, Y, cnt, lam, wc.CG, 3, True)
+    assert relF(Y, Yo) < TOL_F32
+    assert abs(loss - lo) <= TOL_F32 * abs(lo)
+
+
+def test_unsupported_options_fail_loudly(cases):
+    c = cases["synth_cg_early_exit_k16"]
+    with pytest.raises(L.B200AlsError) as e:
+        als_implicit(c["ptr"], c["idx"], c["val"], c["X"], c["Y0"].copy(), 0.1, L.NNLS)
+    assert e.value.code == L.EUNSUPPORTED
+    with pytest.raises(L.B200AlsError) as e:
+        als_implicit(c["ptr"], c["idx"], c["val"], c["X"], c["Y0"].copy(), 0.1, L.CHOLESKY, with_user_item_bias=True)
+    assert e.value.code == L.EUNSUPPORTED
