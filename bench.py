@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py -- WRMF-implicit ALS user-updates/sec at rank 128 (BASELINE.json metric).
+
+A "step" is one USER half-iteration of implicit-feedback WRMF with the CG(3) solver over the whole
+synthetic matrix: XtX = I'I + lambda*I, (basis change), per-row CG solve of every user row, and -- when
+N > 1 -- the NCCL exchange that gives every rank the updated user factors.
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on; fits one GPU):
+10M x 1M CSR, 80 nnz/row, rank 128, CG(3), lambda 0.1.  N > 1: the same 10M users row-sharded
+(strong scaling), one process per GPU under torchrun.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Prints ONE JSON line on rank 0.  `value`: device-resident throughput (CUDA events on the engine's
+stream, max over ranks).  `e2e`: the same step through the stateless C-ABI call with HOST buffers
+(pinned; CSR values as R's doubles), H2D and D2H inside the timed region.  `roofline`: the per-row CG
+kernel against the measured HBM peak.  `cpu_baseline` / `--impl reference`: the reference's CPU path on
+this box's host cores (the only place the oracle is executed, as the thing being timed as a baseline).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_user, n_item, nnz_per_row, rank, cg_steps, lambda)
+    "c3": (10_000_000, 1_000_000, 80, 128, 3, 0.1),
+    "c3-small": (1_000_000, 1_000_000, 80, 128, 3, 0.1),   # ncu captures
+    "c3-tiny": (100_000, 50_000, 80, 128, 3, 0.1),         # CPU-side dry runs
+}
+BYTES_PER_ROW = lambda n, k: 4 * n * k + 8 * n + 4 + 4 * k + 4 * k   # 42,628 at n=80, k=128
+FLOPS_PER_ROW = lambda n, k, s: (s + 1) * (4 * n * k + 2 * k * k)
+
+
+def measured_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, device):
+        self.rows, self.device, self.proc = [], device, None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def host_csr(L, n_rows, n_item, nnz, seed, pinned=True, offset=0):
+    alloc = L.pinned_empty if pinned else (lambda shape, dt: np.empty(shape, dt))
+    ptr = alloc((n_rows + 1,), np.int32)
+    idx = alloc((n_rows * nnz,), np.int32)
+    val = alloc((n_rows * nnz,), np.float64)   # R's @x is double
+    L.check(L.lib().b200als_synth_csr_host(n_rows, n_item, nnz, seed, 0, offset, L.vp(ptr), L.vp(idx), None, L.vp(val)))
+    return ptr, idx, val
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores."""
+    if rank != 0:
+        return
+    import oracle
+    from rsparse_b200 import _lib as L
+    n_user, n_item, nnz, k, cg, lam = WORKLOADS[args.workload]
+    threads = oracle.max_threads()
+    sample = min(n_user, args.cpu_rows)
+    ptr = np.empty(sample + 1, np.int32)
+    idx = np.empty(sample * nnz, np.int32)
+    val = np.empty(sample * nnz, np.float64)
+    L.check(L.lib().b200als_synth_csr_host(sample, n_item, nnz, 42, 0, 0, L.vp(ptr), L.vp(idx), None, L.vp(val)))
+    rng = np.random.default_rng(0)
+    X = (rng.standard_normal((n_item, k), dtype=np.float32) / 100)
+    Y = (rng.standard_normal((sample, k), dtype=np.float32) / 100)
+    G = oracle.gram(X, lam, threads)
+    impls = ["oracle"] + (["ref"] if oracle.ref_available() else [])
+    # which implementation is "the reference" here: oracle/_ref is the reference's own source but linked against
+    # our naive mini_arma (no BLAS), so it understates what Armadillo+OpenBLAS would do; the port uses hand-written
+    # AVX2 loops.  Report the FASTER of the two as the reference arm and give both numbers.
+    speeds = {}
+    for impl in impls:
+        n_probe = min(sample, 100_000)
+        best_t = 1e30
+        for _rep in range(2):   # first pass warms caches / page tables
+            Yp = Y[:n_probe].copy()
+            t = time.perf_counter()
+            oracle.als_implicit(ptr[:n_probe + 1], idx[:ptr[n_probe]], val[:ptr[n_probe]], X, Yp, G, lam, 1, cg, threads, impl=impl)
+            best_t = min(best_t, time.perf_counter() - t)
+        speeds[impl] = n_probe / best_t
+    best = max(speeds, key=speeds.get)
+    for _ in range(args.warmup):
+        oracle.als_implicit(ptr, idx, val, X, Y, G, lam, 1, cg, threads, impl=best)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.als_implicit(ptr, idx, val, X, Y, G, lam, 1, cg, threads, impl=best)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    kind = "reference" if best == "ref" else "port"
+    sample_desc = ("first %d rows of the %dx%d/%d-nnz CSR against the full item matrix, XtX precomputed (not timed); "
+                   "probe on 100k rows: %s" % (sample, n_user, n_item, nnz,
+                                                ", ".join("%s %.0f rows/s" % (("oracle/_ref (reference source + mini_arma)" if i == "ref" else "oracle port (AVX2 loops)"), v) for i, v in speeds.items())))
+    out = {"impl": "reference", "metric": "WRMF-implicit ALS user-updates/sec at rank=128", "value": value,
+           "unit": "user-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "%s: %dx%d CSR, %d nnz/row, WRMF implicit rank=%d CG(%d), lambda=%g; CPU sample of %d rows"
+                      % (args.workload, n_user, n_item, nnz, k, cg, lam, sample)},
+           "cpu_baseline": {"value": value, "unit": "user-updates/s", "cores": threads, "kind": kind, "sample": sample_desc},
+           "e2e": {"value": value, "unit": "user-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("B200ALS_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 resident full-XtX, 3 resident eigenbasis")
+    ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="rows in the CPU baseline sample")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    from rsparse_b200 import parallel
+    rank, world, local_rank = parallel.env_rank_world()
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    from rsparse_b200 import Session
+    from rsparse_b200 import _lib as L
+    n_user, n_item, nnz, k, cg, lam = WORKLOADS[args.workload]
+    if L.device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device: libb200als.so has no CPU fallback")
+    L.check(L.lib().b200als_set_device(local_rank))
+    parallel.init_engine_comm()
+    begin, end = parallel.shard_range(n_user, rank, world)
+    n_local = end - begin
+
+    s = Session.synthetic(n_local, begin, n_user, n_item, nnz, 42, k, "implicit", L.CONJUGATE_GRADIENT, cg, True, lam,
+                          args.kernel)
+    s.randomize_factors(L.ITEMS, 1234, 0.01)
+    s.randomize_factors(L.USERS, 5678, 0.01)
+
+    for _ in range(args.warmup):
+        s.half_iteration(L.USERS)
+    sampler = ClockSampler(local_rank)
+    launches0 = L.lib().b200als_launch_count()
+    parallel.barrier()
+    sampler.start()
+    L.check(L.lib().b200als_timer_start())
+    parts = {"gram_ms": 0.0, "prep_ms": 0.0, "solve_ms": 0.0, "comm_ms": 0.0}
+    loss = None
+    for _ in range(args.steps):
+        loss = s.half_iteration(L.USERS)
+        for kk, v in s.last_timing().items():
+            parts[kk] += v
+    ms = C.c_float(0)
+    L.check(L.lib().b200als_timer_stop(C.byref(ms)))
+    clocks = sampler.stop()
+    parallel.barrier()
+    launches = int(L.lib().b200als_launch_count() - launches0)
+    ms_total = parallel.max_over_ranks(ms.value)
+    ms_per_step = ms_total / args.steps
+    value = n_user * args.steps / (ms_total / 1e3)
+
+    # roofline of the dominant kernel (als_cg_resident_kernel): algorithmic bytes / its own device time
+    hbm_peak, peak_src = measured_peaks()
+    solve_ms = parallel.max_over_ranks(parts["solve_ms"]) / args.steps
+    achieved = n_local * BYTES_PER_ROW(nnz, k) / (solve_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "als_cg_resident_kernel", "achieved": achieved, "peak": hbm_peak,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(args.workload),
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": n_local * BYTES_PER_ROW(nnz, k),
+                "kernel_ms": solve_ms, "fp32_tflops": n_local * FLOPS_PER_ROW(nnz, k, cg) / (solve_ms / 1e3) / 1e12}
+
+    # ---- e2e: stateless C-ABI call, host buffers, copies inside the timed region -----------------------
+    e2e = None
+    if not args.no_e2e:
+        from rsparse_b200 import als_implicit
+        ptr, idx, val = host_csr(L, n_local, n_item, nnz, 42, True, begin)
+        Xh = L.pinned_empty((n_item, k), np.float32)
+        Yh = L.pinned_empty((n_local, k), np.float32)
+        L.check(L.lib().b200als_get_factors(s._h, L.ITEMS, L.vp(Xh)))
+        Yfull = s.get_factors(L.USERS) if world == 1 else None
+        if Yfull is not None:
+            Yh[:] = Yfull
+            del Yfull
+        else:
+            Yh[:] = 0.01
+        als_implicit(ptr, idx, val, Xh, Yh, lam, L.CONJUGATE_GRADIENT, cg)   # warm-up (allocations, first touch)
+        parallel.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            als_implicit(ptr, idx, val, Xh, Yh, lam, L.CONJUGATE_GRADIENT, cg)
+        dt = parallel.max_over_ranks(time.perf_counter() - t0)
+        h2d = ptr.nbytes + idx.nbytes + val.nbytes + Xh.nbytes + Yh.nbytes
+        e2e = {"value": n_user * args.e2e_steps / dt, "unit": "user-updates/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(Yh.nbytes), "ms_per_step": 1e3 * dt / args.e2e_steps, "steps": args.e2e_steps,
+               "api": "b200als_als_implicit_float (stateless, host pointers, CSR values double as in R's dgCMatrix)"}
+
+    # ---- CPU baseline (rank 0, N = 1): the oracle timed on this box's host cores -------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import oracle
+        threads = oracle.max_threads()
+        sample = min(n_local, args.cpu_rows)
+        if args.no_e2e:
+            ptr, idx, val = host_csr(L, sample, n_item, nnz, 42, False, 0)
+            Xh = s.get_factors(L.ITEMS)
+        Yc = (np.random.default_rng(1).standard_normal((sample, k), dtype=np.float32) / 100)
+        G = oracle.gram(np.asarray(Xh), lam, threads)
+        nn = int(ptr[sample])
+        t0 = time.perf_counter()
+        oracle.als_implicit(ptr[:sample + 1], idx[:nn], val[:nn], np.asarray(Xh), Yc, G, lam, 1, cg, threads)
+        dt = time.perf_counter() - t0
+        cpu = {"value": sample / dt, "unit": "user-updates/s", "cores": threads, "kind": "port",
+               "sample": "oracle port (C++/OpenMP restatement of wrmf_implicit.hpp, AVX2) on the first %d rows of the "
+                         "same CSR against the full item matrix, %d threads, XtX precomputed" % (sample, threads),
+               "seconds": dt}
+
+    if rank == 0:
+        out = {"metric": "WRMF-implicit ALS user-updates/sec at rank=128", "value": value, "unit": "user-updates/s",
+               "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": "%s: %dx%d CSR, %d nnz/row, WRMF implicit rank=%d CG(%d) lambda=%g, user half-iteration"
+                                      % (args.workload, n_user, n_item, nnz, k, cg, lam),
+                          "parallelism": "rows sharded over %d GPU(s), NCCL exchange of updated factors" % world,
+                          "l2": "inputs larger than L2 (CSR %.1f GB + factors %.1f GB per step vs 126 MB L2); no flush needed"
+                                % (n_local * nnz * 8 / 1e9, (n_local + n_item) * k * 4 / 1e9),
+                          "kernel": args.kernel, "loss": loss},
+               "step_breakdown_ms": {kk: v / args.steps for kk, v in parts.items()},
+               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(out), flush=True)
+    s.close()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one als_cg_resident_kernel launch, from the committed
+# `ncu --set full` capture (profiles/); None until a capture for that workload exists.
+TRAFFIC_BYTES_PER_LAUNCH = {}
+
+if __name__ == "__main__":
+    main()

@@ -69,6 +69,15 @@ int b200als_version(void);
 int b200als_device_count(int* count);
 int b200als_set_device(int device);
 
+/* Host programs without their own CUDA binding (the R shim, bench.py): page-locked host buffers, a
+ * CUDA-event timer on the engine's stream (start: device sync + record; stop: record + sync, returns
+ * elapsed device milliseconds) and the number of kernels this library has launched so far. */
+int b200als_host_alloc(size_t bytes, void** out);
+int b200als_host_free(void* p);
+int b200als_timer_start(void);
+int b200als_timer_stop(float* ms);
+unsigned long long b200als_launch_count(void);
+
 /* ------------------------------------------------------------------------------------------------
  * 1. Stateless half-iteration calls -- same argument lists as the reference's Rcpp exports
  *    (src/wrmf_implicit.cpp:5-31, src/wrmf_explicit.cpp:5-27) with the S4/SEXP objects flattened:
@@ -139,6 +148,8 @@ int b200als_set_factors(b200als_session* s, int which, const float* host);
 int b200als_get_factors(b200als_session* s, int which, float* host);
 /* Initialise like R/model_WRMF.R:203-244: users ~ N(0,1)/100, items zero for CG / N(0,1)/100 else. */
 int b200als_init_factors(b200als_session* s, uint64_t seed);
+/* Fill one factor matrix with N(0,1)*scale on the device (synthetic benchmarks; basis is left as is). */
+int b200als_randomize_factors(b200als_session* s, int which, uint64_t seed, float scale);
 
 /* One half-iteration solving for `which` (B200ALS_ITEMS / B200ALS_USERS); solver_override < 0
  * keeps the session's solver, otherwise uses the given code (the avoid_cg path of

@@ -39,6 +39,11 @@ _PROTOS = {
     "b200als_version": (C.c_int, []),
     "b200als_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "b200als_set_device": (C.c_int, [C.c_int]),
+    "b200als_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "b200als_host_free": (C.c_int, [C.c_void_p]),
+    "b200als_timer_start": (C.c_int, []),
+    "b200als_timer_stop": (C.c_int, [C.POINTER(C.c_float)]),
+    "b200als_launch_count": (C.c_ulonglong, []),
     "b200als_als_implicit_float": (C.c_int, [C.POINTER(Csc), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                              C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_double, C.c_void_p,
                                              C.c_int, C.POINTER(C.c_double)]),
@@ -59,6 +64,7 @@ _PROTOS = {
     "b200als_set_factors": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "b200als_get_factors": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "b200als_init_factors": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "b200als_randomize_factors": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_float]),
     "b200als_half_iteration": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "b200als_fit": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.POINTER(C.c_int)]),
     "b200als_transform": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
@@ -122,3 +128,25 @@ def make_csc(n_rows, ptr, idx, val):
         val = np.ascontiguousarray(val, dtype=np.float64)
         s = Csc(int(n_rows), len(ptr) - 1, len(idx), vp(ptr), vp(idx), vp(val), None)
     return s, (ptr, idx, val)
+
+
+def pinned_empty(shape, dtype):
+    """numpy array over page-locked host memory from b200als_host_alloc (freed when garbage collected)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    p = C.c_void_p(None)
+    check(lib().b200als_host_alloc(n * dtype.itemsize, C.byref(p)))
+    buf = (C.c_char * (n * dtype.itemsize)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+    _pinned_keep[arr.ctypes.data] = p
+
+    return arr
+
+
+_pinned_keep = {}
+
+
+def pinned_free(arr):
+    p = _pinned_keep.pop(arr.ctypes.data, None)
+    if p is not None:
+        lib().b200als_host_free(p)

@@ -51,7 +51,11 @@ static int fail(int code, const std::string& msg) {
     if (rc__ != B200ALS_OK) return rc__; \
   } while (0)
 
+static unsigned long long g_launches = 0;  // kernels launched by this library (bench.py reports the delta)
+#define LAUNCHED() (++g_launches)
+
 extern "C" const char* b200als_last_error(void) { return g_err.c_str(); }
+extern "C" unsigned long long b200als_launch_count(void) { return g_launches; }
 extern "C" int b200als_version(void) { return B200ALS_VERSION; }
 extern "C" int b200als_device_count(int* count) {
   int n = 0;
@@ -247,7 +251,7 @@ static int upload_csc(const b200als_csc* A, CscDev<T>& D, cudaStream_t st) {
       const unsigned gs = (unsigned)((A->nnz + bs - 1) / bs);
       if (A->val_f64) convert_kernel<double, T><<<gs, bs, 0, st>>>(tmp.f64(), D.val.template as<T>(), A->nnz);
       else convert_kernel<float, T><<<gs, bs, 0, st>>>(tmp.f32(), D.val.template as<T>(), A->nnz);
-      CU(cudaGetLastError());
+      LAUNCHED(); CU(cudaGetLastError());
       CU(cudaStreamSynchronize(st));
     }
   }
@@ -269,10 +273,10 @@ static int run_gram(Ctx& c, const T* X, int k, long long n, double lambda, T* G,
   CU(c.gram_partials.ensure(sizeof(double) * (size_t)n_cta * n_tiles * kGramTile * kGramTile));
   gram_partial_kernel<T><<<dim3((unsigned)n_cta, (unsigned)n_tiles), 256, 0, c.stream>>>(X, k, n, rows_per,
                                                                                          c.gram_partials.f64(), nt1);
-  CU(cudaGetLastError());
+  LAUNCHED(); CU(cudaGetLastError());
   gram_reduce_kernel<T><<<(k * k + 255) / 256, 256, 0, c.stream>>>(c.gram_partials.f64(), (int)n_cta, n_tiles, k,
                                                                    lambda, G, G64);
-  CU(cudaGetLastError());
+  LAUNCHED(); CU(cudaGetLastError());
   return B200ALS_OK;
 }
 
@@ -296,7 +300,7 @@ static int classify_rows(Ctx& c, CscDev<T>& A) {
     classify_rows_kernel<<<(A.n_cols + 255) / 256, 256, 0, c.stream>>>(A.ptr.i32(), A.n_cols, kResMaxN,
                                                                       A.short_list.i32(), A.long_list.i32(),
                                                                       counts.i32());
-    CU(cudaGetLastError());
+    LAUNCHED(); CU(cudaGetLastError());
   }
   int h[3];
   CU(cudaMemcpyAsync(h, counts.p, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
@@ -312,7 +316,7 @@ template <typename T, int KPL>
 static int launch_cg_generic(Ctx& c, const SolveParams<T>& P, int n_work, int* grid_out) {
   const int grid = (int)std::min<long long>((long long)c.sm_count * 4, std::max(1, (n_work + 7) / 8));
   als_cg_generic_kernel<T, KPL><<<grid, 256, 0, c.stream>>>(P);
-  CU(cudaGetLastError());
+  LAUNCHED(); CU(cudaGetLastError());
   *grid_out = grid;
   return B200ALS_OK;
 }
@@ -362,7 +366,7 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
     else if (k <= 256) TRY((launch_cg_generic<T, 8>(c, P, n_work, &grid)));
     else return fail(B200ALS_EUNSUPPORTED, "rank > 256 is not supported");
     sum_partials_kernel<<<1, 32, 0, c.stream>>>(P.loss_partials, grid, c.loss_acc.f64(), 1);
-    CU(cudaGetLastError());
+    LAUNCHED(); CU(cudaGetLastError());
     return B200ALS_OK;
   };
 
@@ -376,9 +380,9 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
     const int grid = std::min(c.sm_count * per_sm, std::max(1, A.n_cols));
     CU(cudaMemsetAsync(c.ticket.p, 0, sizeof(unsigned long long), c.stream));
     als_chol_generic_kernel<T><<<grid, 256, smem, c.stream>>>(P);
-    CU(cudaGetLastError());
+    LAUNCHED(); CU(cudaGetLastError());
     sum_partials_kernel<<<1, 32, 0, c.stream>>>(P.loss_partials, grid, c.loss_acc.f64(), 1);
-    CU(cudaGetLastError());
+    LAUNCHED(); CU(cudaGetLastError());
     return B200ALS_OK;
   }
 
@@ -395,7 +399,7 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
   if constexpr (sizeof(T) == 4) {
     TRY(classify_rows(c, A));
     zero_empty_rows_kernel<T><<<(unsigned)(((long long)A.n_cols * k + 255) / 256), 256, 0, c.stream>>>(P.ptr, A.n_cols, k, Y);
-    CU(cudaGetLastError());
+    LAUNCHED(); CU(cudaGetLastError());
     if (A.n_short > 0) {
       ResidentParams R;
       R.ptr = P.ptr;
@@ -422,9 +426,9 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
         CU(cudaFuncSetAttribute(als_cg_resident_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         als_cg_resident_kernel<false><<<grid, kResThreads, smem, c.stream>>>(R);
       }
-      CU(cudaGetLastError());
+      LAUNCHED(); CU(cudaGetLastError());
       sum_partials_kernel<<<1, 32, 0, c.stream>>>(P.loss_partials, grid, c.loss_acc.f64(), 1);
-      CU(cudaGetLastError());
+      LAUNCHED(); CU(cudaGetLastError());
     }
     if (A.n_long > 0) {
       if (diag && !G) return fail(B200ALS_EINVAL, "rows longer than 80 need the full XtX for the streaming kernel");
@@ -445,9 +449,9 @@ static int finish_loss(Ctx& c, const T* X, int k, long long n_src, const T* cnt_
     const int grid = c.sm_count * 2;
     CU(c.reg_partials.ensure(sizeof(double) * (size_t)grid));
     sqnorm_kernel<T><<<grid, 256, 0, c.stream>>>(X, k, n_src, weighted ? cnt_X : nullptr, c.reg_partials.f64());
-    CU(cudaGetLastError());
+    LAUNCHED(); CU(cudaGetLastError());
     sum_partials_kernel<<<1, 32, 0, c.stream>>>(c.reg_partials.f64(), grid, c.loss_acc.f64() + 1, 0);
-    CU(cudaGetLastError());
+    LAUNCHED(); CU(cudaGetLastError());
   }
   double h[2] = {0, 0};
   int st = 0;
@@ -548,6 +552,36 @@ extern "C" int b200als_gram_float(const float* X, int rank, int64_t n, double la
   return B200ALS_OK;
 }
 
+// pinned host memory + device timers for host programs without a CUDA binding (bench.py, the R shim)
+extern "C" int b200als_host_alloc(size_t bytes, void** out) {
+  TRY(ctx().init());
+  if (!out) return fail(B200ALS_EINVAL, "null out");
+  CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return B200ALS_OK;
+}
+extern "C" int b200als_host_free(void* p) {
+  if (p) CU(cudaFreeHost(p));
+  return B200ALS_OK;
+}
+static cudaEvent_t g_t0 = nullptr, g_t1 = nullptr;
+extern "C" int b200als_timer_start(void) {
+  Ctx& c = ctx();
+  TRY(c.init());
+  if (!g_t0) { CU(cudaEventCreate(&g_t0)); CU(cudaEventCreate(&g_t1)); }
+  CU(cudaDeviceSynchronize());
+  CU(cudaEventRecord(g_t0, c.stream));
+  return B200ALS_OK;
+}
+extern "C" int b200als_timer_stop(float* ms) {
+  Ctx& c = ctx();
+  if (!g_t0 || !ms) return fail(B200ALS_EINVAL, "timer not started");
+  CU(cudaEventRecord(g_t1, c.stream));
+  CU(cudaEventSynchronize(g_t1));
+  CU(cudaDeviceSynchronize());
+  CU(cudaEventElapsedTime(ms, g_t0, g_t1));
+  return B200ALS_OK;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // 3. communicator (one process per GPU)
 // ------------------------------------------------------------------------------------------------------
@@ -639,7 +673,7 @@ static int session_alloc(b200als_session* s) {
   CU(s->Btmp.ensure(sizeof(double) * k * k));
   CU(s->Bf.ensure(sizeof(float) * k * k));
   set_identity_kernel<<<(unsigned)((k * k + 255) / 256), 256, 0, c.stream>>>(s->B64.f64(), (int)k);
-  CU(cudaGetLastError());
+  LAUNCHED(); CU(cudaGetLastError());
   s->basis_identity = true;
   for (auto& e : s->ev) CU(cudaEventCreate(&e));
   return B200ALS_OK;
@@ -666,7 +700,7 @@ static int session_counts(b200als_session* s) {
     const int other = 1 - w;
     count_idx_kernel<<<(unsigned)((s->csc[w].nnz + 255) / 256), 256, 0, c.stream>>>(s->csc[w].idx.i32(), s->csc[w].nnz,
                                                                                    s->cnt[other].f32());
-    CU(cudaGetLastError());
+    LAUNCHED(); CU(cudaGetLastError());
   }
   if (g_comm.world > 1) {
     for (int w = 0; w < 2; w++) {
@@ -748,7 +782,7 @@ static int rotate_matrix(Ctx& c, float* M, long long n, const float* R) {
   const long long blocks = (n + kRotRows - 1) / kRotRows;
   const int grid = (int)std::min<long long>(blocks, c.sm_count * 2);
   rotate_rows_kernel<<<grid, 256, smem, c.stream>>>(M, M, R, n);
-  CU(cudaGetLastError());
+  LAUNCHED(); CU(cudaGetLastError());
   return B200ALS_OK;
 }
 
@@ -760,7 +794,7 @@ extern "C" int b200als_set_factors(b200als_session* s, int which, const float* h
   CU(cudaMemcpyAsync(s->fac[which].p, host, sizeof(float) * (size_t)s->k * (size_t)n, cudaMemcpyHostToDevice, c.stream));
   if (!s->basis_identity) {
     convert_kk_kernel<<<(s->k * s->k + 255) / 256, 256, 0, c.stream>>>(s->B64.f64(), s->Bf.f32(), s->k, 0);
-    CU(cudaGetLastError());
+    LAUNCHED(); CU(cudaGetLastError());
     TRY(rotate_matrix(c, s->fac[which].f32(), n, s->Bf.f32()));
   }
   CU(cudaStreamSynchronize(c.stream));
@@ -775,7 +809,7 @@ static int export_rotated(b200als_session* s, const float* dev, long long n, flo
     CU(s->scratch.ensure(bytes));
     CU(cudaMemcpyAsync(s->scratch.p, dev, bytes, cudaMemcpyDeviceToDevice, c.stream));
     convert_kk_kernel<<<(s->k * s->k + 255) / 256, 256, 0, c.stream>>>(s->B64.f64(), s->Bf.f32(), s->k, 1);
-    CU(cudaGetLastError());
+    LAUNCHED(); CU(cudaGetLastError());
     TRY(rotate_matrix(c, s->scratch.f32(), n, s->Bf.f32()));
     CU(cudaMemcpyAsync(host, s->scratch.p, bytes, cudaMemcpyDeviceToHost, c.stream));
   }
@@ -793,17 +827,27 @@ extern "C" int b200als_init_factors(b200als_session* s, uint64_t seed) {
   if (!s) return fail(B200ALS_EINVAL, "null session");
   const long long nu = (long long)s->k * s->n_user, ni = (long long)s->k * s->n_item;
   if (nu) init_normal_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, c.stream>>>(s->fac[B200ALS_USERS].f32(), nu, seed, 0.01f);
-  CU(cudaGetLastError());
+  LAUNCHED(); CU(cudaGetLastError());
   if (s->opt.solver == B200ALS_CONJUGATE_GRADIENT) {
     CU(cudaMemsetAsync(s->fac[B200ALS_ITEMS].p, 0, sizeof(float) * (size_t)ni, c.stream));  // R/model_WRMF.R:217-230
   } else if (ni) {
     init_normal_kernel<<<(unsigned)((ni + 255) / 256), 256, 0, c.stream>>>(s->fac[B200ALS_ITEMS].f32(), ni,
                                                                            seed ^ 0xA5A5A5A5ull, 0.01f);
-    CU(cudaGetLastError());
+    LAUNCHED(); CU(cudaGetLastError());
   }
   set_identity_kernel<<<(s->k * s->k + 255) / 256, 256, 0, c.stream>>>(s->B64.f64(), s->k);
-  CU(cudaGetLastError());
+  LAUNCHED(); CU(cudaGetLastError());
   s->basis_identity = true;
+  CU(cudaStreamSynchronize(c.stream));
+  return B200ALS_OK;
+}
+
+extern "C" int b200als_randomize_factors(b200als_session* s, int which, uint64_t seed, float scale) {
+  Ctx& c = ctx();
+  if (!s || which < 0 || which > 1) return fail(B200ALS_EINVAL, "bad argument");
+  const long long n = (long long)s->k * ((which == B200ALS_ITEMS) ? s->n_item : s->n_user);
+  if (n) init_normal_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(s->fac[which].f32(), n, seed, scale);
+  LAUNCHED(); CU(cudaGetLastError());
   CU(cudaStreamSynchronize(c.stream));
   return B200ALS_OK;
 }
@@ -863,13 +907,13 @@ static int session_half(b200als_session* s, int which, int solver, float* Yout, 
   if (use_diag) {
     jacobi_eig_kernel<<<1, kJacobiThreads, 0, c.stream>>>(s->G64.f64(), s->Vt.f64(), s->k, s->Q.f32(),
                                                           s->diag.f32(), s->Btmp.f64(), 30);
-    CU(cudaGetLastError());
+    LAUNCHED(); CU(cudaGetLastError());
     // fixed <- fixed Q (whole matrix), solved slice <- slice Q, B <- B Q
     TRY(rotate_matrix(c, X, n_fixed, s->Q.f32()));
     TRY(rotate_matrix(c, Y, A.n_cols, s->Q.f32()));
     matmul_kk_kernel<<<(s->k * s->k + 255) / 256, 256, 0, c.stream>>>(s->B64.f64(), s->Btmp.f64(),
                                                                      s->Vt.f64(), s->k);
-    CU(cudaGetLastError());
+    LAUNCHED(); CU(cudaGetLastError());
     CU(cudaMemcpyAsync(s->B64.p, s->Vt.p, sizeof(double) * (size_t)s->k * s->k, cudaMemcpyDeviceToDevice, c.stream));
     s->basis_identity = false;
     diag = s->diag.f32();
@@ -999,7 +1043,7 @@ extern "C" int b200als_create_synthetic(b200als_session** out, int32_t n_user_lo
   synth_csr_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c.stream>>>(n_user_local, n_item, nnz_per_row, seed,
                                                                          s->opt.feedback == B200ALS_EXPLICIT, user_offset,
                                                                          A.ptr.i32(), A.idx.i32(), A.val.f32());
-  if (cudaGetLastError() != cudaSuccess) return bail(B200ALS_ECUDA, "synth kernel launch");
+  LAUNCHED(); if (cudaGetLastError() != cudaSuccess) return bail(B200ALS_ECUDA, "synth kernel launch");
   s->has[B200ALS_USERS] = true;
   s->shard_begin[B200ALS_USERS] = (int32_t)user_offset;
   s->shard_end[B200ALS_USERS] = (int32_t)user_offset + n_user_local;

@@ -1,0 +1,84 @@
+"""Host-side multi-GPU plumbing: one process per GPU (torchrun), rows sharded by contiguous
+blocks, NCCL communicator owned by libb200als.so.  torch.distributed is used
+only to hand the 128-byte NCCL id around and for barriers / max-over-ranks of timings."""
+import os
+
+import numpy as np
+
+
+def shard_range(n, rank, world):
+    """Contiguous block [begin, end) of n rows owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(int(n), int(world))
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def shard_by_nnz(ptr, world):
+    """Contiguous row blocks balanced by the nnz prefix sum (for skewed matrices): returns world+1 cut points."""
+    ptr = np.asarray(ptr, dtype=np.int64)
+    n = len(ptr) - 1
+    targets = ptr[-1] * np.arange(1, world, dtype=np.float64) / world
+    cuts = np.searchsorted(ptr, targets, side="left")
+    cuts = np.clip(cuts, 0, n)
+    return np.concatenate([[0], np.maximum.accumulate(cuts), [n]]).astype(np.int64)
+
+
+def env_rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def init_process_group(backend="gloo"):
+    """Join the torchrun rendezvous (MASTER_ADDR/MASTER_PORT from the environment)."""
+    import torch.distributed as dist
+    rank, world, _ = env_rank_world()
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world
+
+
+def broadcast_bytes(payload, src=0):
+    """Broadcast a bytes object from `src` to every rank over torch.distributed."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return payload
+    n = 128
+    t = torch.zeros(n, dtype=torch.uint8)
+    if dist.get_rank() == src:
+        t = torch.frombuffer(bytearray(payload), dtype=torch.uint8).clone()
+    dist.broadcast(t, src=src)
+    return bytes(t.numpy().tobytes())
+
+
+def init_engine_comm():
+    """Create the engine's NCCL communicator across the torchrun ranks (call after set_device)."""
+    import ctypes as C
+
+    from . import _lib as L
+    rank, world = init_process_group("gloo")
+    if world == 1:
+        return rank, world
+    buf = (C.c_char * 128)()
+    if rank == 0:
+        L.check(L.lib().b200als_comm_unique_id(buf))
+    uid = broadcast_bytes(bytes(buf.raw), 0)
+    buf2 = (C.c_char * 128).from_buffer_copy(uid)
+    L.check(L.lib().b200als_comm_init(buf2, rank, world))
+    return rank, world
+
+
+def max_over_ranks(x):
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(x)
+    t = torch.tensor([float(x)], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier():
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
