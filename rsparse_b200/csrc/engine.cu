@@ -5,7 +5,8 @@
 //   session / fit     R/model_WRMF.R:173-360 (outer loop :318-338, final transform_ :412-452)
 // No CPU fallback anywhere: every compute entry point needs a CUDA device.
 #include <cuda_runtime.h>
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: the library is resolved lazily with dlopen (see NcclApi)
 
 #include <algorithm>
 #include <cmath>
@@ -42,7 +43,7 @@ static int fail(int code, const std::string& msg) {
   do {                                                                                             \
     ncclResult_t e__ = (expr);                                                                     \
     if (e__ != ncclSuccess)                                                                        \
-      return fail(B200ALS_ENCCL, std::string(#expr) + ": " + ncclGetErrorString(e__) + " @" +      \
+      return fail(B200ALS_ENCCL, std::string(#expr) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(e__) : "nccl error") + " @" +      \
                                      __FILE__ + ":" + std::to_string(__LINE__));                   \
   } while (0)
 #define TRY(expr)                \
@@ -585,6 +586,35 @@ extern "C" int b200als_timer_stop(float* ms) {
 // ------------------------------------------------------------------------------------------------------
 // 3. communicator (one process per GPU)
 // ------------------------------------------------------------------------------------------------------
+// NCCL is bound at run time, not link time: a host process may already carry a different libnccl.so.2 (PyTorch
+// bundles its own), and single-GPU users need none at all.  dlopen() returns whichever copy is already loaded.
+struct NcclApi {
+  void* h = nullptr;
+  decltype(&::ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&::ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&::ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&::ncclAllReduce) AllReduce = nullptr;
+  decltype(&::ncclAllGather) AllGather = nullptr;
+  decltype(&::ncclBroadcast) Broadcast = nullptr;
+  decltype(&::ncclGroupStart) GroupStart = nullptr;
+  decltype(&::ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&::ncclGetErrorString) GetErrorString = nullptr;
+  int load() {
+    if (h) return B200ALS_OK;
+    h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(B200ALS_ENCCL, std::string("cannot load libnccl.so.2: ") + dlerror());
+#define B200ALS_SYM(name)                                                                     \
+    name = reinterpret_cast<decltype(name)>(dlsym(h, "nccl" #name));                        \
+    if (!name) return fail(B200ALS_ENCCL, "libnccl.so.2 lacks nccl" #name)
+    B200ALS_SYM(GetUniqueId); B200ALS_SYM(CommInitRank); B200ALS_SYM(CommDestroy); B200ALS_SYM(AllReduce);
+    B200ALS_SYM(AllGather); B200ALS_SYM(Broadcast); B200ALS_SYM(GroupStart); B200ALS_SYM(GroupEnd);
+    B200ALS_SYM(GetErrorString);
+#undef B200ALS_SYM
+    return B200ALS_OK;
+  }
+};
+static NcclApi g_nccl;
 struct Comm {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
@@ -594,25 +624,27 @@ static Comm g_comm;
 extern "C" int b200als_comm_unique_id(void* id_out) {
   static_assert(sizeof(ncclUniqueId) == B200ALS_UNIQUE_ID_BYTES, "ncclUniqueId size");
   if (!id_out) return fail(B200ALS_EINVAL, "null id");
+  TRY(g_nccl.load());
   ncclUniqueId id;
-  NC(ncclGetUniqueId(&id));
+  NC(g_nccl.GetUniqueId(&id));
   std::memcpy(id_out, &id, sizeof(id));
   return B200ALS_OK;
 }
 extern "C" int b200als_comm_init(const void* id, int rank, int world_size) {
   if (!id || world_size < 1 || rank < 0 || rank >= world_size) return fail(B200ALS_EINVAL, "bad communicator arguments");
   TRY(ctx().init());
+  TRY(g_nccl.load());
   if (g_comm.comm) return fail(B200ALS_EINVAL, "communicator already initialised");
   ncclUniqueId uid;
   std::memcpy(&uid, id, sizeof(uid));
-  NC(ncclCommInitRank(&g_comm.comm, world_size, uid, rank));
+  NC(g_nccl.CommInitRank(&g_comm.comm, world_size, uid, rank));
   g_comm.rank = rank;
   g_comm.world = world_size;
   return B200ALS_OK;
 }
 extern "C" int b200als_comm_destroy(void) {
   if (g_comm.comm) {
-    ncclCommDestroy(g_comm.comm);
+    g_nccl.CommDestroy(g_comm.comm);
     g_comm.comm = nullptr;
   }
   g_comm.rank = 0;
@@ -705,7 +737,7 @@ static int session_counts(b200als_session* s) {
   if (g_comm.world > 1) {
     for (int w = 0; w < 2; w++) {
       const int32_t n = (w == B200ALS_ITEMS) ? s->n_item : s->n_user;
-      if (s->has[1 - w]) NC(ncclAllReduce(s->cnt[w].p, s->cnt[w].p, (size_t)n, ncclFloat, ncclSum, g_comm.comm, c.stream));
+      if (s->has[1 - w]) NC(g_nccl.AllReduce(s->cnt[w].p, s->cnt[w].p, (size_t)n, ncclFloat, ncclSum, g_comm.comm, c.stream));
     }
   }
   return B200ALS_OK;
@@ -742,7 +774,7 @@ extern "C" int b200als_create(b200als_session** out, const b200als_csc* c_ui, co
       DevBuf t;
       if (t.ensure(sizeof(long long)) != cudaSuccess) { rc = fail(B200ALS_ECUDA, "alloc"); break; }
       cudaMemcpyAsync(t.p, &nnz, sizeof(nnz), cudaMemcpyHostToDevice, c.stream);
-      if (ncclAllReduce(t.p, t.p, 1, ncclInt64, ncclSum, g_comm.comm, c.stream) != ncclSuccess) { rc = fail(B200ALS_ENCCL, "allreduce nnz"); break; }
+      if (g_nccl.AllReduce(t.p, t.p, 1, ncclInt64, ncclSum, g_comm.comm, c.stream) != ncclSuccess) { rc = fail(B200ALS_ENCCL, "allreduce nnz"); break; }
       cudaMemcpyAsync(&nnz, t.p, sizeof(nnz), cudaMemcpyDeviceToHost, c.stream);
       cudaStreamSynchronize(c.stream);
     }
@@ -862,18 +894,18 @@ static int exchange_slices(b200als_session* s, int which) {
   CU(d.ensure(sizeof(int32_t) * 2 * g_comm.world));
   int32_t mine[2] = {s->shard_begin[which], s->shard_end[which]};
   CU(cudaMemcpyAsync(d.i32() + 2 * g_comm.rank, mine, sizeof(mine), cudaMemcpyHostToDevice, c.stream));
-  NC(ncclAllGather(d.i32() + 2 * g_comm.rank, d.p, 2, ncclInt32, g_comm.comm, c.stream));
+  NC(g_nccl.AllGather(d.i32() + 2 * g_comm.rank, d.p, 2, ncclInt32, g_comm.comm, c.stream));
   CU(cudaMemcpyAsync(ranges.data(), d.p, sizeof(int32_t) * 2 * g_comm.world, cudaMemcpyDeviceToHost, c.stream));
   CU(cudaStreamSynchronize(c.stream));
   float* M = s->fac[which].f32();
-  NC(ncclGroupStart());
+  NC(g_nccl.GroupStart());
   for (int r = 0; r < g_comm.world; r++) {
     const size_t cnt = (size_t)(ranges[2 * r + 1] - ranges[2 * r]) * (size_t)s->k;
     if (cnt == 0) continue;
     float* p = M + (size_t)ranges[2 * r] * s->k;
-    NC(ncclBroadcast(p, p, cnt, ncclFloat, r, g_comm.comm, c.stream));
+    NC(g_nccl.Broadcast(p, p, cnt, ncclFloat, r, g_comm.comm, c.stream));
   }
-  NC(ncclGroupEnd());
+  NC(g_nccl.GroupEnd());
   return B200ALS_OK;
 }
 
@@ -928,7 +960,7 @@ static int session_half(b200als_session* s, int which, int solver, float* Yout, 
   double rows_sum = 0.0;
   {
     double h = 0.0;
-    if (g_comm.world > 1) NC(ncclAllReduce(c.loss_acc.p, c.loss_acc.p, 1, ncclDouble, ncclSum, g_comm.comm, c.stream));
+    if (g_comm.world > 1) NC(g_nccl.AllReduce(c.loss_acc.p, c.loss_acc.p, 1, ncclDouble, ncclSum, g_comm.comm, c.stream));
     CU(cudaMemcpyAsync(&h, c.loss_acc.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     CU(cudaStreamSynchronize(c.stream));
     rows_sum = h;

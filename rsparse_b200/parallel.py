@@ -56,9 +56,10 @@ def init_engine_comm():
     import ctypes as C
 
     from . import _lib as L
-    rank, world = init_process_group("gloo")
+    rank, world, _ = env_rank_world()
     if world == 1:
-        return rank, world
+        return rank, world       # single GPU: neither torch nor NCCL is touched
+    rank, world = init_process_group("gloo")
     buf = (C.c_char * 128)()
     if rank == 0:
         L.check(L.lib().b200als_comm_unique_id(buf))
@@ -69,6 +70,8 @@ def init_engine_comm():
 
 
 def max_over_ranks(x):
+    if env_rank_world()[1] == 1:
+        return float(x)
     import torch
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size() == 1:
@@ -79,6 +82,8 @@ def max_over_ranks(x):
 
 
 def barrier():
+    if env_rank_world()[1] == 1:
+        return
     import torch.distributed as dist
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()
