@@ -30,6 +30,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+ITEM_SCALE, ITEM_DECAY = 0.1, 0.5
+
 WORKLOADS = {
     # name: (n_user, n_item, nnz_per_row, rank, cg_steps, lambda)
     "c3": (10_000_000, 1_000_000, 80, 128, 3, 0.1),
@@ -114,7 +116,9 @@ def run_reference(args, rank, world):
     val = np.empty(sample * nnz, np.float64)
     L.check(L.lib().b200als_synth_csr_host(sample, n_item, nnz, 42, 0, 0, L.vp(ptr), L.vp(idx), None, L.vp(val)))
     rng = np.random.default_rng(0)
-    X = (rng.standard_normal((n_item, k), dtype=np.float32) / 100)
+    # same input distribution as the GPU arm (see main()): trained-like item factors, R-initialised user factors
+    X = rng.standard_normal((n_item, k), dtype=np.float32) * (ITEM_SCALE * (1.0 + np.arange(k, dtype=np.float32)) ** -ITEM_DECAY)
+    X = np.ascontiguousarray(X, dtype=np.float32)
     Y = (rng.standard_normal((sample, k), dtype=np.float32) / 100)
     G = oracle.gram(X, lam, threads)
     impls = ["oracle"] + (["ref"] if oracle.ref_available() else [])
@@ -186,8 +190,12 @@ def main():
 
     s = Session.synthetic(n_local, begin, n_user, n_item, nnz, 42, k, "implicit", L.CONJUGATE_GRADIENT, cg, True, lam,
                           args.kernel)
-    s.randomize_factors(L.ITEMS, 1234, 0.01)
-    s.randomize_factors(L.USERS, 5678, 0.01)
+    # Inputs: users at R's initialisation scale N(0,1)/100 (R/model_WRMF.R:203-215); items "trained-like":
+    # N(0,1) * 0.1 * (1+f)^-0.5, so XtX has a ~128:1 spectrum and CG takes all its steps.  (i.i.d. item factors
+    # make XtX ~ c*I: every row then leaves the CG loop after ONE step through `rsnew < CG_TOL`,
+    # wrmf_implicit.hpp:27, which would flatter the throughput by ~1.7x.)
+    s.randomize_factors(L.ITEMS, 1234, ITEM_SCALE, ITEM_DECAY)
+    s.randomize_factors(L.USERS, 5678, 0.01, 0.0)
 
     for _ in range(args.warmup):
         s.half_iteration(L.USERS)
@@ -260,7 +268,16 @@ def main():
         t0 = time.perf_counter()
         oracle.als_implicit(ptr[:sample + 1], idx[:nn], val[:nn], np.asarray(Xh), Yc, G, lam, 1, cg, threads)
         dt = time.perf_counter() - t0
+        # evidence that the workload exercises all CG steps: result of CG(3) vs CG(2) on 2000 rows
+        m = min(2000, sample)
+        Ya, Yb = Yc[:m].copy(), Yc[:m].copy()
+        Ya[:] = 0.01
+        Yb[:] = 0.01
+        oracle.als_implicit(ptr[:m + 1], idx[:ptr[m]], val[:ptr[m]], np.asarray(Xh), Ya, G, lam, 1, cg, threads)
+        oracle.als_implicit(ptr[:m + 1], idx[:ptr[m]], val[:ptr[m]], np.asarray(Xh), Yb, G, lam, 1, cg - 1, threads)
+        step_effect = float(np.linalg.norm(Ya - Yb) / np.linalg.norm(Ya))
         cpu = {"value": sample / dt, "unit": "user-updates/s", "cores": threads, "kind": "port",
+               "last_cg_step_changes_result_by_relF": step_effect,
                "sample": "oracle port (C++/OpenMP restatement of wrmf_implicit.hpp, AVX2) on the first %d rows of the "
                          "same CSR against the full item matrix, %d threads, XtX precomputed" % (sample, threads),
                "seconds": dt}

@@ -148,8 +148,10 @@ int b200als_set_factors(b200als_session* s, int which, const float* host);
 int b200als_get_factors(b200als_session* s, int which, float* host);
 /* Initialise like R/model_WRMF.R:203-244: users ~ N(0,1)/100, items zero for CG / N(0,1)/100 else. */
 int b200als_init_factors(b200als_session* s, uint64_t seed);
-/* Fill one factor matrix with N(0,1)*scale on the device (synthetic benchmarks; basis is left as is). */
-int b200als_randomize_factors(b200als_session* s, int which, uint64_t seed, float scale);
+/* Fill one factor matrix with N(0,1) * scale * (1+f)^-decay (f = feature index) on the device.  decay > 0
+ * gives a trained-like, ill-conditioned XtX so that the fixed-step CG really takes all its steps (i.i.d.
+ * factors make XtX ~ c*I and CG exits after one step through the rsnew < CG_TOL test). */
+int b200als_randomize_factors(b200als_session* s, int which, uint64_t seed, float scale, float decay);
 
 /* One half-iteration solving for `which` (B200ALS_ITEMS / B200ALS_USERS); solver_override < 0
  * keeps the session's solver, otherwise uses the given code (the avoid_cg path of

@@ -64,7 +64,7 @@ _PROTOS = {
     "b200als_set_factors": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "b200als_get_factors": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "b200als_init_factors": (C.c_int, [C.c_void_p, C.c_uint64]),
-    "b200als_randomize_factors": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_float]),
+    "b200als_randomize_factors": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_float, C.c_float]),
     "b200als_half_iteration": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "b200als_fit": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.POINTER(C.c_int)]),
     "b200als_transform": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),

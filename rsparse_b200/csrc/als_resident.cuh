@@ -10,10 +10,12 @@
 //   * the two mat-vecs of a CG step are fused into one sweep over the registers:
 //       u_j = x_j . p   (4 FMA/lane + one transposing halving reduction per warp: 21 SHFL for 20 rows)
 //       w_j = (c_j - 1) u_j ;  acc += w_j x_j   (80 FMA/lane), then a 4-way cross-warp sum in smem;
-//   * the NEXT row's tile (and its warm-start y) is prefetched while this row computes: warp 0 issues
-//     one 512-byte cp.async.bulk (TMA engine, SASS UBLKCP) per gathered row into a 40.5 KB shared
-//     memory slot, completion by mbarrier complete_tx; the CSR indices for the row after that are
-//     software-pipelined through registers => no thread ever waits on a dependent HBM load chain;
+//   * the NEXT row's tile (and its warm-start y) is prefetched while this row computes: every warp stages
+//     its own 20 gathered rows with one 512-byte cp.async.bulk (TMA engine, SASS UBLKCP) per owner lane
+//     into its own 10.5 KB shared-memory slot, completion by a per-warp mbarrier (complete_tx); the CSR
+//     indices / confidences of the row after that and the row pointers of the one after that travel
+//     through registers => no thread ever waits on a dependent HBM load chain, the four warps do
+//     identical work and meet only at the one cross-warp sum per sweep;
 //   * XtX p: either the session has rotated both factor matrices into the eigenbasis of XtX (kDiag:
 //     XtX p = d (.) p, 4 FMA/lane -- see eig.cuh), or (kFullG) each warp multiplies a 32-column slab
 //     of XtX from L1/L2 and the slabs are summed by the same cross-warp reduction;
@@ -52,13 +54,11 @@ struct ResidentParams {
 };
 
 struct __align__(128) ResidentSmem {
-  float tile[(kResMaxN + 1) * kResK];      // gathered rows + the warm-start y in row kResMaxN
+  // per-warp tile slot: rows 0..19 = this warp's gathered rows (item j = w + 4q), row 20 = the warm-start y
+  float tile[kResWarps][(kResIPW + 1) * kResK];
   float vbuf[2][kResWarps][kResK];         // cross-warp partial sums (double buffered per sweep)
   float wbuf[kResWarps][32];               // per-warp w_j broadcast
-  int meta_idx[2][kResMaxN];               // CSR indices of the row after next / next
-  float meta_val[2][kResMaxN];
-  int meta_n[2];
-  uint64_t bar;                            // mbarrier for the tile slot
+  uint64_t bar[kResWarps];                 // one mbarrier per warp slot
   double red[32];
 };
 
@@ -180,53 +180,55 @@ __global__ void __launch_bounds__(kResThreads, 3) als_cg_resident_kernel(Residen
   const int lane = lane_id(), w = warp_id(), tid = threadIdx.x;
   const bool implicit = (P.feedback == 0);
   const int stride = gridDim.x;
-  const int slot = resident_owner_slot(lane);
+  const int slot = resident_owner_slot(lane);      // gathered-row slot this lane owns after the halving reduce
+  const int my_j = (slot >= 0) ? (w + kResWarps * slot) : (1 << 30);  // its position within the CSR row
+  float* my_tile = &S.tile[w][0];
+  uint64_t* my_bar = &S.bar[w];
 
   auto valid = [&](int i) -> bool { return (long long)blockIdx.x + (long long)i * stride < (long long)P.n_list; };
   auto row_of = [&](int i) -> int {  // i-th row of this CTA (caller checks valid(i))
     const long long t = (long long)blockIdx.x + (long long)i * stride;
     return P.row_list ? __ldg(P.row_list + t) : (int)t;
   };
-  // warp 0: issue the bulk copies of row `r` whose indices sit in meta buffer b
-  auto issue_tile = [&](int r, int b) {
-    const int n = S.meta_n[b];
-    if (lane == 0) mbar_expect_tx(&S.bar, (uint32_t)(n + 1) * kResRowBytes);
+  // Every warp stages ITS OWN 20 gathered rows (+ its own copy of the warm-start y) with one 512-byte bulk
+  // copy per owner lane, so the four warps do identical work and never wait for a producer warp.
+  auto issue_tile = [&](int row, int n, int my_idx) {
+    const int nw = (n > w) ? (n - w + kResWarps - 1) / kResWarps : 0;
+    if (lane == 0) mbar_expect_tx(my_bar, (uint32_t)(nw + 1) * kResRowBytes);
     __syncwarp();
-    for (int j = lane; j < n; j += 32)
-      bulk_g2s(&S.tile[j * kResK], P.X + (size_t)S.meta_idx[b][j] * kResK, kResRowBytes, &S.bar);
-    if (lane == 0) bulk_g2s(&S.tile[kResMaxN * kResK], P.Y + (size_t)r * kResK, kResRowBytes, &S.bar);
-  };
-  // warp 0: blocking fetch of the CSR slice of row r into meta buffer b (prologue only)
-  auto fetch_meta_blocking = [&](int r, int b) {
-    const int p1 = P.ptr[r], n = P.ptr[r + 1] - p1;
-    for (int j = lane; j < n; j += 32) {
-      S.meta_idx[b][j] = __ldg(P.idx + p1 + j);
-      S.meta_val[b][j] = __ldg(P.val + p1 + j);
-    }
-    if (lane == 0) S.meta_n[b] = n;
+    if (my_j < n) bulk_g2s(my_tile + slot * kResK, P.X + (size_t)my_idx * kResK, kResRowBytes, my_bar);
+    if (lane == 0) bulk_g2s(my_tile + kResIPW * kResK, P.Y + (size_t)row * kResK, kResRowBytes, my_bar);
   };
 
-  if (tid == 0) {
-    mbar_init(&S.bar, 1);
-    mbar_fence_init();
-  }
+  if (tid < kResWarps) mbar_init(&S.bar[tid], 1);
+  if (tid == 0) mbar_fence_init();
   __syncthreads();
-  // ---- prologue (warp 0): row 0 tile in flight, row 1 indices in smem, row 2 CSR range and row 3 id in
-  //      registers.  From then on every global load warp 0 issues is consumed one row later. -------------
-  int rid0 = -1, rid1 = -1, rid2 = -1, rid3 = -1;  // warp 0: ids of rows i .. i+3
-  int pf_p1 = 0, pf_n = 0;                          // warp 0: CSR range of row i+2
-  if (w == 0) {
-    if (valid(0)) {
-      rid0 = row_of(0);
-      fetch_meta_blocking(rid0, 0);
-      __syncwarp();
-      issue_tile(rid0, 0);
-    }
-    if (valid(1)) { rid1 = row_of(1); fetch_meta_blocking(rid1, 1); }
-    if (valid(2)) { rid2 = row_of(2); pf_p1 = P.ptr[rid2]; pf_n = P.ptr[rid2 + 1] - pf_p1; }
-    if (valid(3)) rid3 = row_of(3);
+
+  // ---- software pipeline state (per warp, in registers; every global load is consumed one row later) ----
+  //   row i   : n0, cq (confidence of my slot)                         -- tile landing / landed
+  //   row i+1 : rid1, n1, idx1, val1                                    -- bulk copies issued at the start of row i
+  //   row i+2 : rid2, p2, n2 known; idx2/val2 loaded during row i
+  //   row i+3 : rid3 known; CSR range loaded during row i
+  //   row i+4 : id loaded during row i (only when a row list is used)
+  int rid0 = -1, rid1 = -1, rid2 = -1, rid3 = -1;
+  int n0 = 0, n1 = 0, n2 = 0, p2 = 0, idx1 = 0;
+  float cq = 0.f, val1 = 0.f;
+  if (valid(0)) {
+    rid0 = row_of(0);
+    const int p = __ldg(P.ptr + rid0);
+    n0 = __ldg(P.ptr + rid0 + 1) - p;
+    int idx0 = 0;
+    if (my_j < n0) { idx0 = __ldg(P.idx + p + my_j); cq = __ldg(P.val + p + my_j); }
+    issue_tile(rid0, n0, idx0);
   }
-  __syncthreads();
+  if (valid(1)) {
+    rid1 = row_of(1);
+    const int p = __ldg(P.ptr + rid1);
+    n1 = __ldg(P.ptr + rid1 + 1) - p;
+    if (my_j < n1) { idx1 = __ldg(P.idx + p + my_j); val1 = __ldg(P.val + p + my_j); }
+  }
+  if (valid(2)) { rid2 = row_of(2); p2 = __ldg(P.ptr + rid2); n2 = __ldg(P.ptr + rid2 + 1) - p2; }
+  if (valid(3)) rid3 = row_of(3);
 
   float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
   if (!kFullG && implicit) dg = ldg_f4(P.diag + lane * 4);
@@ -234,43 +236,25 @@ __global__ void __launch_bounds__(kResThreads, 3) als_cg_resident_kernel(Residen
   int sweep = 0;
 
   for (int i = 0; valid(i); i++) {
-    const int b = i & 1;
-    const int n = S.meta_n[b];
-    // ---- tile -> registers ------------------------------------------------------------------------
-    mbar_wait(&S.bar, (uint32_t)(i & 1));
+    const int n = n0;
+    // ---- my 20 rows: shared memory -> registers ----------------------------------------------------------
+    mbar_wait(my_bar, (uint32_t)(i & 1));
     float4 xt[kResIPW];
 #pragma unroll
     for (int q = 0; q < kResIPW; q++) {
       const int j = w + kResWarps * q;
-      xt[q] = (j < n) ? *reinterpret_cast<const float4*>(&S.tile[j * kResK + lane * 4]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      xt[q] = (j < n) ? *reinterpret_cast<const float4*>(my_tile + q * kResK + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    float4 x = *reinterpret_cast<const float4*>(&S.tile[kResMaxN * kResK + lane * 4]);
-    float cq = 0.0f;
-    if (slot >= 0) {
-      const int j = w + kResWarps * slot;
-      if (j < n) cq = S.meta_val[b][j];
-    }
-    __syncthreads();  // slot and meta[b] are free from here on
-    // ---- producer duties (warp 0; nothing here waits on memory) -------------------------------------
-    int pf_idx[3] = {0, 0, 0};
-    float pf_val[3] = {0.f, 0.f, 0.f};
-    int nx_p1 = 0, nx_p2 = 0, rid4 = -1;
-    if (w == 0) {
-      if (valid(i + 1)) issue_tile(rid1, b ^ 1);
-      if (valid(i + 2)) {
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          const int j = lane + 32 * c;
-          if (j < pf_n) {
-            pf_idx[c] = __ldg(P.idx + pf_p1 + j);
-            pf_val[c] = __ldg(P.val + pf_p1 + j);
-          }
-        }
-      }
-      if (valid(i + 3)) { nx_p1 = __ldg(P.ptr + rid3); nx_p2 = __ldg(P.ptr + rid3 + 1); }
-      if (valid(i + 4)) rid4 = row_of(i + 4);
-    }
-    // ---- CG -------------------------------------------------------------------------------------
+    float4 x = *reinterpret_cast<const float4*>(my_tile + kResIPW * kResK + lane * 4);
+    __syncwarp();  // my slot is free again
+    // ---- prefetch (nothing here waits on memory) ----------------------------------------------------------
+    if (valid(i + 1)) issue_tile(rid1, n1, idx1);
+    int idx2 = 0, p3 = 0, p3e = 0, rid4 = -1;
+    float val2 = 0.f;
+    if (valid(i + 2) && my_j < n2) { idx2 = __ldg(P.idx + p2 + my_j); val2 = __ldg(P.val + p2 + my_j); }
+    if (valid(i + 3)) { p3 = __ldg(P.ptr + rid3); p3e = __ldg(P.ptr + rid3 + 1); }
+    if (valid(i + 4)) rid4 = row_of(i + 4);
+    // ---- CG ---------------------------------------------------------------------------------------------
     const float lam_use = implicit ? P.lambda : (P.lambda * (P.dynamic_lambda ? (float)n : 1.0f));
     float u_own;
     float4 v = resident_sweep<kFullG>(xt, x, cq, implicit ? 0 : 2, slot, S, sweep++, P.G, u_own);
@@ -299,16 +283,16 @@ __global__ void __launch_bounds__(kResThreads, 3) als_cg_resident_kernel(Residen
       r.x = fmaf(-a, Ap.x, r.x); r.y = fmaf(-a, Ap.y, r.y); r.z = fmaf(-a, Ap.z, r.z); r.w = fmaf(-a, Ap.w, r.w);
       uy = fmaf(a, u_own, uy);
       const float rsnew = warp_sum(dot4(r, r));
-      if (rsnew < (float)B200ALS_CG_TOL) break;
+      if (rsnew < (float)B200ALS_CG_TOL) break;   // identical in all four warps (same data, same order)
       const float bt = __fdiv_rn(rsnew, rsold);
       p.x = fmaf(p.x, bt, r.x); p.y = fmaf(p.y, bt, r.y); p.z = fmaf(p.z, bt, r.z); p.w = fmaf(p.w, bt, r.w);
       rsold = rsnew;
     }
     if (w == 0) *reinterpret_cast<float4*>(P.Y + (size_t)rid0 * kResK + lane * 4) = x;
-    // ---- loss ------------------------------------------------------------------------------------
+    // ---- loss ---------------------------------------------------------------------------------------------
     {
       float l = 0.0f;
-      if (slot >= 0 && (w + kResWarps * slot) < n) {
+      if (my_j < n) {
         const float d = implicit ? (1.0f - uy) : (cq - uy);
         l = implicit ? d * d * cq : d * d;
       }
@@ -316,21 +300,11 @@ __global__ void __launch_bounds__(kResThreads, 3) als_cg_resident_kernel(Residen
       if (w == 0) l = fmaf(lam_use, warp_sum(dot4(x, x)), l);
       warp_loss += (double)l;
     }
-    // ---- retire the software pipeline stage: indices of row i+2 -> meta[b] -------------------------------
-    if (w == 0) {
-      if (valid(i + 2)) {
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          const int j = lane + 32 * c;
-          if (j < pf_n) { S.meta_idx[b][j] = pf_idx[c]; S.meta_val[b][j] = pf_val[c]; }
-        }
-        if (lane == 0) S.meta_n[b] = pf_n;
-      }
-      pf_p1 = nx_p1;
-      pf_n = nx_p2 - nx_p1;
-      rid0 = rid1; rid1 = rid2; rid2 = rid3; rid3 = rid4;
-    }
-    __syncthreads();  // meta[b] visible to all before it is read as "row i+2"
+    // ---- advance the pipeline ------------------------------------------------------------------------------
+    n0 = n1; cq = val1; rid0 = rid1;
+    n1 = n2; idx1 = idx2; val1 = val2; rid1 = rid2;
+    p2 = p3; n2 = p3e - p3; rid2 = rid3;
+    rid3 = rid4;
   }
   const double tot = block_sum_double((lane == 0) ? warp_loss : 0.0, S.red);
   if (tid == 0) P.loss_partials[blockIdx.x] = tot;

@@ -170,9 +170,12 @@ __global__ void synth_csr_kernel(int32_t n_rows, int32_t n_cols, int32_t nnz_per
   synth_entry(r + row_offset, j, n_cols, nnz_per_row, seed, explicit_values, &idx[e], &val[e]);
 }
 // factor init: N(0,1)/100 from a counter-based Box-Muller (R/model_WRMF.R:203-215, src/utils.cpp:131-143)
-__global__ void init_normal_kernel(float* __restrict__ out, long long n, uint64_t seed, float scale) {
+// `decay` > 0 gives feature f the extra scale (1+f)^-decay: a trained-like, ill-conditioned Gram
+__global__ void init_normal_kernel(float* __restrict__ out, long long n, uint64_t seed, float scale, int k = 1,
+                                   float decay = 0.f) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (decay != 0.f) scale *= powf(1.0f + (float)(i % k), -decay);
   const uint64_t h1 = synth_hash(seed ^ (uint64_t)(2 * i)), h2 = synth_hash(seed ^ (uint64_t)(2 * i + 1));
   const float u1 = ((float)((h1 >> 40) & 0xFFFFFF) + 1.0f) / 16777217.0f;
   const float u2 = (float)((h2 >> 40) & 0xFFFFFF) / 16777216.0f;
@@ -399,8 +402,10 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
   }
   if constexpr (sizeof(T) == 4) {
     TRY(classify_rows(c, A));
-    zero_empty_rows_kernel<T><<<(unsigned)(((long long)A.n_cols * k + 255) / 256), 256, 0, c.stream>>>(P.ptr, A.n_cols, k, Y);
-    LAUNCHED(); CU(cudaGetLastError());
+    if (A.n_empty > 0) {
+      zero_empty_rows_kernel<T><<<(unsigned)(((long long)A.n_cols * k + 255) / 256), 256, 0, c.stream>>>(P.ptr, A.n_cols, k, Y);
+      LAUNCHED(); CU(cudaGetLastError());
+    }
     if (A.n_short > 0) {
       ResidentParams R;
       R.ptr = P.ptr;
@@ -874,11 +879,11 @@ extern "C" int b200als_init_factors(b200als_session* s, uint64_t seed) {
   return B200ALS_OK;
 }
 
-extern "C" int b200als_randomize_factors(b200als_session* s, int which, uint64_t seed, float scale) {
+extern "C" int b200als_randomize_factors(b200als_session* s, int which, uint64_t seed, float scale, float decay) {
   Ctx& c = ctx();
   if (!s || which < 0 || which > 1) return fail(B200ALS_EINVAL, "bad argument");
   const long long n = (long long)s->k * ((which == B200ALS_ITEMS) ? s->n_item : s->n_user);
-  if (n) init_normal_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(s->fac[which].f32(), n, seed, scale);
+  if (n) init_normal_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(s->fac[which].f32(), n, seed, scale, s->k, decay);
   LAUNCHED(); CU(cudaGetLastError());
   CU(cudaStreamSynchronize(c.stream));
   return B200ALS_OK;
@@ -937,8 +942,11 @@ static int session_half(b200als_session* s, int which, int solver, float* Yout, 
     if (o.kernel != 3 && (A.n_long > 0 || (long long)A.n_cols * g_comm.world < 50000)) use_diag = false;
   }
   if (use_diag) {
-    jacobi_eig_kernel<<<1, kJacobiThreads, 0, c.stream>>>(s->G64.f64(), s->Vt.f64(), s->k, s->Q.f32(),
-                                                          s->diag.f32(), s->Btmp.f64(), 30);
+    const size_t jsm = sizeof(double) * (size_t)s->k * s->k;
+    const int a_in_smem = (jsm + 8192 <= c.smem_optin) ? 1 : 0;
+    if (a_in_smem) CU(cudaFuncSetAttribute(jacobi_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm));
+    jacobi_eig_kernel<<<1, kJacobiThreads, a_in_smem ? jsm : 0, c.stream>>>(s->G64.f64(), s->Vt.f64(), s->k, s->Q.f32(),
+                                                                          s->diag.f32(), s->Btmp.f64(), 30, a_in_smem);
     LAUNCHED(); CU(cudaGetLastError());
     // fixed <- fixed Q (whole matrix), solved slice <- slice Q, B <- B Q
     TRY(rotate_matrix(c, X, n_fixed, s->Q.f32()));

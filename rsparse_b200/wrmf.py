@@ -88,8 +88,8 @@ class Session:
     def init_factors(self, seed):
         L.check(L.lib().b200als_init_factors(self._h, int(seed)))
 
-    def randomize_factors(self, which, seed, scale=0.01):
-        L.check(L.lib().b200als_randomize_factors(self._h, which, int(seed), float(scale)))
+    def randomize_factors(self, which, seed, scale=0.01, decay=0.0):
+        L.check(L.lib().b200als_randomize_factors(self._h, which, int(seed), float(scale), float(decay)))
 
     def set_shard(self, which, begin, end):
         L.check(L.lib().b200als_set_shard(self._h, which, int(begin), int(end)))

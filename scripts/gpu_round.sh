@@ -8,11 +8,11 @@ export PYTHONUNBUFFERED=1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > $OUT/nvsmi.txt 2>&1
 echo "== pytest -m gpu"; timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee $OUT/pytest_gpu.txt
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee $OUT/smoke.txt
-echo "== bench c3 default"; timeout 900 python bench.py 2>&1 | tail -3 | tee $OUT/bench_c3.json
+echo "== bench c3 default"; timeout 900 python bench.py 2>&1 | tail -3 | tee $OUT/bench_c3.json | cut -c1-2600
 for K in 2 1; do
-  echo "== bench c3 kernel=$K"; timeout 600 python bench.py --kernel $K --steps 3 --no-e2e --no-cpu 2>&1 | tail -1 | tee $OUT/bench_c3_kernel$K.json
+  echo "== bench c3 kernel=$K"; timeout 600 python bench.py --kernel $K --steps 3 --no-e2e --no-cpu 2>&1 | tail -1 | cut -c1-1400 | tee $OUT/bench_c3_kernel$K.json
 done
-echo "== reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -1 | tee $OUT/bench_reference.json
+echo "== reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -1 | tee $OUT/bench_reference.json | cut -c1-1200
 echo "== ncu launch list (same command as the bench, fewer steps)"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > $OUT/launches_bench.log 2>&1

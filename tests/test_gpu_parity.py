@@ -179,11 +179,15 @@ def test_larger_synthetic_vs_oracle_all_cg_paths():
     idx = np.zeros(n_user * nnz, np.int32)
     v64 = np.zeros(n_user * nnz, np.float64)
     L.check(L.lib().b200als_synth_csr_host(n_user, n_item, nnz, 42, 0, 0, L.vp(ptr), L.vp(idx), None, L.vp(v64)))
-    X = wc.det_factors(n_item, k, 901)
+    # trained-like item factors (decaying spectrum): every row takes all three CG steps
+    X = np.ascontiguousarray(wc.det_factors(n_item, k, 901, 0.1) * (1.0 + np.arange(k, dtype=np.float32)) ** -0.5)
     Y0 = wc.det_factors(n_user, k, 902)
     G = oracle.gram(X, lam)
     Yo = Y0.copy()
     lo = oracle.als_implicit(ptr, idx, v64, X, Yo, G, lam, wc.CG, 3, oracle.max_threads())
+    Y2 = Y0[:500].copy()
+    oracle.als_implicit(ptr[:501], idx[:ptr[500]], v64[:ptr[500]], X, Y2, G, lam, wc.CG, 2, 1)
+    assert relF(Y2, Yo[:500]) > 1e-4   # the third CG step matters on this input
     for kernel in (1, 2, 3):
         s = Session.synthetic(n_user, 0, n_user, n_item, nnz, 42, k, "implicit", L.CONJUGATE_GRADIENT, 3, True, lam, kernel)
         s.set_factors(L.ITEMS, X)
