@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("B200ALS_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 resident full-XtX, 3 resident eigenbasis")
+    ap.add_argument("--stage", type=int, default=0, help="resident-kernel tile staging: 0 default, 1 cp.async.bulk, 2 cp.async")
     ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="rows in the CPU baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
@@ -189,7 +190,7 @@ def main():
     n_local = end - begin
 
     s = Session.synthetic(n_local, begin, n_user, n_item, nnz, 42, k, "implicit", L.CONJUGATE_GRADIENT, cg, True, lam,
-                          args.kernel)
+                          args.kernel, args.stage)
     # Inputs: users at R's initialisation scale N(0,1)/100 (R/model_WRMF.R:203-215); items "trained-like":
     # N(0,1) * 0.1 * (1+f)^-0.5, so XtX has a ~128:1 spectrum and CG takes all its steps.  (i.i.d. item factors
     # make XtX ~ c*I: every row then leaves the CG loop after ONE step through `rsnew < CG_TOL`,
@@ -291,7 +292,7 @@ def main():
                           "parallelism": "rows sharded over %d GPU(s), NCCL exchange of updated factors" % world,
                           "l2": "inputs larger than L2 (CSR %.1f GB + factors %.1f GB per step vs 126 MB L2); no flush needed"
                                 % (n_local * nnz * 8 / 1e9, (n_local + n_item) * k * 4 / 1e9),
-                          "kernel": args.kernel, "loss": loss},
+                          "kernel": args.kernel, "stage": args.stage, "loss": loss},
                "step_breakdown_ms": {kk: v / args.steps for kk, v in parts.items()},
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(out), flush=True)

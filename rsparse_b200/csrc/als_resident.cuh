@@ -57,32 +57,40 @@ struct __align__(128) ResidentSmem {
   // per-warp tile slot: rows 0..19 = this warp's gathered rows (item j = w + 4q), row 20 = the warm-start y
   float tile[kResWarps][(kResIPW + 1) * kResK];
   float vbuf[2][kResWarps][kResK];         // cross-warp partial sums (double buffered per sweep)
-  float wbuf[kResWarps][32];               // per-warp w_j broadcast
+  float wbuf[kResWarps][32];               // per-warp w_j broadcast: 4 blocks of 5, each padded to 8 floats
   uint64_t bar[kResWarps];                 // one mbarrier per warp slot
   double red[32];
 };
 
 // Transposing halving reduction: on entry lane L holds t[0..N) partial dot products, on exit the lane
 // whose bits select slot q holds the full 32-lane sum of t[q]; returns it (0 for padding lanes).
+// Levels with kSwapFree = true assume the registers of lanes whose bit M is set were LOADED with their two
+// halves swapped (see resident_natural_slot), so "keep the low registers, send the high registers" is the
+// same instruction stream for every lane -- no selects.  Odd-sized levels fall back to selects.
 template <int N>
 struct Halver {
-  template <int M>
+  template <int M, int kSwapFreeLevels>
   static __device__ __forceinline__ float run(float (&t)[N], int lane) {
     constexpr int H = (N + 1) / 2;
-    const bool upper = (lane & M) != 0;
     float o[H];
+    if constexpr (kSwapFreeLevels > 0 && (N % 2 == 0)) {
 #pragma unroll
-    for (int v = 0; v < H; v++) {
-      const float lo = t[v];
-      const float hi = (v + H < N) ? t[v + H] : 0.0f;
-      const float send = upper ? lo : hi;
-      const float keep = upper ? hi : lo;
-      o[v] = keep + __shfl_xor_sync(kFull, send, M);
+      for (int v = 0; v < H; v++) o[v] = t[v] + __shfl_xor_sync(kFull, t[v + H], M);
+    } else {
+      const bool upper = (lane & M) != 0;
+#pragma unroll
+      for (int v = 0; v < H; v++) {
+        const float lo = t[v];
+        const float hi = (v + H < N) ? t[v + H] : 0.0f;
+        const float send = upper ? lo : hi;
+        const float keep = upper ? hi : lo;
+        o[v] = keep + __shfl_xor_sync(kFull, send, M);
+      }
     }
     if constexpr (M == 1) {
       return o[0];
     } else {
-      return Halver<H>::template run<M / 2>(o, lane);
+      return Halver<H>::template run<M / 2, (kSwapFreeLevels > 0 ? kSwapFreeLevels - 1 : 0)>(o, lane);
     }
   }
 };
@@ -93,6 +101,17 @@ __device__ __forceinline__ int resident_owner_slot(int lane) {
   const int in5 = 3 * b2 + in3;         // index within the group of 5 (valid < 5)
   if (in3 >= 3 || in5 >= 5) return -1;
   return 10 * b4 + 5 * b3 + in5;
+}
+// lane that owns slot q (inverse of resident_owner_slot)
+__host__ __device__ constexpr int resident_owner_lane(int q) {
+  const int b4 = q / 10, r = q % 10, b3 = r / 5, in5 = r % 5, b2 = in5 / 3, in3 = in5 % 3;
+  return 16 * b4 + 8 * b3 + 4 * b2 + 2 * (in3 / 2) + (in3 % 2);
+}
+// Which gathered-row slot lane L keeps in register q: the two halving levels 20->10 and 10->5 are select-free
+// because lanes with bit 4 (bit 3) set hold the two halves (quarters) of their registers swapped.
+__device__ __forceinline__ int resident_natural_slot(int q, int lane) {
+  const int h1 = q / 10, r1 = q % 10, h2 = r1 / 5, r2 = r1 % 5;
+  return 10 * (h1 ^ ((lane >> 4) & 1)) + 5 * (h2 ^ ((lane >> 3) & 1)) + r2;
 }
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
@@ -108,7 +127,7 @@ __device__ __forceinline__ float4 resident_sweep(const float4 (&xt)[kResIPW], co
   float t[kResIPW];
 #pragma unroll
   for (int q = 0; q < kResIPW; q++) t[q] = dot4(xt[q], vec);
-  const float u = Halver<kResIPW>::template run<16>(t, lane);
+  const float u = Halver<kResIPW>::template run<16, 2>(t, lane);
   u_own = u;
   float wq;
   switch (mode) {
@@ -117,16 +136,18 @@ __device__ __forceinline__ float4 resident_sweep(const float4 (&xt)[kResIPW], co
     case 2: wq = cq - u; break;
     default: wq = u; break;
   }
-  if (slot >= 0) S.wbuf[w][slot] = wq;
+  if (slot >= 0) S.wbuf[w][(slot / 5) * 8 + (slot % 5)] = wq;
   __syncwarp();
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int bsel = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);  // this lane's register blocks hold natural blocks blk ^ bsel
 #pragma unroll
-  for (int q4 = 0; q4 < kResIPW / 4; q4++) {
-    const float4 wv = *reinterpret_cast<const float4*>(&S.wbuf[w][q4 * 4]);
-    const float ws[4] = {wv.x, wv.y, wv.z, wv.w};
+  for (int blk = 0; blk < 4; blk++) {
+    const float* wp = &S.wbuf[w][(blk ^ bsel) * 8];
+    const float4 wv = *reinterpret_cast<const float4*>(wp);
+    const float ws[5] = {wv.x, wv.y, wv.z, wv.w, wp[4]};
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const float4& x = xt[q4 * 4 + i];
+    for (int i = 0; i < 5; i++) {
+      const float4& x = xt[blk * 5 + i];
       acc.x = fmaf(ws[i], x.x, acc.x);
       acc.y = fmaf(ws[i], x.y, acc.y);
       acc.z = fmaf(ws[i], x.z, acc.z);
@@ -173,7 +194,9 @@ __device__ __forceinline__ float4 resident_sweep(const float4 (&xt)[kResIPW], co
   return v;
 }
 
-template <bool kFullG>
+// kStage: 0 = cp.async.bulk (TMA engine, UBLKCP; one 512-byte copy per owner lane, serialised through the
+// uniform datapath), 1 = cp.async 16 B per thread (LDGSTS; one warp-wide instruction per gathered row).
+template <bool kFullG, int kStage>
 __global__ void __launch_bounds__(kResThreads, 3) als_cg_resident_kernel(ResidentParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ResidentSmem& S = *reinterpret_cast<ResidentSmem*>(smem_raw);
@@ -193,14 +216,24 @@ __global__ void __launch_bounds__(kResThreads, 3) als_cg_resident_kernel(Residen
   // Every warp stages ITS OWN 20 gathered rows (+ its own copy of the warm-start y) with one 512-byte bulk
   // copy per owner lane, so the four warps do identical work and never wait for a producer warp.
   auto issue_tile = [&](int row, int n, int my_idx) {
-    const int nw = (n > w) ? (n - w + kResWarps - 1) / kResWarps : 0;
-    if (lane == 0) mbar_expect_tx(my_bar, (uint32_t)(nw + 1) * kResRowBytes);
-    __syncwarp();
-    if (my_j < n) bulk_g2s(my_tile + slot * kResK, P.X + (size_t)my_idx * kResK, kResRowBytes, my_bar);
-    if (lane == 0) bulk_g2s(my_tile + kResIPW * kResK, P.Y + (size_t)row * kResK, kResRowBytes, my_bar);
+    if constexpr (kStage == 0) {
+      const int nw = (n > w) ? (n - w + kResWarps - 1) / kResWarps : 0;
+      if (lane == 0) mbar_expect_tx(my_bar, (uint32_t)(nw + 1) * kResRowBytes);
+      __syncwarp();
+      if (my_j < n) bulk_g2s(my_tile + slot * kResK, P.X + (size_t)my_idx * kResK, kResRowBytes, my_bar);
+      if (lane == 0) bulk_g2s(my_tile + kResIPW * kResK, P.Y + (size_t)row * kResK, kResRowBytes, my_bar);
+    } else {
+#pragma unroll
+      for (int q = 0; q < kResIPW; q++) {
+        const int src = __shfl_sync(kFull, my_idx, resident_owner_lane(q));
+        if (w + kResWarps * q < n) cp_async_16(my_tile + q * kResK + lane * 4, P.X + (size_t)src * kResK + lane * 4);
+      }
+      cp_async_16(my_tile + kResIPW * kResK + lane * 4, P.Y + (size_t)row * kResK + lane * 4);
+      cp_async_mbar_arrive_noinc(my_bar);
+    }
   };
 
-  if (tid < kResWarps) mbar_init(&S.bar[tid], 1);
+  if (tid < kResWarps) mbar_init(&S.bar[tid], kStage == 0 ? 1 : 32);
   if (tid == 0) mbar_fence_init();
   __syncthreads();
 
@@ -242,8 +275,9 @@ __global__ void __launch_bounds__(kResThreads, 3) als_cg_resident_kernel(Residen
     float4 xt[kResIPW];
 #pragma unroll
     for (int q = 0; q < kResIPW; q++) {
-      const int j = w + kResWarps * q;
-      xt[q] = (j < n) ? *reinterpret_cast<const float4*>(my_tile + q * kResK + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int nat = resident_natural_slot(q, lane);   // register q holds gathered row w + 4*nat (see Halver)
+      xt[q] = (w + kResWarps * nat < n) ? *reinterpret_cast<const float4*>(my_tile + nat * kResK + lane * 4)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float4 x = *reinterpret_cast<const float4*>(my_tile + kResIPW * kResK + lane * 4);
     __syncwarp();  // my slot is free again

@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(kJacobiThreads) jacobi_eig_kernel(double* __re
                                                                     int max_sweeps, int a_in_smem) {
   extern __shared__ __align__(16) unsigned char jacobi_smem[];
   double* A = a_in_smem ? reinterpret_cast<double*>(jacobi_smem) : Ag;
+  const int lda = a_in_smem ? (k + 1) : k;   // odd leading dimension: the column rotations are bank-conflict free
   __shared__ double s_c[128], s_s[128];
   __shared__ int s_p[128], s_q[128];
   __shared__ double s_red[32];
@@ -38,14 +39,14 @@ __global__ void __launch_bounds__(kJacobiThreads) jacobi_eig_kernel(double* __re
   const int npad = 2 * np;          // even number of players
   for (int e = tid; e < k * k; e += kJacobiThreads) {
     Vt[e] = ((e / k) == (e % k)) ? 1.0 : 0.0;
-    if (a_in_smem) A[e] = Ag[e];
+    if (a_in_smem) A[(e / k) * lda + (e % k)] = Ag[e];
   }
   __syncthreads();
   for (int sweep = 0; sweep < max_sweeps; sweep++) {
     // convergence: off(A)^2 <= 1e-26 * diag(A)^2 (off/diag <= 1e-13: far below the fp32 consumers' precision)
     double off = 0.0, dg = 0.0;
     for (int e = tid; e < k * k; e += kJacobiThreads) {
-      const double v = A[e];
+      const double v = A[(e / k) * lda + (e % k)];
       if ((e / k) == (e % k)) dg += v * v; else off += v * v;
     }
     const double toff = block_sum_double(off, s_red);
@@ -62,9 +63,9 @@ __global__ void __launch_bounds__(kJacobiThreads) jacobi_eig_kernel(double* __re
         if (p > q) { const int t = p; p = q; q = t; }
         double c = 1.0, s = 0.0;
         if (q < k) {
-          const double apq = A[p * k + q];
+          const double apq = A[p * lda + q];
           if (apq != 0.0) {
-            const double tau = (A[q * k + q] - A[p * k + p]) / (2.0 * apq);
+            const double tau = (A[q * lda + q] - A[p * lda + p]) / (2.0 * apq);
             const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
             c = 1.0 / sqrt(1.0 + t * t);
             s = t * c;
@@ -81,9 +82,9 @@ __global__ void __launch_bounds__(kJacobiThreads) jacobi_eig_kernel(double* __re
         const int p = s_p[pr], q = s_q[pr];
         if (q < 0) continue;
         const double c = s_c[pr], s = s_s[pr];
-        const double ap = A[i * k + p], aq = A[i * k + q];
-        A[i * k + p] = c * ap - s * aq;
-        A[i * k + q] = s * ap + c * aq;
+        const double ap = A[i * lda + p], aq = A[i * lda + q];
+        A[i * lda + p] = c * ap - s * aq;
+        A[i * lda + q] = s * ap + c * aq;
       }
       __syncthreads();
       // A <- J' A (rows p, q) ;  Vt <- J' Vt  (i.e. V <- V J)
@@ -92,9 +93,9 @@ __global__ void __launch_bounds__(kJacobiThreads) jacobi_eig_kernel(double* __re
         const int p = s_p[pr], q = s_q[pr];
         if (q < 0) continue;
         const double c = s_c[pr], s = s_s[pr];
-        const double ap = A[p * k + j], aq = A[q * k + j];
-        A[p * k + j] = c * ap - s * aq;
-        A[q * k + j] = s * ap + c * aq;
+        const double ap = A[p * lda + j], aq = A[q * lda + j];
+        A[p * lda + j] = c * ap - s * aq;
+        A[q * lda + j] = s * ap + c * aq;
         const double vp = Vt[p * k + j], vq = Vt[q * k + j];
         Vt[p * k + j] = c * vp - s * vq;
         Vt[q * k + j] = s * vp + c * vq;
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(kJacobiThreads) jacobi_eig_kernel(double* __re
     Qf[e] = (float)v;
     if (Q64) Q64[e] = v;
   }
-  for (int e = tid; e < k; e += kJacobiThreads) df[e] = (float)A[e * k + e];
+  for (int e = tid; e < k; e += kJacobiThreads) df[e] = (float)A[e * lda + e];
 }
 
 // C = A * B (k x k, row-major, double) -- basis bookkeeping B <- B Q ; trivially small.

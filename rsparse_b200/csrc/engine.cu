@@ -290,7 +290,9 @@ static int run_gram(Ctx& c, const T* X, int k, long long n, double lambda, T* G,
 struct HalfOpts {
   int feedback, solver, cg_steps, dynamic_lambda, kernel;
   double lambda;
+  int stage = 0;  // tile staging of the resident kernel: 0 default, 1 cp.async.bulk (UBLKCP), 2 cp.async (LDGSTS)
 };
+constexpr int kDefaultStage = 0;
 
 template <typename T>
 static int classify_rows(Ctx& c, CscDev<T>& A) {
@@ -425,13 +427,15 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
       const int grid = std::min(c.sm_count * 3, A.n_short);
       const size_t smem = sizeof(ResidentSmem);
       const bool full_g = (o.feedback == B200ALS_IMPLICIT) && !diag;
-      if (full_g) {
-        CU(cudaFuncSetAttribute(als_cg_resident_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        als_cg_resident_kernel<true><<<grid, kResThreads, smem, c.stream>>>(R);
-      } else {
-        CU(cudaFuncSetAttribute(als_cg_resident_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        als_cg_resident_kernel<false><<<grid, kResThreads, smem, c.stream>>>(R);
-      }
+      auto launch = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, kResThreads, smem, c.stream>>>(R);
+        return cudaSuccess;
+      };
+      const int stage = (o.stage == 1) ? 0 : (o.stage == 2 ? 1 : kDefaultStage);
+      if (full_g) CU(stage == 0 ? launch(als_cg_resident_kernel<true, 0>) : launch(als_cg_resident_kernel<true, 1>));
+      else CU(stage == 0 ? launch(als_cg_resident_kernel<false, 0>) : launch(als_cg_resident_kernel<false, 1>));
       LAUNCHED(); CU(cudaGetLastError());
       sum_partials_kernel<<<1, 32, 0, c.stream>>>(P.loss_partials, grid, c.loss_acc.f64(), 1);
       LAUNCHED(); CU(cudaGetLastError());
@@ -924,7 +928,7 @@ static int session_half(b200als_session* s, int which, int solver, float* Yout, 
   float* X = s->fac[fixed].f32();
   float* Yfull = s->fac[which].f32();
   float* Y = Yout ? Yout : (Yfull + (size_t)s->shard_begin[which] * s->k);
-  HalfOpts o{s->opt.feedback, solver, s->opt.cg_steps, s->opt.dynamic_lambda, s->opt.kernel, s->opt.lambda};
+  HalfOpts o{s->opt.feedback, solver, s->opt.cg_steps, s->opt.dynamic_lambda, s->opt.kernel, s->opt.lambda, s->opt.reserved[0]};
   CscDev<float>& A = s->csc[which];
   const bool implicit = (o.feedback == B200ALS_IMPLICIT);
   CU(cudaEventRecord(s->ev[0], c.stream));
@@ -942,7 +946,7 @@ static int session_half(b200als_session* s, int which, int solver, float* Yout, 
     if (o.kernel != 3 && (A.n_long > 0 || (long long)A.n_cols * g_comm.world < 50000)) use_diag = false;
   }
   if (use_diag) {
-    const size_t jsm = sizeof(double) * (size_t)s->k * s->k;
+    const size_t jsm = sizeof(double) * (size_t)s->k * (s->k + 1);
     const int a_in_smem = (jsm + 8192 <= c.smem_optin) ? 1 : 0;
     if (a_in_smem) CU(cudaFuncSetAttribute(jacobi_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm));
     jacobi_eig_kernel<<<1, kJacobiThreads, a_in_smem ? jsm : 0, c.stream>>>(s->G64.f64(), s->Vt.f64(), s->k, s->Q.f32(),

@@ -29,7 +29,7 @@ class Session:
     """Thin RAII wrapper over the session API of include/b200als.h."""
 
     def __init__(self, c_ui, c_iu, n_user, n_item, rank, feedback, solver, cg_steps=3, dynamic_lambda=True,
-                 lambda_=0.0, kernel=0):
+                 lambda_=0.0, kernel=0, stage=0):
         self._h = C.c_void_p(None)
         o = L.Options()
         L.lib().b200als_default_options(C.byref(o))
@@ -39,6 +39,7 @@ class Session:
         o.dynamic_lambda = int(bool(dynamic_lambda))
         o.lambda_ = float(lambda_)
         o.kernel = int(kernel)
+        o.reserved[0] = int(stage)   # resident-kernel tile staging: 0 default, 1 cp.async.bulk, 2 cp.async
         self.rank, self.n_user, self.n_item = int(rank), int(n_user), int(n_item)
         keep = []
         s_ui = s_iu = None
@@ -54,13 +55,14 @@ class Session:
 
     @classmethod
     def synthetic(cls, n_user_local, user_offset, n_user_global, n_item, nnz_per_row, seed, rank, feedback="implicit",
-                  solver=L.CONJUGATE_GRADIENT, cg_steps=3, dynamic_lambda=True, lambda_=0.1, kernel=0):
+                  solver=L.CONJUGATE_GRADIENT, cg_steps=3, dynamic_lambda=True, lambda_=0.1, kernel=0, stage=0):
         self = cls.__new__(cls)
         self._h = C.c_void_p(None)
         o = L.Options()
         L.lib().b200als_default_options(C.byref(o))
         o.feedback = L.IMPLICIT if feedback == "implicit" else L.EXPLICIT
         o.solver, o.cg_steps, o.dynamic_lambda, o.lambda_, o.kernel = int(solver), int(cg_steps), int(dynamic_lambda), float(lambda_), int(kernel)
+        o.reserved[0] = int(stage)
         self.rank, self.n_user, self.n_item = int(rank), int(n_user_global), int(n_item)
         L.check(L.lib().b200als_create_synthetic(C.byref(self._h), int(n_user_local), int(user_offset), int(n_user_global),
                                                  int(n_item), int(nnz_per_row), int(seed), int(rank), C.byref(o)))

@@ -58,24 +58,25 @@ def test_f32_engine_vs_reference_golden(name, xtx, cases, golden_half):
     assert np.all(Y[empty] == 0)
 
 
-def _session_for(c, kernel, solver=None):
+def _session_for(c, kernel, solver=None, stage=0):
     n_src, k = c["X"].shape
     n_tgt = c["Y0"].shape[0]
     s = Session(None, (c["ptr"], c["idx"], c["val"]), n_tgt, n_src, k, c["feedback"], c["solver"] if solver is None else solver,
-                c["cg_steps"], c["dynamic_lambda"], c["lam"], kernel)
+                c["cg_steps"], c["dynamic_lambda"], c["lam"], kernel, stage)
     s.set_factors(L.ITEMS, c["X"])
     s.set_factors(L.USERS, c["Y0"])
     return s
 
 
 @pytest.mark.parametrize("name", [n for n in CASES if "k128" in n and "_cg_" in n])
-@pytest.mark.parametrize("kernel", [1, 2, 3])
-def test_cg_kernel_variants_agree_with_reference(name, kernel, cases, golden_half):
-    """generic streaming (1), register-resident with full XtX (2), register-resident in the eigenbasis (3)."""
+@pytest.mark.parametrize("kernel,stage", [(1, 0), (2, 1), (2, 2), (3, 1), (3, 2)])
+def test_cg_kernel_variants_agree_with_reference(name, kernel, stage, cases, golden_half):
+    """generic streaming (1), register-resident with full XtX (2), register-resident in the eigenbasis (3);
+    tile staging by cp.async.bulk (stage 1) or cp.async (stage 2)."""
     c = cases[name]
     if kernel == 3 and (c["feedback"] != "implicit" or np.diff(c["ptr"]).max() > 80):
         pytest.skip("eigenbasis path: implicit feedback, rows <= 80 nnz")
-    s = _session_for(c, kernel)
+    s = _session_for(c, kernel, stage=stage)
     loss = s.half_iteration(L.USERS)
     Y = s.get_factors(L.USERS)
     X = s.get_factors(L.ITEMS)
