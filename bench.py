@@ -301,7 +301,7 @@ def main():
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one als_cg_resident_kernel launch, from the committed
 # `ncu --set full` capture (profiles/); None until a capture for that workload exists.
-TRAFFIC_BYTES_PER_LAUNCH = {}
+TRAFFIC_BYTES_PER_LAUNCH = {"c3": 353241793792 + 5129585152}   # profiles/r1/resident_dram_c3.csv (N = 1)
 
 if __name__ == "__main__":
     main()

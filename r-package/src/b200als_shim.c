@@ -1,0 +1,177 @@
+/* b200als_shim.c -- the `.Call` layer an rsparse maintainer drops into src/ in place of the four
+ * Rcpp-generated ALS wrappers (src/RcppExports.cpp:329-416 -> src/wrmf_implicit.cpp:5-31,
+ * src/wrmf_explicit.cpp:5-27).  Plain C against Rinternals.h only: no Rcpp, no Armadillo.
+ * It unpacks the same SEXPs the reference unpacks (src/utils.cpp:69-78 for the dgCMatrix slots,
+ * src/utils.cpp:115-128 for float32 S4 objects) into the C ABI of include/b200als.h and maps a
+ * non-zero status to an R error, as END_RCPP does for C++ exceptions.
+ *
+ * The routines are registered under the reference's own symbol names (src/RcppExports.cpp:456-490),
+ * so R/RcppExports.R:88-102 and R/model_WRMF.R:493-495,:514 keep working unchanged.
+ *
+ * NOT compiled in the authoring image (no R there); build: R CMD SHLIB b200als_shim.c -lb200als
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+
+#include "b200als.h"
+
+static void csc_from_s4(SEXP m, b200als_csc* out) { /* src/utils.cpp:69-78 */
+  SEXP dim = R_do_slot(m, Rf_install("Dim"));
+  SEXP x = R_do_slot(m, Rf_install("x"));
+  SEXP i = R_do_slot(m, Rf_install("i"));
+  SEXP p = R_do_slot(m, Rf_install("p"));
+  out->n_rows = INTEGER(dim)[0];
+  out->n_cols = INTEGER(dim)[1];
+  out->nnz = (int64_t)XLENGTH(x);
+  out->ptr = INTEGER(p);
+  out->idx = INTEGER(i);
+  out->val_f64 = REAL(x);
+  out->val_f32 = NULL;
+}
+
+/* float32 S4 (package `float`): slot Data is an INTSXP matrix whose payload is IEEE float
+ * (src/utils.cpp:115-128) */
+static float* float32_matrix(SEXP s4, int* nrow, int* ncol) {
+  SEXP d = R_do_slot(s4, Rf_install("Data"));
+  SEXP dims = Rf_getAttrib(d, R_DimSymbol);
+  if (nrow) *nrow = Rf_isNull(dims) ? (int)XLENGTH(d) : INTEGER(dims)[0];
+  if (ncol) *ncol = Rf_isNull(dims) ? 1 : INTEGER(dims)[1];
+  return (float*)INTEGER(d);
+}
+static float* float32_vector_or_null(SEXP s4) {
+  SEXP d = R_do_slot(s4, Rf_install("Data"));
+  return XLENGTH(d) ? (float*)INTEGER(d) : NULL;
+}
+static void check(int rc) {
+  if (rc != B200ALS_OK) Rf_error("b200als: %s (status %d)", b200als_last_error(), rc);
+}
+
+SEXP _rsparse_als_implicit_float(SEXP m_csc_r, SEXP X_, SEXP Y_, SEXP XtX_, SEXP lambda, SEXP n_threads,
+                                 SEXP solver, SEXP cg_steps, SEXP with_biases, SEXP is_x_bias_last_row,
+                                 SEXP global_bias, SEXP global_bias_base_, SEXP initialize_bias_base) {
+  b200als_csc A;
+  csc_from_s4(m_csc_r, &A);
+  int k = 0, kx = 0;
+  float* X = float32_matrix(X_, &k, NULL);
+  float* Y = float32_matrix(Y_, NULL, NULL); /* updated in place, like arma's aliasing fmat */
+  float* XtX = float32_matrix(XtX_, &kx, NULL);
+  double loss = 0.0;
+  check(b200als_als_implicit_float(&A, k, X, Y, XtX, Rf_asReal(lambda), Rf_asInteger(n_threads),
+                                   (unsigned)Rf_asInteger(solver), (unsigned)Rf_asInteger(cg_steps),
+                                   Rf_asLogical(with_biases), Rf_asLogical(is_x_bias_last_row),
+                                   Rf_asReal(global_bias), float32_vector_or_null(global_bias_base_),
+                                   Rf_asLogical(initialize_bias_base), &loss));
+  return Rf_ScalarReal(loss);
+}
+
+SEXP _rsparse_als_implicit_double(SEXP m_csc_r, SEXP X, SEXP Y, SEXP XtX, SEXP lambda, SEXP n_threads,
+                                  SEXP solver, SEXP cg_steps, SEXP with_biases, SEXP is_x_bias_last_row,
+                                  SEXP global_bias, SEXP global_bias_base, SEXP initialize_bias_base) {
+  b200als_csc A;
+  csc_from_s4(m_csc_r, &A);
+  double loss = 0.0;
+  check(b200als_als_implicit_double(&A, Rf_nrows(X), REAL(X), REAL(Y), REAL(XtX), Rf_asReal(lambda),
+                                    Rf_asInteger(n_threads), (unsigned)Rf_asInteger(solver),
+                                    (unsigned)Rf_asInteger(cg_steps), Rf_asLogical(with_biases),
+                                    Rf_asLogical(is_x_bias_last_row), Rf_asReal(global_bias),
+                                    XLENGTH(global_bias_base) ? REAL(global_bias_base) : NULL,
+                                    Rf_asLogical(initialize_bias_base), &loss));
+  return Rf_ScalarReal(loss);
+}
+
+SEXP _rsparse_als_explicit_float(SEXP m_csc_r, SEXP X_, SEXP Y_, SEXP cnt_X_, SEXP lambda, SEXP n_threads,
+                                 SEXP solver, SEXP cg_steps, SEXP dynamic_lambda, SEXP with_biases,
+                                 SEXP is_x_bias_last_row) {
+  b200als_csc A;
+  csc_from_s4(m_csc_r, &A);
+  int k = 0;
+  float* X = float32_matrix(X_, &k, NULL);
+  float* Y = float32_matrix(Y_, NULL, NULL);
+  double loss = 0.0;
+  check(b200als_als_explicit_float(&A, k, X, Y, float32_vector_or_null(cnt_X_), Rf_asReal(lambda),
+                                   (unsigned)Rf_asInteger(n_threads), (unsigned)Rf_asInteger(solver),
+                                   (unsigned)Rf_asInteger(cg_steps), Rf_asLogical(dynamic_lambda),
+                                   Rf_asLogical(with_biases), Rf_asLogical(is_x_bias_last_row), &loss));
+  return Rf_ScalarReal(loss);
+}
+
+SEXP _rsparse_als_explicit_double(SEXP m_csc_r, SEXP X, SEXP Y, SEXP cnt_X, SEXP lambda, SEXP n_threads,
+                                  SEXP solver, SEXP cg_steps, SEXP dynamic_lambda, SEXP with_biases,
+                                  SEXP is_x_bias_last_row) {
+  b200als_csc A;
+  csc_from_s4(m_csc_r, &A);
+  double loss = 0.0;
+  check(b200als_als_explicit_double(&A, Rf_nrows(X), REAL(X), REAL(Y), XLENGTH(cnt_X) ? REAL(cnt_X) : NULL,
+                                    Rf_asReal(lambda), (unsigned)Rf_asInteger(n_threads),
+                                    (unsigned)Rf_asInteger(solver), (unsigned)Rf_asInteger(cg_steps),
+                                    Rf_asLogical(dynamic_lambda), Rf_asLogical(with_biases),
+                                    Rf_asLogical(is_x_bias_last_row), &loss));
+  return Rf_ScalarReal(loss);
+}
+
+/* ---- device-resident session: what WRMF$fit_transform(precision = "float") binds to -------------- */
+static void session_finalizer(SEXP ptr) {
+  b200als_session* s = (b200als_session*)R_ExternalPtrAddr(ptr);
+  if (s) b200als_destroy(s);
+  R_ClearExternalPtr(ptr);
+}
+/* c_ui, c_iu: dgCMatrix (users x items as CSC; items x users as CSC == R/model_WRMF.R:184-189) */
+SEXP b200als_R_create(SEXP c_ui, SEXP c_iu, SEXP rank, SEXP feedback, SEXP solver, SEXP cg_steps,
+                      SEXP dynamic_lambda, SEXP lambda) {
+  b200als_csc A, B;
+  csc_from_s4(c_ui, &A);
+  csc_from_s4(c_iu, &B);
+  b200als_options o;
+  b200als_default_options(&o);
+  o.feedback = Rf_asInteger(feedback);
+  o.solver = Rf_asInteger(solver);
+  o.cg_steps = Rf_asInteger(cg_steps);
+  o.dynamic_lambda = Rf_asLogical(dynamic_lambda);
+  o.lambda = Rf_asReal(lambda);
+  b200als_session* s = NULL;
+  check(b200als_create(&s, &A, &B, A.n_rows, A.n_cols, Rf_asInteger(rank), &o));
+  SEXP ptr = PROTECT(R_MakeExternalPtr(s, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(ptr, session_finalizer, TRUE);
+  UNPROTECT(1);
+  return ptr;
+}
+SEXP b200als_R_set_factors(SEXP ptr, SEXP which, SEXP fl) {
+  check(b200als_set_factors((b200als_session*)R_ExternalPtrAddr(ptr), Rf_asInteger(which), float32_matrix(fl, NULL, NULL)));
+  return R_NilValue;
+}
+SEXP b200als_R_get_factors(SEXP ptr, SEXP which, SEXP fl_out) {
+  check(b200als_get_factors((b200als_session*)R_ExternalPtrAddr(ptr), Rf_asInteger(which), float32_matrix(fl_out, NULL, NULL)));
+  return R_NilValue;
+}
+SEXP b200als_R_fit(SEXP ptr, SEXP n_iter, SEXP tol) {
+  const int n = Rf_asInteger(n_iter);
+  SEXP trace = PROTECT(Rf_allocVector(REALSXP, 2 * (n > 0 ? n : 1)));
+  int done = 0;
+  check(b200als_fit((b200als_session*)R_ExternalPtrAddr(ptr), n, Rf_asReal(tol), REAL(trace), &done));
+  SEXP out = PROTECT(Rf_lengthgets(trace, 2 * done));
+  UNPROTECT(2);
+  return out;
+}
+SEXP b200als_R_transform(SEXP ptr, SEXP fl_out) {
+  double loss = 0.0;
+  check(b200als_transform((b200als_session*)R_ExternalPtrAddr(ptr), float32_matrix(fl_out, NULL, NULL), &loss));
+  return Rf_ScalarReal(loss);
+}
+
+static const R_CallMethodDef CallEntries[] = {
+    {"_rsparse_als_implicit_float", (DL_FUNC)&_rsparse_als_implicit_float, 13},
+    {"_rsparse_als_implicit_double", (DL_FUNC)&_rsparse_als_implicit_double, 13},
+    {"_rsparse_als_explicit_float", (DL_FUNC)&_rsparse_als_explicit_float, 11},
+    {"_rsparse_als_explicit_double", (DL_FUNC)&_rsparse_als_explicit_double, 11},
+    {"b200als_R_create", (DL_FUNC)&b200als_R_create, 8},
+    {"b200als_R_set_factors", (DL_FUNC)&b200als_R_set_factors, 3},
+    {"b200als_R_get_factors", (DL_FUNC)&b200als_R_get_factors, 3},
+    {"b200als_R_fit", (DL_FUNC)&b200als_R_fit, 3},
+    {"b200als_R_transform", (DL_FUNC)&b200als_R_transform, 2},
+    {NULL, NULL, 0}};
+
+void R_init_rsparse(DllInfo* dll) {
+  R_registerRoutines(dll, NULL, CallEntries, NULL, NULL);
+  R_useDynamicSymbols(dll, FALSE);
+}
