@@ -225,7 +225,8 @@ def main():
     solve_ms = parallel.max_over_ranks(parts["solve_ms"]) / args.steps
     achieved = n_local * BYTES_PER_ROW(nnz, k) / (solve_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "kernel": "als_cg_resident_kernel", "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(args.workload),
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": (TRAFFIC_BYTES_PER_LAUNCH[args.workload] * n_local // n_user
+                            if args.workload in TRAFFIC_BYTES_PER_LAUNCH else None),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": n_local * BYTES_PER_ROW(nnz, k),
                 "kernel_ms": solve_ms, "fp32_tflops": n_local * FLOPS_PER_ROW(nnz, k, cg) / (solve_ms / 1e3) / 1e12}
 

@@ -30,6 +30,8 @@ struct SolveParams {
   double lambda;
   const int32_t* row_list;  // optional subset of rows to solve
   int n_list;
+  const int* n_list_dev;    // when non-null the list length is read from device memory (pipelined calls)
+  int ptr_base;             // ptr[] values are offsets into a buffer that starts at this absolute offset
   unsigned long long* ticket;
   double* loss_partials;  // [gridDim.x]
   int* status;            // != 0: some system was not positive definite
@@ -131,7 +133,8 @@ __global__ void __launch_bounds__(256) als_cg_generic_kernel(SolveParams<T> P) {
   const int lane = lane_id();
   const int k = P.k;
   const bool implicit = (P.feedback == 0);
-  const unsigned long long total = P.row_list ? (unsigned long long)P.n_list : (unsigned long long)P.n_targets;
+  const unsigned long long total = P.n_list_dev ? (unsigned long long)__ldg(P.n_list_dev)
+                                   : (P.row_list ? (unsigned long long)P.n_list : (unsigned long long)P.n_targets);
   double warp_loss = 0.0;
   for (;;) {
     unsigned long long t = 0;
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(256) als_cg_generic_kernel(SolveParams<T> P) {
     t = __shfl_sync(kFull, t, 0);
     if (t >= total) break;
     const int row = P.row_list ? P.row_list[t] : (int)t;
-    const int p1 = P.ptr[row], p2 = P.ptr[row + 1];
+    const int p1 = P.ptr[row] - P.ptr_base, p2 = P.ptr[row + 1] - P.ptr_base;
     T* y = P.Y + (size_t)row * k;
     if (p1 >= p2) {  // wrmf_implicit.hpp:281 / wrmf_explicit.hpp:144
 #pragma unroll
@@ -237,7 +240,7 @@ __global__ void __launch_bounds__(256) als_chol_generic_kernel(SolveParams<T> P)
   T* cs = wts + kCholTN;                          // kCholTN
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const bool implicit = (P.feedback == 0);
-  const int total = P.row_list ? P.n_list : P.n_targets;
+  const int total = P.n_list_dev ? __ldg(P.n_list_dev) : (P.row_list ? P.n_list : P.n_targets);
   double cta_loss = 0.0;
   for (;;) {
     __syncthreads();
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(256) als_chol_generic_kernel(SolveParams<T> P)
     __syncthreads();
     const int row = s_row;
     if (row < 0) break;
-    const int p1 = P.ptr[row], p2 = P.ptr[row + 1];
+    const int p1 = P.ptr[row] - P.ptr_base, p2 = P.ptr[row + 1] - P.ptr_base;
     T* y = P.Y + (size_t)row * k;
     if (p1 >= p2) {
       for (int f = tid; f < k; f += 256) y[f] = T(0);

@@ -50,6 +50,8 @@ struct ResidentParams {
   float lambda;
   const int32_t* row_list;  // rows with 1 <= nnz <= kResMaxN (nullptr: all rows 0..n_list-1 qualify)
   int n_list;
+  const int* n_list_dev;    // when non-null the list length is read from device memory (pipelined calls)
+  int ptr_base;             // ptr[] values are offsets into a buffer that starts at this absolute offset
   double* loss_partials;    // [gridDim.x]
 };
 
@@ -208,7 +210,8 @@ __global__ void __launch_bounds__(kResThreads, 3) als_cg_resident_kernel(Residen
   float* my_tile = &S.tile[w][0];
   uint64_t* my_bar = &S.bar[w];
 
-  auto valid = [&](int i) -> bool { return (long long)blockIdx.x + (long long)i * stride < (long long)P.n_list; };
+  const long long n_list = P.n_list_dev ? (long long)__ldg(P.n_list_dev) : (long long)P.n_list;
+  auto valid = [&](int i) -> bool { return (long long)blockIdx.x + (long long)i * stride < n_list; };
   auto row_of = [&](int i) -> int {  // i-th row of this CTA (caller checks valid(i))
     const long long t = (long long)blockIdx.x + (long long)i * stride;
     return P.row_list ? __ldg(P.row_list + t) : (int)t;
@@ -248,19 +251,19 @@ __global__ void __launch_bounds__(kResThreads, 3) als_cg_resident_kernel(Residen
   float cq = 0.f, val1 = 0.f;
   if (valid(0)) {
     rid0 = row_of(0);
-    const int p = __ldg(P.ptr + rid0);
-    n0 = __ldg(P.ptr + rid0 + 1) - p;
+    const int p = __ldg(P.ptr + rid0) - P.ptr_base;
+    n0 = __ldg(P.ptr + rid0 + 1) - P.ptr_base - p;
     int idx0 = 0;
     if (my_j < n0) { idx0 = __ldg(P.idx + p + my_j); cq = __ldg(P.val + p + my_j); }
     issue_tile(rid0, n0, idx0);
   }
   if (valid(1)) {
     rid1 = row_of(1);
-    const int p = __ldg(P.ptr + rid1);
-    n1 = __ldg(P.ptr + rid1 + 1) - p;
+    const int p = __ldg(P.ptr + rid1) - P.ptr_base;
+    n1 = __ldg(P.ptr + rid1 + 1) - P.ptr_base - p;
     if (my_j < n1) { idx1 = __ldg(P.idx + p + my_j); val1 = __ldg(P.val + p + my_j); }
   }
-  if (valid(2)) { rid2 = row_of(2); p2 = __ldg(P.ptr + rid2); n2 = __ldg(P.ptr + rid2 + 1) - p2; }
+  if (valid(2)) { rid2 = row_of(2); p2 = __ldg(P.ptr + rid2) - P.ptr_base; n2 = __ldg(P.ptr + rid2 + 1) - P.ptr_base - p2; }
   if (valid(3)) rid3 = row_of(3);
 
   float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(kResThreads, 3) als_cg_resident_kernel(Residen
     int idx2 = 0, p3 = 0, p3e = 0, rid4 = -1;
     float val2 = 0.f;
     if (valid(i + 2) && my_j < n2) { idx2 = __ldg(P.idx + p2 + my_j); val2 = __ldg(P.val + p2 + my_j); }
-    if (valid(i + 3)) { p3 = __ldg(P.ptr + rid3); p3e = __ldg(P.ptr + rid3 + 1); }
+    if (valid(i + 3)) { p3 = __ldg(P.ptr + rid3) - P.ptr_base; p3e = __ldg(P.ptr + rid3 + 1) - P.ptr_base; }
     if (valid(i + 4)) rid4 = row_of(i + 4);
     // ---- CG ---------------------------------------------------------------------------------------------
     const float lam_use = implicit ? P.lambda : (P.lambda * (P.dynamic_lambda ? (float)n : 1.0f));

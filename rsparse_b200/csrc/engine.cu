@@ -353,6 +353,8 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
   P.lambda = o.lambda;
   P.row_list = nullptr;
   P.n_list = 0;
+  P.n_list_dev = nullptr;
+  P.ptr_base = 0;
   P.ticket = c.ticket.u64();
   P.status = c.status.i32();
   const int max_grid = c.sm_count * 8;
@@ -423,6 +425,8 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
       R.lambda = (float)o.lambda;
       R.row_list = A.all_short ? nullptr : A.short_list.i32();
       R.n_list = A.n_short;
+      R.n_list_dev = nullptr;
+      R.ptr_base = 0;
       R.loss_partials = P.loss_partials;
       const int grid = std::min(c.sm_count * 3, A.n_short);
       const size_t smem = sizeof(ResidentSmem);
@@ -513,6 +517,201 @@ static int stateless_half(const b200als_csc* A, int rank, const T* X, T* Y, cons
   return B200ALS_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// 1b. pipelined stateless call: fp32, CG, rank 128, large inputs.  The solved rows are cut into blocks of
+//     <= 512k rows / 64M non-zeros; block c+1 and c+2 travel host->device (copy engine) while block c is
+//     classified, rotated, solved and rotated back on the compute stream and block c-1 returns device->host.
+//     Device buffers are cached in the context between calls; no data is retained.
+// ------------------------------------------------------------------------------------------------------
+__global__ void diag_matrix_kernel(const float* __restrict__ d, float* __restrict__ G, int k) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < k * k) G[e] = ((e / k) == (e % k)) ? d[e / k] : 0.f;
+}
+struct PipeBuf {
+  DevBuf ptr, idx, val64, val32, Y, short_list, long_list, counts;
+  cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
+  bool used = false;
+};
+struct PipeCtx {
+  static constexpr int NB = 3;
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  PipeBuf buf[NB];
+  DevBuf X, G, G64, Vt, Q, Qt, Q64, diag, Gdiag, cnt;
+  int init() {
+    if (h2d) return B200ALS_OK;
+    CU(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
+    for (auto& b : buf) {
+      CU(cudaEventCreateWithFlags(&b.h2d_done, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&b.compute_done, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&b.d2h_done, cudaEventDisableTiming));
+    }
+    return B200ALS_OK;
+  }
+};
+static PipeCtx& pipe_ctx() {
+  static thread_local PipeCtx p;
+  return p;
+}
+static int rotate_matrix(Ctx& c, float* M, long long n, const float* R);
+
+static int stateless_pipelined(const b200als_csc* A, const float* X, float* Y, const float* XtX, const float* cnt_X,
+                               const HalfOpts& o, double* loss) {
+  Ctx& c = ctx();
+  PipeCtx& pc = pipe_ctx();
+  TRY(pc.init());
+  const int k = kResK;
+  const bool implicit = (o.feedback == B200ALS_IMPLICIT);
+  const int32_t* hp = A->ptr;
+  // ---- block boundaries from the host row pointers ----
+  int64_t kMaxRows = 512 * 1024;
+  const int64_t kMaxNnz = 64ll * 1024 * 1024;
+  if (const char* er = getenv("B200ALS_PIPELINE_ROWS")) kMaxRows = std::max<int64_t>(1, atoll(er));  // tests: force many blocks
+  std::vector<int32_t> cuts{0};
+  int64_t max_rows = 0, max_nnz = 0;
+  while (cuts.back() < A->n_cols) {
+    const int32_t b = cuts.back();
+    int32_t e = (int32_t)std::min<int64_t>(A->n_cols, (int64_t)b + kMaxRows);
+    while (e > b + 1 && (int64_t)hp[e] - hp[b] > kMaxNnz) e = b + std::max(1, (e - b) / 2);
+    cuts.push_back(e);
+    max_rows = std::max<int64_t>(max_rows, e - b);
+    max_nnz = std::max<int64_t>(max_nnz, (int64_t)hp[e] - hp[b]);
+  }
+  const int n_chunks = (int)cuts.size() - 1;
+  for (auto& b : pc.buf) {
+    CU(b.ptr.ensure(sizeof(int32_t) * (size_t)(max_rows + 1)));
+    CU(b.idx.ensure(sizeof(int32_t) * (size_t)max_nnz));
+    if (A->val_f64) CU(b.val64.ensure(sizeof(double) * (size_t)max_nnz));
+    CU(b.val32.ensure(sizeof(float) * (size_t)max_nnz));
+    CU(b.Y.ensure(sizeof(float) * (size_t)max_rows * k));
+    CU(b.short_list.ensure(sizeof(int32_t) * (size_t)max_rows));
+    CU(b.long_list.ensure(sizeof(int32_t) * (size_t)max_rows));
+    CU(b.counts.ensure(4 * sizeof(int)));
+    b.used = false;
+  }
+  // ---- fixed matrix, Gram, eigenbasis (compute stream) ----
+  const size_t xbytes = sizeof(float) * (size_t)k * (size_t)A->n_rows;
+  CU(pc.X.ensure(xbytes));
+  CU(cudaMemcpyAsync(pc.X.p, X, xbytes, cudaMemcpyHostToDevice, c.stream));
+  const float* diag = nullptr;
+  const float* Glong = nullptr;
+  if (implicit) {
+    CU(pc.G.ensure(sizeof(float) * k * k));
+    CU(pc.G64.ensure(sizeof(double) * k * k));
+    CU(pc.Vt.ensure(sizeof(double) * k * k));
+    CU(pc.Q64.ensure(sizeof(double) * k * k));
+    CU(pc.Q.ensure(sizeof(float) * k * k));
+    CU(pc.Qt.ensure(sizeof(float) * k * k));
+    CU(pc.diag.ensure(sizeof(float) * k));
+    CU(pc.Gdiag.ensure(sizeof(float) * k * k));
+    if (XtX) {
+      CU(cudaMemcpyAsync(pc.G.p, XtX, sizeof(float) * k * k, cudaMemcpyHostToDevice, c.stream));
+      convert_kernel<float, double><<<(k * k + 255) / 256, 256, 0, c.stream>>>(pc.G.f32(), pc.G64.f64(), k * k);
+      LAUNCHED(); CU(cudaGetLastError());
+    } else {
+      TRY(run_gram<float>(c, pc.X.f32(), k, A->n_rows, o.lambda, pc.G.f32(), pc.G64.f64()));
+    }
+    const size_t jsm = sizeof(double) * (size_t)k * (k + 1);
+    CU(cudaFuncSetAttribute(jacobi_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm));
+    jacobi_eig_kernel<<<1, kJacobiThreads, jsm, c.stream>>>(pc.G64.f64(), pc.Vt.f64(), k, pc.Q.f32(), pc.diag.f32(),
+                                                            pc.Q64.f64(), 30, 1);
+    LAUNCHED(); CU(cudaGetLastError());
+    convert_kk_kernel<<<(k * k + 255) / 256, 256, 0, c.stream>>>(pc.Q64.f64(), pc.Qt.f32(), k, 1);
+    LAUNCHED(); CU(cudaGetLastError());
+    diag_matrix_kernel<<<(k * k + 255) / 256, 256, 0, c.stream>>>(pc.diag.f32(), pc.Gdiag.f32(), k);
+    LAUNCHED(); CU(cudaGetLastError());
+    TRY(rotate_matrix(c, pc.X.f32(), A->n_rows, pc.Q.f32()));
+    diag = pc.diag.f32();
+    Glong = pc.Gdiag.f32();
+  }
+  const float* dcnt = nullptr;
+  if (!implicit && o.dynamic_lambda && o.lambda > 0) {
+    if (!cnt_X) return fail(B200ALS_EINVAL, "explicit feedback with dynamic_lambda needs cnt_X");
+    CU(pc.cnt.ensure(sizeof(float) * (size_t)A->n_rows));
+    CU(cudaMemcpyAsync(pc.cnt.p, cnt_X, sizeof(float) * (size_t)A->n_rows, cudaMemcpyHostToDevice, c.stream));
+    dcnt = pc.cnt.f32();
+  }
+  CU(cudaMemsetAsync(c.loss_acc.p, 0, sizeof(double), c.stream));
+  CU(cudaMemsetAsync(c.status.p, 0, sizeof(int), c.stream));
+  const int res_grid = c.sm_count * 3;
+  const int gen_grid = c.sm_count * 4;
+  CU(c.loss_partials.ensure(sizeof(double) * (size_t)c.sm_count * 8));
+  const size_t res_smem = sizeof(ResidentSmem);
+  CU(cudaFuncSetAttribute(als_cg_resident_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem));
+  // ---- the pipeline ----
+  for (int ci = 0; ci < n_chunks; ci++) {
+    PipeBuf& b = pc.buf[ci % PipeCtx::NB];
+    const int32_t r0 = cuts[ci], r1 = cuts[ci + 1], nr = r1 - r0;
+    const int64_t e0 = hp[r0], ne = (int64_t)hp[r1] - e0;
+    // host -> device
+    if (b.used) CU(cudaStreamWaitEvent(pc.h2d, b.d2h_done, 0));
+    CU(cudaMemcpyAsync(b.ptr.p, hp + r0, sizeof(int32_t) * (size_t)(nr + 1), cudaMemcpyHostToDevice, pc.h2d));
+    if (ne) {
+      CU(cudaMemcpyAsync(b.idx.p, A->idx + e0, sizeof(int32_t) * (size_t)ne, cudaMemcpyHostToDevice, pc.h2d));
+      if (A->val_f64) CU(cudaMemcpyAsync(b.val64.p, A->val_f64 + e0, sizeof(double) * (size_t)ne, cudaMemcpyHostToDevice, pc.h2d));
+      else CU(cudaMemcpyAsync(b.val32.p, A->val_f32 + e0, sizeof(float) * (size_t)ne, cudaMemcpyHostToDevice, pc.h2d));
+    }
+    CU(cudaMemcpyAsync(b.Y.p, Y + (size_t)r0 * k, sizeof(float) * (size_t)nr * k, cudaMemcpyHostToDevice, pc.h2d));
+    CU(cudaEventRecord(b.h2d_done, pc.h2d));
+    // compute
+    CU(cudaStreamWaitEvent(c.stream, b.h2d_done, 0));
+    if (A->val_f64 && ne) {
+      convert_kernel<double, float><<<(unsigned)((ne + 255) / 256), 256, 0, c.stream>>>(b.val64.f64(), b.val32.f32(), ne);
+      LAUNCHED(); CU(cudaGetLastError());
+    }
+    CU(cudaMemsetAsync(b.counts.p, 0, 4 * sizeof(int), c.stream));
+    classify_rows_kernel<<<(nr + 255) / 256, 256, 0, c.stream>>>(b.ptr.i32(), nr, kResMaxN, b.short_list.i32(), b.long_list.i32(), b.counts.i32());
+    LAUNCHED(); CU(cudaGetLastError());
+    zero_empty_rows_kernel<float><<<(unsigned)(((long long)nr * k + 255) / 256), 256, 0, c.stream>>>(b.ptr.i32(), nr, k, b.Y.f32());
+    LAUNCHED(); CU(cudaGetLastError());
+    if (implicit) TRY(rotate_matrix(c, b.Y.f32(), nr, pc.Q.f32()));
+    ResidentParams R;
+    R.ptr = b.ptr.i32(); R.idx = b.idx.i32(); R.val = b.val32.f32();
+    R.X = pc.X.f32(); R.Y = b.Y.f32(); R.diag = diag; R.G = nullptr;
+    R.feedback = o.feedback; R.cg_steps = o.cg_steps; R.dynamic_lambda = o.dynamic_lambda; R.lambda = (float)o.lambda;
+    R.row_list = b.short_list.i32(); R.n_list = 0; R.n_list_dev = b.counts.i32(); R.ptr_base = (int)e0;
+    R.loss_partials = c.loss_partials.f64();
+    als_cg_resident_kernel<false, 1><<<res_grid, kResThreads, res_smem, c.stream>>>(R);
+    LAUNCHED(); CU(cudaGetLastError());
+    sum_partials_kernel<<<1, 32, 0, c.stream>>>(c.loss_partials.f64(), res_grid, c.loss_acc.f64(), 1);
+    LAUNCHED(); CU(cudaGetLastError());
+    {  // rows longer than the register tile: streaming kernel on the same (rotated) data
+      SolveParams<float> P;
+      P.ptr = b.ptr.i32(); P.idx = b.idx.i32(); P.val = b.val32.f32(); P.X = pc.X.f32(); P.Y = b.Y.f32();
+      P.G = implicit ? Glong : nullptr; P.k = k; P.n_targets = nr; P.feedback = o.feedback; P.cg_steps = o.cg_steps;
+      P.dynamic_lambda = o.dynamic_lambda; P.lambda = o.lambda; P.row_list = b.long_list.i32(); P.n_list = 0;
+      P.n_list_dev = b.counts.i32() + 1; P.ptr_base = (int)e0; P.ticket = c.ticket.u64();
+      P.loss_partials = c.loss_partials.f64(); P.status = c.status.i32();
+      CU(cudaMemsetAsync(c.ticket.p, 0, sizeof(unsigned long long), c.stream));
+      als_cg_generic_kernel<float, 4><<<gen_grid, 256, 0, c.stream>>>(P);
+      LAUNCHED(); CU(cudaGetLastError());
+      sum_partials_kernel<<<1, 32, 0, c.stream>>>(c.loss_partials.f64(), gen_grid, c.loss_acc.f64(), 1);
+      LAUNCHED(); CU(cudaGetLastError());
+    }
+    if (implicit) TRY(rotate_matrix(c, b.Y.f32(), nr, pc.Qt.f32()));
+    CU(cudaEventRecord(b.compute_done, c.stream));
+    // device -> host
+    CU(cudaStreamWaitEvent(pc.d2h, b.compute_done, 0));
+    CU(cudaMemcpyAsync(Y + (size_t)r0 * k, b.Y.p, sizeof(float) * (size_t)nr * k, cudaMemcpyDeviceToHost, pc.d2h));
+    CU(cudaEventRecord(b.d2h_done, pc.d2h));
+    b.used = true;
+  }
+  TRY(finish_loss<float>(c, pc.X.f32(), k, A->n_rows, dcnt, o, A->nnz, 0.0, false, loss));
+  CU(cudaStreamSynchronize(pc.d2h));
+  CU(cudaStreamSynchronize(pc.h2d));
+  return B200ALS_OK;
+}
+
+// large fp32 CG problems at rank 128 take the pipelined path (B200ALS_PIPELINE=0 disables, =1 forces)
+static bool use_pipelined(const b200als_csc* m, int rank, const float* X, const float* Y, const HalfOpts& o) {
+  if (!m || !X || !Y || !m->ptr || rank != kResK || o.solver != B200ALS_CONJUGATE_GRADIENT) return false;
+  if (ctx().init() != B200ALS_OK) return false;
+  const char* env = getenv("B200ALS_PIPELINE");
+  if (env && env[0] == '0') return false;
+  if (env && env[0] == '1') return m->n_cols > 0;
+  return m->n_cols >= 200000;
+}
+
 static int check_bias_args(int with_biases, double global_bias) {
   if (with_biases) return fail(B200ALS_EUNSUPPORTED, "with_user_item_bias is not implemented (SURVEY 8f-3)");
   if (global_bias != 0.0) return fail(B200ALS_EUNSUPPORTED, "with_global_bias is not implemented (SURVEY 8f-3)");
@@ -524,6 +723,7 @@ extern "C" int b200als_als_implicit_float(const b200als_csc* m, int rank, const 
                                           double global_bias, float*, int, double* loss) {
   TRY(check_bias_args(with_biases, global_bias));
   HalfOpts o{B200ALS_IMPLICIT, (int)solver, (int)cg_steps, 0, 0, lambda};
+  if (use_pipelined(m, rank, X, Y, o)) return stateless_pipelined(m, X, Y, XtX, nullptr, o, loss);
   return stateless_half<float>(m, rank, X, Y, XtX, nullptr, o, loss);
 }
 extern "C" int b200als_als_implicit_double(const b200als_csc* m, int rank, const double* X, double* Y, const double* XtX,
@@ -538,6 +738,7 @@ extern "C" int b200als_als_explicit_float(const b200als_csc* m, int rank, const 
                                           int with_biases, int, double* loss) {
   TRY(check_bias_args(with_biases, 0.0));
   HalfOpts o{B200ALS_EXPLICIT, (int)solver, (int)cg_steps, dynamic_lambda != 0, 0, lambda};
+  if (use_pipelined(m, rank, X, Y, o)) return stateless_pipelined(m, X, Y, nullptr, cnt_X, o, loss);
   return stateless_half<float>(m, rank, X, Y, nullptr, cnt_X, o, loss);
 }
 extern "C" int b200als_als_explicit_double(const b200als_csc* m, int rank, const double* X, double* Y, const double* cnt_X,

@@ -225,3 +225,23 @@ def test_unsupported_options_fail_loudly(cases):
     with pytest.raises(L.B200AlsError) as e:
         als_implicit(c["ptr"], c["idx"], c["val"], c["X"], c["Y0"].copy(), 0.1, L.CHOLESKY, with_user_item_bias=True)
     assert e.value.code == L.EUNSUPPORTED
+
+
+@pytest.mark.parametrize("name", ["synth_ragged_implicit_cg_k128", "synth_long_implicit_cg_k128", "synth_explicit_cg_k128",
+                                  "synth_implicit_cg_k128"])
+@pytest.mark.parametrize("vals", ["f64", "f32"])
+def test_pipelined_stateless_path(name, vals, cases, golden_half, monkeypatch):
+    """The chunked H2D / solve / D2H pipeline of the stateless call (used for >= 200k rows), forced on small
+    inputs with 97-row blocks: empty rows, rows longer than the register tile, explicit feedback."""
+    import os
+    monkeypatch.setenv("B200ALS_PIPELINE", "1")
+    monkeypatch.setenv("B200ALS_PIPELINE_ROWS", "97")
+    c = dict(cases[name])
+    if vals == "f32":
+        c["val"] = c["val"].astype(np.float32)
+    for xtx in ("host", "engine"):
+        Y, loss = run_stateless(c, np.float32, XtX=xtx)
+        ref = golden_half[name + "/Y_f64"]
+        assert relF(Y, ref) < TOL_F32, (xtx, relF(Y, ref))
+        assert abs(loss - float(golden_half[name + "/loss_f64"])) <= TOL_F32 * abs(loss)
+        assert np.all(Y[np.diff(c["ptr"]) == 0] == 0)
