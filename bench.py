@@ -37,7 +37,11 @@ WORKLOADS = {
     "c3": (10_000_000, 1_000_000, 80, 128, 3, 0.1),
     "c3-small": (1_000_000, 1_000_000, 80, 128, 3, 0.1),   # ncu captures
     "c3-tiny": (100_000, 50_000, 80, 128, 3, 0.1),         # CPU-side dry runs
+    "c4": (10_000_000, 1_000_000, 80, 128, 3, 0.1),        # BASELINE configs[3]: explicit feedback (MMMF)
+    "c2": (1_000_000, 100_000, 50, 64, 3, 0.1),            # BASELINE configs[1]: implicit, rank 64, Cholesky
 }
+# (feedback, solver) per workload; everything not listed is implicit CG
+WORKLOAD_MODE = {"c4": ("explicit", 1), "c2": ("implicit", 0)}
 BYTES_PER_ROW = lambda n, k: 4 * n * k + 8 * n + 4 + 4 * k + 4 * k   # 42,628 at n=80, k=128
 FLOPS_PER_ROW = lambda n, k, s: (s + 1) * (4 * n * k + 2 * k * k)
 
@@ -167,6 +171,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("B200ALS_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 resident full-XtX, 3 resident eigenbasis")
     ap.add_argument("--stage", type=int, default=0, help="resident-kernel tile staging: 0 default, 1 cp.async.bulk, 2 cp.async")
+    ap.add_argument("--ctas", type=int, default=0, help="resident-kernel CTAs per SM: 0 default, 3, 4")
     ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="rows in the CPU baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
@@ -189,8 +194,11 @@ def main():
     begin, end = parallel.shard_range(n_user, rank, world)
     n_local = end - begin
 
-    s = Session.synthetic(n_local, begin, n_user, n_item, nnz, 42, k, "implicit", L.CONJUGATE_GRADIENT, cg, True, lam,
-                          args.kernel, args.stage)
+    feedback, solver = WORKLOAD_MODE.get(args.workload, ("implicit", L.CONJUGATE_GRADIENT))
+    if (feedback, solver) != ("implicit", L.CONJUGATE_GRADIENT):
+        args.no_e2e = args.no_cpu = True     # side workloads: device-resident number only
+    s = Session.synthetic(n_local, begin, n_user, n_item, nnz, 42, k, feedback, solver, cg, True, lam,
+                          args.kernel, args.stage, args.ctas)
     # Inputs: users at R's initialisation scale N(0,1)/100 (R/model_WRMF.R:203-215); items "trained-like":
     # N(0,1) * 0.1 * (1+f)^-0.5, so XtX has a ~128:1 spectrum and CG takes all its steps.  (i.i.d. item factors
     # make XtX ~ c*I: every row then leaves the CG loop after ONE step through `rsnew < CG_TOL`,
@@ -224,11 +232,23 @@ def main():
     hbm_peak, peak_src = measured_peaks()
     solve_ms = parallel.max_over_ranks(parts["solve_ms"]) / args.steps
     achieved = n_local * BYTES_PER_ROW(nnz, k) / (solve_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "als_cg_resident_kernel", "achieved": achieved, "peak": hbm_peak,
+    if solver == L.CHOLESKY:   # compute-bound path: 2nk^2 + 2nk + k^3/3 + 2k^2 flop per row
+        fl = 2 * nnz * k * k + 2 * nnz * k + k ** 3 / 3 + 2 * k * k
+        roofline = {"bound": "tensor", "kernel": "als_chol_generic_kernel (fp32 FMA; no tensor cores yet)",
+                    "achieved": n_local * fl / (solve_ms / 1e3) / 1e12, "peak": None, "unit": "TFLOP/s", "frac": None,
+                    "traffic": None, "kernel_ms": solve_ms}
+    else:
+      roofline = {"bound": "hbm", "kernel": "als_cg_resident_kernel", "achieved": achieved, "peak": hbm_peak,
                 "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": (TRAFFIC_BYTES_PER_LAUNCH[args.workload] * n_local // n_user
                             if args.workload in TRAFFIC_BYTES_PER_LAUNCH else None),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": n_local * BYTES_PER_ROW(nnz, k),
                 "kernel_ms": solve_ms, "fp32_tflops": n_local * FLOPS_PER_ROW(nnz, k, cg) / (solve_ms / 1e3) / 1e12}
+    if solver == L.CHOLESKY:
+        try:
+            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
+            roofline["peak"], roofline["frac"] = pk, roofline["achieved"] / pk
+        except Exception:
+            pass
 
     # ---- e2e: stateless C-ABI call, host buffers, copies inside the timed region -----------------------
     e2e = None
@@ -288,12 +308,13 @@ def main():
         out = {"metric": "WRMF-implicit ALS user-updates/sec at rank=128", "value": value, "unit": "user-updates/s",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": "%s: %dx%d CSR, %d nnz/row, WRMF implicit rank=%d CG(%d) lambda=%g, user half-iteration"
-                                      % (args.workload, n_user, n_item, nnz, k, cg, lam),
+               "config": {"workload": "%s: %dx%d CSR, %d nnz/row, WRMF %s rank=%d %s lambda=%g, user half-iteration"
+                                      % (args.workload, n_user, n_item, nnz, feedback, k,
+                                         "CG(%d)" % cg if solver == 1 else "Cholesky", lam),
                           "parallelism": "rows sharded over %d GPU(s), NCCL exchange of updated factors" % world,
                           "l2": "inputs larger than L2 (CSR %.1f GB + factors %.1f GB per step vs 126 MB L2); no flush needed"
                                 % (n_local * nnz * 8 / 1e9, (n_local + n_item) * k * 4 / 1e9),
-                          "kernel": args.kernel, "stage": args.stage, "loss": loss},
+                          "kernel": args.kernel, "stage": args.stage, "ctas": args.ctas, "loss": loss},
                "step_breakdown_ms": {kk: v / args.steps for kk, v in parts.items()},
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(out), flush=True)

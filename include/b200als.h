@@ -130,7 +130,8 @@ typedef struct b200als_options {
                           kernel with the full XtX (rank 128 only); 3 = register-resident kernel in the
                           eigenbasis of XtX even for small inputs (implicit, rank 128 only)       */
   int reserved[7];     /* reserved[0]: tile staging of the register-resident kernel -- 0 default, 1 cp.async.bulk
-                          (TMA engine), 2 cp.async (LDGSTS); the rest must be 0                       */
+                          (TMA engine), 2 cp.async (LDGSTS); reserved[1]: CTAs/SM the kernel is built for
+                          (0 default, 3, 4); the rest must be 0                                       */
 } b200als_options;
 
 void b200als_default_options(b200als_options* o);

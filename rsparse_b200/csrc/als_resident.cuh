@@ -198,8 +198,10 @@ __device__ __forceinline__ float4 resident_sweep(const float4 (&xt)[kResIPW], co
 
 // kStage: 0 = cp.async.bulk (TMA engine, UBLKCP; one 512-byte copy per owner lane, serialised through the
 // uniform datapath), 1 = cp.async 16 B per thread (LDGSTS; one warp-wide instruction per gathered row).
-template <bool kFullG, int kStage>
-__global__ void __launch_bounds__(kResThreads, 3) als_cg_resident_kernel(ResidentParams P) {
+// kCtas: resident CTAs per SM the register allocation is sized for (3: 168 registers, no spills; 4: 128
+// registers with ~170 B of spills per thread that stay in L1).
+template <bool kFullG, int kStage, int kCtas>
+__global__ void __launch_bounds__(kResThreads, kCtas) als_cg_resident_kernel(ResidentParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ResidentSmem& S = *reinterpret_cast<ResidentSmem*>(smem_raw);
   const int lane = lane_id(), w = warp_id(), tid = threadIdx.x;

@@ -291,7 +291,9 @@ struct HalfOpts {
   int feedback, solver, cg_steps, dynamic_lambda, kernel;
   double lambda;
   int stage = 0;  // tile staging of the resident kernel: 0 default, 1 cp.async.bulk (UBLKCP), 2 cp.async (LDGSTS)
+  int ctas = 0;   // resident CTAs per SM the kernel is compiled for: 0 default, 3 or 4
 };
+constexpr int kDefaultCtas = 3;
 constexpr int kDefaultStage = 1;  // LDGSTS: measured 6 % faster than the UBLKCP variant on C3 (profiles/)
 
 template <typename T>
@@ -428,7 +430,8 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
       R.n_list_dev = nullptr;
       R.ptr_base = 0;
       R.loss_partials = P.loss_partials;
-      const int grid = std::min(c.sm_count * 3, A.n_short);
+      const int ctas = (o.ctas == 3 || o.ctas == 4) ? o.ctas : kDefaultCtas;
+      const int grid = std::min(c.sm_count * ctas, A.n_short);
       const size_t smem = sizeof(ResidentSmem);
       const bool full_g = (o.feedback == B200ALS_IMPLICIT) && !diag;
       auto launch = [&](auto kern) -> cudaError_t {
@@ -438,8 +441,13 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
         return cudaSuccess;
       };
       const int stage = (o.stage == 1) ? 0 : (o.stage == 2 ? 1 : kDefaultStage);
-      if (full_g) CU(stage == 0 ? launch(als_cg_resident_kernel<true, 0>) : launch(als_cg_resident_kernel<true, 1>));
-      else CU(stage == 0 ? launch(als_cg_resident_kernel<false, 0>) : launch(als_cg_resident_kernel<false, 1>));
+      if (full_g) {
+        if (ctas == 4) CU(stage == 0 ? launch(als_cg_resident_kernel<true, 0, 4>) : launch(als_cg_resident_kernel<true, 1, 4>));
+        else CU(stage == 0 ? launch(als_cg_resident_kernel<true, 0, 3>) : launch(als_cg_resident_kernel<true, 1, 3>));
+      } else {
+        if (ctas == 4) CU(stage == 0 ? launch(als_cg_resident_kernel<false, 0, 4>) : launch(als_cg_resident_kernel<false, 1, 4>));
+        else CU(stage == 0 ? launch(als_cg_resident_kernel<false, 0, 3>) : launch(als_cg_resident_kernel<false, 1, 3>));
+      }
       LAUNCHED(); CU(cudaGetLastError());
       sum_partials_kernel<<<1, 32, 0, c.stream>>>(P.loss_partials, grid, c.loss_acc.f64(), 1);
       LAUNCHED(); CU(cudaGetLastError());
@@ -637,7 +645,7 @@ static int stateless_pipelined(const b200als_csc* A, const float* X, float* Y, c
   const int gen_grid = c.sm_count * 4;
   CU(c.loss_partials.ensure(sizeof(double) * (size_t)c.sm_count * 8));
   const size_t res_smem = sizeof(ResidentSmem);
-  CU(cudaFuncSetAttribute(als_cg_resident_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem));
+  CU(cudaFuncSetAttribute(als_cg_resident_kernel<false, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem));
   // ---- the pipeline ----
   for (int ci = 0; ci < n_chunks; ci++) {
     PipeBuf& b = pc.buf[ci % PipeCtx::NB];
@@ -671,7 +679,7 @@ static int stateless_pipelined(const b200als_csc* A, const float* X, float* Y, c
     R.feedback = o.feedback; R.cg_steps = o.cg_steps; R.dynamic_lambda = o.dynamic_lambda; R.lambda = (float)o.lambda;
     R.row_list = b.short_list.i32(); R.n_list = 0; R.n_list_dev = b.counts.i32(); R.ptr_base = (int)e0;
     R.loss_partials = c.loss_partials.f64();
-    als_cg_resident_kernel<false, 1><<<res_grid, kResThreads, res_smem, c.stream>>>(R);
+    als_cg_resident_kernel<false, 1, 3><<<res_grid, kResThreads, res_smem, c.stream>>>(R);
     LAUNCHED(); CU(cudaGetLastError());
     sum_partials_kernel<<<1, 32, 0, c.stream>>>(c.loss_partials.f64(), res_grid, c.loss_acc.f64(), 1);
     LAUNCHED(); CU(cudaGetLastError());
@@ -1129,7 +1137,7 @@ static int session_half(b200als_session* s, int which, int solver, float* Yout, 
   float* X = s->fac[fixed].f32();
   float* Yfull = s->fac[which].f32();
   float* Y = Yout ? Yout : (Yfull + (size_t)s->shard_begin[which] * s->k);
-  HalfOpts o{s->opt.feedback, solver, s->opt.cg_steps, s->opt.dynamic_lambda, s->opt.kernel, s->opt.lambda, s->opt.reserved[0]};
+  HalfOpts o{s->opt.feedback, solver, s->opt.cg_steps, s->opt.dynamic_lambda, s->opt.kernel, s->opt.lambda, s->opt.reserved[0], s->opt.reserved[1]};
   CscDev<float>& A = s->csc[which];
   const bool implicit = (o.feedback == B200ALS_IMPLICIT);
   CU(cudaEventRecord(s->ev[0], c.stream));

@@ -29,7 +29,7 @@ class Session:
     """Thin RAII wrapper over the session API of include/b200als.h."""
 
     def __init__(self, c_ui, c_iu, n_user, n_item, rank, feedback, solver, cg_steps=3, dynamic_lambda=True,
-                 lambda_=0.0, kernel=0, stage=0):
+                 lambda_=0.0, kernel=0, stage=0, ctas=0):
         self._h = C.c_void_p(None)
         o = L.Options()
         L.lib().b200als_default_options(C.byref(o))
@@ -40,6 +40,7 @@ class Session:
         o.lambda_ = float(lambda_)
         o.kernel = int(kernel)
         o.reserved[0] = int(stage)   # resident-kernel tile staging: 0 default, 1 cp.async.bulk, 2 cp.async
+        o.reserved[1] = int(ctas)    # resident-kernel CTAs/SM: 0 default, 3, 4
         self.rank, self.n_user, self.n_item = int(rank), int(n_user), int(n_item)
         keep = []
         s_ui = s_iu = None
@@ -55,7 +56,7 @@ class Session:
 
     @classmethod
     def synthetic(cls, n_user_local, user_offset, n_user_global, n_item, nnz_per_row, seed, rank, feedback="implicit",
-                  solver=L.CONJUGATE_GRADIENT, cg_steps=3, dynamic_lambda=True, lambda_=0.1, kernel=0, stage=0):
+                  solver=L.CONJUGATE_GRADIENT, cg_steps=3, dynamic_lambda=True, lambda_=0.1, kernel=0, stage=0, ctas=0):
         self = cls.__new__(cls)
         self._h = C.c_void_p(None)
         o = L.Options()
@@ -63,6 +64,7 @@ class Session:
         o.feedback = L.IMPLICIT if feedback == "implicit" else L.EXPLICIT
         o.solver, o.cg_steps, o.dynamic_lambda, o.lambda_, o.kernel = int(solver), int(cg_steps), int(dynamic_lambda), float(lambda_), int(kernel)
         o.reserved[0] = int(stage)
+        o.reserved[1] = int(ctas)
         self.rank, self.n_user, self.n_item = int(rank), int(n_user_global), int(n_item)
         L.check(L.lib().b200als_create_synthetic(C.byref(self._h), int(n_user_local), int(user_offset), int(n_user_global),
                                                  int(n_item), int(nnz_per_row), int(seed), int(rank), C.byref(o)))
