@@ -32,6 +32,7 @@ struct SolveParams {
   int n_list;
   const int* n_list_dev;    // when non-null the list length is read from device memory (pipelined calls)
   int ptr_base;             // ptr[] values are offsets into a buffer that starts at this absolute offset
+  int row_begin;            // without a row list: solve rows [row_begin, row_begin + n_targets)
   unsigned long long* ticket;
   double* loss_partials;  // [gridDim.x]
   int* status;            // != 0: some system was not positive definite
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(256) als_cg_generic_kernel(SolveParams<T> P) {
     if (lane == 0) t = atomicAdd(P.ticket, 1ULL);
     t = __shfl_sync(kFull, t, 0);
     if (t >= total) break;
-    const int row = P.row_list ? P.row_list[t] : (int)t;
+    const int row = P.row_list ? P.row_list[t] : (int)t + P.row_begin;
     const int p1 = P.ptr[row] - P.ptr_base, p2 = P.ptr[row + 1] - P.ptr_base;
     T* y = P.Y + (size_t)row * k;
     if (p1 >= p2) {  // wrmf_implicit.hpp:281 / wrmf_explicit.hpp:144
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(256) als_chol_generic_kernel(SolveParams<T> P)
     __syncthreads();
     if (tid == 0) {
       const unsigned long long t = atomicAdd(P.ticket, 1ULL);
-      s_row = (t < (unsigned long long)total) ? (P.row_list ? P.row_list[t] : (int)t) : -1;
+      s_row = (t < (unsigned long long)total) ? (P.row_list ? P.row_list[t] : (int)t + P.row_begin) : -1;
       s_fail = 0;
     }
     __syncthreads();

@@ -52,6 +52,7 @@ struct ResidentParams {
   int n_list;
   const int* n_list_dev;    // when non-null the list length is read from device memory (pipelined calls)
   int ptr_base;             // ptr[] values are offsets into a buffer that starts at this absolute offset
+  int row_begin;            // without a row list: solve rows [row_begin, row_begin + n_list)
   double* loss_partials;    // [gridDim.x]
 };
 
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(kResThreads, kCtas) als_cg_resident_kernel(Res
   auto valid = [&](int i) -> bool { return (long long)blockIdx.x + (long long)i * stride < n_list; };
   auto row_of = [&](int i) -> int {  // i-th row of this CTA (caller checks valid(i))
     const long long t = (long long)blockIdx.x + (long long)i * stride;
-    return P.row_list ? __ldg(P.row_list + t) : (int)t;
+    return P.row_list ? __ldg(P.row_list + t) : (int)t + P.row_begin;
   };
   // Every warp stages ITS OWN 20 gathered rows (+ its own copy of the warm-start y) with one 512-byte bulk
   // copy per owner lane, so the four warps do identical work and never wait for a producer warp.

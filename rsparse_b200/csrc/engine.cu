@@ -292,6 +292,8 @@ struct HalfOpts {
   double lambda;
   int stage = 0;  // tile staging of the resident kernel: 0 default, 1 cp.async.bulk (UBLKCP), 2 cp.async (LDGSTS)
   int ctas = 0;   // resident CTAs per SM the kernel is compiled for: 0 default, 3 or 4
+  int row_begin = 0, row_count = -1;  // solve only rows [row_begin, row_begin + row_count) of the block (-1: all)
+  bool reset_loss = true;             // zero the loss accumulator first (false: add to it)
 };
 constexpr int kDefaultCtas = 3;
 constexpr int kDefaultStage = 1;  // LDGSTS: measured 6 % faster than the UBLKCP variant on C3 (profiles/)
@@ -337,9 +339,14 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
   if (o.solver == B200ALS_NNLS) return fail(B200ALS_EUNSUPPORTED, "solver = nnls is not implemented (SURVEY 8f-4)");
   if (o.solver != B200ALS_CHOLESKY && o.solver != B200ALS_CONJUGATE_GRADIENT) return fail(B200ALS_EINVAL, "unknown solver code");
   if (o.feedback == B200ALS_IMPLICIT && !G && !diag) return fail(B200ALS_EINVAL, "implicit feedback needs XtX");
-  CU(cudaMemsetAsync(c.loss_acc.p, 0, sizeof(double), c.stream));
-  CU(cudaMemsetAsync(c.status.p, 0, sizeof(int), c.stream));
+  if (o.reset_loss) {
+    CU(cudaMemsetAsync(c.loss_acc.p, 0, sizeof(double), c.stream));
+    CU(cudaMemsetAsync(c.status.p, 0, sizeof(int), c.stream));
+  }
   if (A.n_cols == 0) return B200ALS_OK;
+  const bool sub_range = (o.row_count >= 0);
+  const int n_rows_here = sub_range ? o.row_count : A.n_cols;
+  if (n_rows_here == 0) return B200ALS_OK;
   SolveParams<T> P;
   P.ptr = A.ptr.i32();
   P.idx = A.idx.i32();
@@ -348,7 +355,8 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
   P.Y = Y;
   P.G = (o.feedback == B200ALS_IMPLICIT) ? G : nullptr;
   P.k = k;
-  P.n_targets = A.n_cols;
+  P.n_targets = n_rows_here;
+  P.row_begin = sub_range ? o.row_begin : 0;
   P.feedback = o.feedback;
   P.cg_steps = o.cg_steps;
   P.dynamic_lambda = o.dynamic_lambda;
@@ -366,7 +374,7 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
   auto run_generic_cg = [&](const int32_t* list, int n_list) -> int {
     P.row_list = list;
     P.n_list = n_list;
-    const int n_work = list ? n_list : A.n_cols;
+    const int n_work = list ? n_list : n_rows_here;
     if (n_work == 0) return B200ALS_OK;
     CU(cudaMemsetAsync(c.ticket.p, 0, sizeof(unsigned long long), c.stream));
     int grid = 0;
@@ -387,7 +395,7 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
                                            std::to_string(smem) + " B)");
     CU(cudaFuncSetAttribute(als_chol_generic_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (smem + 1024)));
-    const int grid = std::min(c.sm_count * per_sm, std::max(1, A.n_cols));
+    const int grid = std::min(c.sm_count * per_sm, std::max(1, n_rows_here));
     CU(cudaMemsetAsync(c.ticket.p, 0, sizeof(unsigned long long), c.stream));
     als_chol_generic_kernel<T><<<grid, 256, smem, c.stream>>>(P);
     LAUNCHED(); CU(cudaGetLastError());
@@ -408,6 +416,7 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
   }
   if constexpr (sizeof(T) == 4) {
     TRY(classify_rows(c, A));
+    if (sub_range && !A.all_short) return fail(B200ALS_EINVAL, "row sub-ranges need a block without empty or long rows");
     if (A.n_empty > 0) {
       zero_empty_rows_kernel<T><<<(unsigned)(((long long)A.n_cols * k + 255) / 256), 256, 0, c.stream>>>(P.ptr, A.n_cols, k, Y);
       LAUNCHED(); CU(cudaGetLastError());
@@ -426,12 +435,13 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
       R.dynamic_lambda = o.dynamic_lambda;
       R.lambda = (float)o.lambda;
       R.row_list = A.all_short ? nullptr : A.short_list.i32();
-      R.n_list = A.n_short;
+      R.n_list = sub_range ? n_rows_here : A.n_short;
       R.n_list_dev = nullptr;
       R.ptr_base = 0;
+      R.row_begin = sub_range ? o.row_begin : 0;
       R.loss_partials = P.loss_partials;
       const int ctas = (o.ctas == 3 || o.ctas == 4) ? o.ctas : kDefaultCtas;
-      const int grid = std::min(c.sm_count * ctas, A.n_short);
+      const int grid = std::min(c.sm_count * ctas, R.n_list);
       const size_t smem = sizeof(ResidentSmem);
       const bool full_g = (o.feedback == B200ALS_IMPLICIT) && !diag;
       auto launch = [&](auto kern) -> cudaError_t {
@@ -677,7 +687,7 @@ static int stateless_pipelined(const b200als_csc* A, const float* X, float* Y, c
     R.ptr = b.ptr.i32(); R.idx = b.idx.i32(); R.val = b.val32.f32();
     R.X = pc.X.f32(); R.Y = b.Y.f32(); R.diag = diag; R.G = nullptr;
     R.feedback = o.feedback; R.cg_steps = o.cg_steps; R.dynamic_lambda = o.dynamic_lambda; R.lambda = (float)o.lambda;
-    R.row_list = b.short_list.i32(); R.n_list = 0; R.n_list_dev = b.counts.i32(); R.ptr_base = (int)e0;
+    R.row_list = b.short_list.i32(); R.n_list = 0; R.n_list_dev = b.counts.i32(); R.ptr_base = (int)e0; R.row_begin = 0;
     R.loss_partials = c.loss_partials.f64();
     als_cg_resident_kernel<false, 1, 3><<<res_grid, kResThreads, res_smem, c.stream>>>(R);
     LAUNCHED(); CU(cudaGetLastError());
@@ -688,7 +698,7 @@ static int stateless_pipelined(const b200als_csc* A, const float* X, float* Y, c
       P.ptr = b.ptr.i32(); P.idx = b.idx.i32(); P.val = b.val32.f32(); P.X = pc.X.f32(); P.Y = b.Y.f32();
       P.G = implicit ? Glong : nullptr; P.k = k; P.n_targets = nr; P.feedback = o.feedback; P.cg_steps = o.cg_steps;
       P.dynamic_lambda = o.dynamic_lambda; P.lambda = o.lambda; P.row_list = b.long_list.i32(); P.n_list = 0;
-      P.n_list_dev = b.counts.i32() + 1; P.ptr_base = (int)e0; P.ticket = c.ticket.u64();
+      P.n_list_dev = b.counts.i32() + 1; P.ptr_base = (int)e0; P.row_begin = 0; P.ticket = c.ticket.u64();
       P.loss_partials = c.loss_partials.f64(); P.status = c.status.i32();
       CU(cudaMemsetAsync(c.ticket.p, 0, sizeof(unsigned long long), c.stream));
       als_cg_generic_kernel<float, 4><<<gen_grid, 256, 0, c.stream>>>(P);
@@ -891,6 +901,9 @@ struct b200als_session {
   DevBuf cnt[2];   // cnt[w][j] = nnz of row j of factor matrix w (global), for the dynamic-lambda regulariser
   DevBuf G, G64, Vt, Q, Qt, diag, B64, Btmp, Bf, scratch;
   bool basis_identity = true;
+  std::vector<int32_t> ranges[2];   // [3*world]: every rank's [begin, end, can_chunk) per orientation (multi-GPU)
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_chunk[8] = {}, ev_comm_done = nullptr;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   float t_gram = 0, t_prep = 0, t_solve = 0, t_comm = 0;
 };
@@ -926,6 +939,11 @@ static int session_alloc(b200als_session* s) {
   LAUNCHED(); CU(cudaGetLastError());
   s->basis_identity = true;
   for (auto& e : s->ev) CU(cudaEventCreate(&e));
+  for (auto& e : s->ev_chunk) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&s->ev_comm_done, cudaEventDisableTiming));
+  int lo = 0, hi = 0;
+  CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  CU(cudaStreamCreateWithPriority(&s->comm_stream, cudaStreamNonBlocking, hi));  // the exchange must get SM slots early
   return B200ALS_OK;
 }
 
@@ -1011,6 +1029,10 @@ extern "C" int b200als_destroy(b200als_session* s) {
   if (!s) return B200ALS_OK;
   for (auto& e : s->ev)
     if (e) cudaEventDestroy(e);
+  for (auto& e : s->ev_chunk)
+    if (e) cudaEventDestroy(e);
+  if (s->ev_comm_done) cudaEventDestroy(s->ev_comm_done);
+  if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
   delete s;
   return B200ALS_OK;
 }
@@ -1022,6 +1044,7 @@ extern "C" int b200als_set_shard(b200als_session* s, int which, int32_t begin, i
     return fail(B200ALS_EINVAL, "shard range does not match the uploaded block");
   s->shard_begin[which] = begin;
   s->shard_end[which] = end;
+  s->ranges[which].clear();
   return B200ALS_OK;
 }
 
@@ -1102,29 +1125,46 @@ extern "C" int b200als_randomize_factors(b200als_session* s, int which, uint64_t
   return B200ALS_OK;
 }
 
-// all-gather of the freshly solved slices (unequal block sizes => one broadcast per owner, grouped)
-static int exchange_slices(b200als_session* s, int which) {
-  if (g_comm.world <= 1) return B200ALS_OK;
+// every rank learns every rank's [begin, end) of the solved matrix (cached until set_shard)
+static int gather_ranges(b200als_session* s, int which) {
+  if (!s->ranges[which].empty()) return B200ALS_OK;
   Ctx& c = ctx();
-  // every rank learns every rank's [begin, end)
-  std::vector<int32_t> ranges(2 * g_comm.world);
+  TRY(classify_rows(c, s->csc[which]));
+  std::vector<int32_t> ranges(3 * g_comm.world);
   DevBuf d;
-  CU(d.ensure(sizeof(int32_t) * 2 * g_comm.world));
-  int32_t mine[2] = {s->shard_begin[which], s->shard_end[which]};
-  CU(cudaMemcpyAsync(d.i32() + 2 * g_comm.rank, mine, sizeof(mine), cudaMemcpyHostToDevice, c.stream));
-  NC(g_nccl.AllGather(d.i32() + 2 * g_comm.rank, d.p, 2, ncclInt32, g_comm.comm, c.stream));
-  CU(cudaMemcpyAsync(ranges.data(), d.p, sizeof(int32_t) * 2 * g_comm.world, cudaMemcpyDeviceToHost, c.stream));
+  CU(d.ensure(sizeof(int32_t) * 3 * g_comm.world));
+  int32_t mine[3] = {s->shard_begin[which], s->shard_end[which],
+                     (s->csc[which].all_short && s->csc[which].n_cols >= 4 * 4096) ? 1 : 0};
+  CU(cudaMemcpyAsync(d.i32() + 3 * g_comm.rank, mine, sizeof(mine), cudaMemcpyHostToDevice, c.stream));
+  NC(g_nccl.AllGather(d.i32() + 3 * g_comm.rank, d.p, 3, ncclInt32, g_comm.comm, c.stream));
+  CU(cudaMemcpyAsync(ranges.data(), d.p, sizeof(int32_t) * 3 * g_comm.world, cudaMemcpyDeviceToHost, c.stream));
   CU(cudaStreamSynchronize(c.stream));
+  s->ranges[which] = ranges;
+  return B200ALS_OK;
+}
+// exchange of the freshly solved rows: chunk `ch` of `n_ch` of every rank's block, one broadcast per owner
+// (unequal block sizes allowed), grouped, on stream `st`.
+static int exchange_chunk(b200als_session* s, int which, int ch, int n_ch, cudaStream_t st) {
+  if (g_comm.world <= 1) return B200ALS_OK;
+  const std::vector<int32_t>& ranges = s->ranges[which];
   float* M = s->fac[which].f32();
   NC(g_nccl.GroupStart());
   for (int r = 0; r < g_comm.world; r++) {
-    const size_t cnt = (size_t)(ranges[2 * r + 1] - ranges[2 * r]) * (size_t)s->k;
-    if (cnt == 0) continue;
-    float* p = M + (size_t)ranges[2 * r] * s->k;
-    NC(g_nccl.Broadcast(p, p, cnt, ncclFloat, r, g_comm.comm, c.stream));
+    const long long rb = ranges[3 * r], len = ranges[3 * r + 1] - rb;
+    const long long cb = rb + len * ch / n_ch, ce = rb + len * (ch + 1) / n_ch;
+    if (ce <= cb) continue;
+    float* p = M + (size_t)cb * s->k;
+    NC(g_nccl.Broadcast(p, p, (size_t)(ce - cb) * (size_t)s->k, ncclFloat, r, g_comm.comm, st));
   }
   NC(g_nccl.GroupEnd());
   return B200ALS_OK;
+}
+__global__ void finalize_gram_kernel(double* __restrict__ G64, float* __restrict__ G, int k, double lambda) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= k * k) return;
+  const double v = G64[e] + (((e / k) == (e % k)) ? lambda : 0.0);
+  G64[e] = v;
+  G[e] = (float)v;
 }
 
 // solve for `which`; Yout == nullptr: in place into the session's factors.  Yout != nullptr (transform_):
@@ -1143,8 +1183,18 @@ static int session_half(b200als_session* s, int which, int solver, float* Yout, 
   CU(cudaEventRecord(s->ev[0], c.stream));
   const float* G = nullptr;
   const float* diag = nullptr;
+  if (g_comm.world > 1) TRY(gather_ranges(s, which));
   if (implicit) {
-    TRY(run_gram<float>(c, X, s->k, n_fixed, o.lambda, s->G.f32(), s->G64.f64()));
+    if (g_comm.world > 1) {
+      // each rank reduces its 1/world slice of the fixed matrix; the k x k partials are summed over NVLink
+      const long long b = n_fixed * g_comm.rank / g_comm.world, e = n_fixed * (g_comm.rank + 1) / g_comm.world;
+      TRY(run_gram<float>(c, X + (size_t)b * s->k, s->k, e - b, 0.0, s->G.f32(), s->G64.f64()));
+      NC(g_nccl.AllReduce(s->G64.p, s->G64.p, (size_t)s->k * s->k, ncclDouble, ncclSum, g_comm.comm, c.stream));
+      finalize_gram_kernel<<<(s->k * s->k + 255) / 256, 256, 0, c.stream>>>(s->G64.f64(), s->G.f32(), s->k, o.lambda);
+      LAUNCHED(); CU(cudaGetLastError());
+    } else {
+      TRY(run_gram<float>(c, X, s->k, n_fixed, o.lambda, s->G.f32(), s->G64.f64()));
+    }
     G = s->G.f32();
   }
   CU(cudaEventRecord(s->ev[1], c.stream));
@@ -1173,9 +1223,30 @@ static int session_half(b200als_session* s, int which, int solver, float* Yout, 
     G = nullptr;
   }
   CU(cudaEventRecord(s->ev[2], c.stream));
-  TRY(solve_rows<float>(c, A, X, Y, G, diag, s->k, o));
-  CU(cudaEventRecord(s->ev[3], c.stream));
-  if (!Yout) TRY(exchange_slices(s, which));
+  if (g_comm.world > 1 && !Yout) {
+    // the block is solved in chunks; chunk c travels to the other ranks (priority stream) while chunk c+1 is solved
+    int n_ch = 4;   // every rank must take the same decision: chunk only if every block qualifies
+    for (int r = 0; r < g_comm.world; r++)
+      if (!s->ranges[which][3 * r + 2]) n_ch = 1;
+    for (int ch = 0; ch < n_ch; ch++) {
+      HalfOpts oc = o;
+      if (n_ch > 1) {
+        oc.row_begin = (int)((long long)A.n_cols * ch / n_ch);
+        oc.row_count = (int)((long long)A.n_cols * (ch + 1) / n_ch) - oc.row_begin;
+      }
+      oc.reset_loss = (ch == 0);
+      TRY(solve_rows<float>(c, A, X, Y, G, diag, s->k, oc));
+      CU(cudaEventRecord(s->ev_chunk[ch], c.stream));
+      CU(cudaStreamWaitEvent(s->comm_stream, s->ev_chunk[ch], 0));
+      TRY(exchange_chunk(s, which, ch, n_ch, s->comm_stream));
+    }
+    CU(cudaEventRecord(s->ev[3], c.stream));
+    CU(cudaEventRecord(s->ev_comm_done, s->comm_stream));
+    CU(cudaStreamWaitEvent(c.stream, s->ev_comm_done, 0));
+  } else {
+    TRY(solve_rows<float>(c, A, X, Y, G, diag, s->k, o));
+    CU(cudaEventRecord(s->ev[3], c.stream));
+  }
   CU(cudaEventRecord(s->ev[4], c.stream));
   // loss: local row sums -> global
   double rows_sum = 0.0;
