@@ -176,7 +176,9 @@ __global__ void __launch_bounds__(256) als_cg_generic_kernel(SolveParams<T> P) {
 #pragma unroll
     for (int e = 0; e < KPL; e++) p[e] = r[e];
     double rsold = (double)dot_lanes<T, KPL>(r, r);
-    for (int it = 0; it < P.cg_steps; it++) {
+    // guard absent from the reference: rsold == 0 (row converged exactly) would give alpha = 0/0 = NaN
+    const int n_steps = (rsold > 0.0) ? P.cg_steps : 0;
+    for (int it = 0; it < n_steps; it++) {
       // Ap = XtX p + X_nnz ((c-1) % X_nnz' p)        (wrmf_implicit.hpp:22)
       // Ap = X_nnz (X_nnz' p) + lambda p             (wrmf_explicit.hpp:21)
       fused_pass<T, KPL>(P, p1, n, p, acc, implicit ? kApImplicit : kApExplicit);
@@ -188,7 +190,8 @@ __global__ void __launch_bounds__(256) als_cg_generic_kernel(SolveParams<T> P) {
 #pragma unroll
         for (int e = 0; e < KPL; e++) Ap[e] = acc[e] + lam_use * p[e];
       }
-      const double alpha = rsold / (double)dot_lanes<T, KPL>(p, Ap);
+      const double pAp = (double)dot_lanes<T, KPL>(p, Ap);
+      const double alpha = (pAp != 0.0) ? rsold / pAp : 0.0;
       const T a = (T)alpha;
 #pragma unroll
       for (int e = 0; e < KPL; e++) {

@@ -308,7 +308,10 @@ __global__ void __launch_bounds__(kResThreads, kCtas) als_cg_resident_kernel(Res
     }
     float4 p = r;
     float rsold = warp_sum(dot4(r, r));
-    for (int it = 0; it < P.cg_steps; it++) {
+    // Guard the reference does not have (wrmf_implicit.hpp:23 computes rsold / (p'Ap) = 0/0 -> NaN once a row
+    // has converged exactly, e.g. when the same half-iteration is repeated): a zero residual skips the loop.
+    const int n_steps = (rsold > 0.0f) ? P.cg_steps : 0;
+    for (int it = 0; it < n_steps; it++) {
       v = resident_sweep<kFullG>(xt, p, cq, implicit ? 1 : 3, slot, S, sweep++, P.G, u_own);
       float4 Ap;
       if (implicit) {
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(kResThreads, kCtas) als_cg_resident_kernel(Res
         Ap = make_float4(fmaf(lam_use, p.x, v.x), fmaf(lam_use, p.y, v.y), fmaf(lam_use, p.z, v.z), fmaf(lam_use, p.w, v.w));
       }
       const float pAp = warp_sum(dot4(p, Ap));
-      const float a = __fdiv_rn(rsold, pAp);
+      const float a = (pAp != 0.0f) ? __fdiv_rn(rsold, pAp) : 0.0f;
       x.x = fmaf(a, p.x, x.x); x.y = fmaf(a, p.y, x.y); x.z = fmaf(a, p.z, x.z); x.w = fmaf(a, p.w, x.w);
       r.x = fmaf(-a, Ap.x, r.x); r.y = fmaf(-a, Ap.y, r.y); r.z = fmaf(-a, Ap.z, r.z); r.w = fmaf(-a, Ap.w, r.w);
       uy = fmaf(a, u_own, uy);
