@@ -60,7 +60,7 @@ struct __align__(128) ResidentSmem {
   // per-warp tile slot: rows 0..19 = this warp's gathered rows (item j = w + 4q), row 20 = the warm-start y
   float tile[kResWarps][(kResIPW + 1) * kResK];
   float vbuf[2][kResWarps][kResK];         // cross-warp partial sums (double buffered per sweep)
-  float wbuf[kResWarps][32];               // per-warp w_j broadcast: 4 blocks of 5, each padded to 8 floats
+  float2 wbuf[kResWarps][32];              // per-warp (w_j, w_j) broadcast: 4 blocks of 5 pairs, each padded to 8
   uint64_t bar[kResWarps];                 // one mbarrier per warp slot
   double red[32];
 };
@@ -117,9 +117,28 @@ __device__ __forceinline__ int resident_natural_slot(int q, int lane) {
   return 10 * (h1 ^ ((lane >> 4) & 1)) + 5 * (h2 ^ ((lane >> 3) & 1)) + r2;
 }
 
+// Packed fp32 math (Blackwell FFMA2 / FMUL2 / FADD2: one instruction per register PAIR): the float4 held per
+// gathered row is two aligned pairs, so the dot products and the axpy take half the issue slots.
+__device__ __forceinline__ float2 lo2(const float4& a) { return make_float2(a.x, a.y); }
+__device__ __forceinline__ float2 hi2(const float4& a) { return make_float2(a.z, a.w); }
+__device__ __forceinline__ float4 join4(const float2& l, const float2& h) { return make_float4(l.x, l.y, h.x, h.y); }
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
-  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+  float2 m = __fmul2_rn(lo2(a), lo2(b));
+  m = __ffma2_rn(hi2(a), hi2(b), m);
+  return m.x + m.y;
 }
+// a * s + c  /  a (.) b + c on float4 operands
+__device__ __forceinline__ float4 axpy4(float s, const float4& a, const float4& c) {
+  const float2 ss = make_float2(s, s);
+  return join4(__ffma2_rn(ss, lo2(a), lo2(c)), __ffma2_rn(ss, hi2(a), hi2(c)));
+}
+__device__ __forceinline__ float4 fma4(const float4& a, const float4& b, const float4& c) {
+  return join4(__ffma2_rn(lo2(a), lo2(b), lo2(c)), __ffma2_rn(hi2(a), hi2(b), hi2(c)));
+}
+__device__ __forceinline__ float4 add4(const float4& a, const float4& b) {
+  return join4(__fadd2_rn(lo2(a), lo2(b)), __fadd2_rn(hi2(a), hi2(b)));
+}
+__device__ __forceinline__ float4 neg4(const float4& a) { return make_float4(-a.x, -a.y, -a.z, -a.w); }
 
 // mode: 0 r0-implicit  w = c - (c-1)u ; 1 Ap-implicit  w = (c-1)u ; 2 r0-explicit  w = c - u ; 3 Ap-explicit  w = u
 template <bool kFullG>
@@ -139,24 +158,30 @@ __device__ __forceinline__ float4 resident_sweep(const float4 (&xt)[kResIPW], co
     case 2: wq = cq - u; break;
     default: wq = u; break;
   }
-  if (slot >= 0) S.wbuf[w][(slot / 5) * 8 + (slot % 5)] = wq;
+  if (slot >= 0) S.wbuf[w][(slot / 5) * 8 + (slot % 5)] = make_float2(wq, wq);
   __syncwarp();
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  // acc = sum_j w_j x_j over this warp's rows: two independent accumulator sets (even / odd rows)
+  float2 a0l = make_float2(0.f, 0.f), a0h = a0l, a1l = a0l, a1h = a0l;
   const int bsel = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);  // this lane's register blocks hold natural blocks blk ^ bsel
 #pragma unroll
   for (int blk = 0; blk < 4; blk++) {
-    const float* wp = &S.wbuf[w][(blk ^ bsel) * 8];
-    const float4 wv = *reinterpret_cast<const float4*>(wp);
-    const float ws[5] = {wv.x, wv.y, wv.z, wv.w, wp[4]};
+    const float2* wp = &S.wbuf[w][(blk ^ bsel) * 8];
+    const float4 w01 = *reinterpret_cast<const float4*>(wp);
+    const float4 w23 = *reinterpret_cast<const float4*>(wp + 2);
+    const float2 ws[5] = {lo2(w01), hi2(w01), lo2(w23), hi2(w23), wp[4]};
 #pragma unroll
     for (int i = 0; i < 5; i++) {
       const float4& x = xt[blk * 5 + i];
-      acc.x = fmaf(ws[i], x.x, acc.x);
-      acc.y = fmaf(ws[i], x.y, acc.y);
-      acc.z = fmaf(ws[i], x.z, acc.z);
-      acc.w = fmaf(ws[i], x.w, acc.w);
+      if (((blk * 5 + i) & 1) == 0) {
+        a0l = __ffma2_rn(ws[i], lo2(x), a0l);
+        a0h = __ffma2_rn(ws[i], hi2(x), a0h);
+      } else {
+        a1l = __ffma2_rn(ws[i], lo2(x), a1l);
+        a1h = __ffma2_rn(ws[i], hi2(x), a1h);
+      }
     }
   }
+  float4 acc = join4(__fadd2_rn(a0l, a1l), __fadd2_rn(a0h, a1h));
   __syncwarp();
   if constexpr (kFullG) {
     // (mode 0/1 only) this warp's slab of XtX * vec: columns j in [32w, 32w+32); vec_j lives in lane j/4 of
@@ -169,36 +194,22 @@ __device__ __forceinline__ float4 resident_sweep(const float4 (&xt)[kResIPW], co
         const float vj[4] = {__shfl_sync(kFull, vec.x, src), __shfl_sync(kFull, vec.y, src),
                              __shfl_sync(kFull, vec.z, src), __shfl_sync(kFull, vec.w, src)};
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-          const float4 gr = ldg_f4(G + (size_t)(src * 4 + c) * kResK + lane * 4);
-          g.x = fmaf(gr.x, vj[c], g.x);
-          g.y = fmaf(gr.y, vj[c], g.y);
-          g.z = fmaf(gr.z, vj[c], g.z);
-          g.w = fmaf(gr.w, vj[c], g.w);
-        }
+        for (int c = 0; c < 4; c++) g = axpy4(vj[c], ldg_f4(G + (size_t)(src * 4 + c) * kResK + lane * 4), g);
       }
       // r0: acc - G x ; Ap: acc + G p
-      const float sgn = (mode == 0) ? -1.0f : 1.0f;
-      acc.x = fmaf(sgn, g.x, acc.x);
-      acc.y = fmaf(sgn, g.y, acc.y);
-      acc.z = fmaf(sgn, g.z, acc.z);
-      acc.w = fmaf(sgn, g.w, acc.w);
+      acc = axpy4((mode == 0) ? -1.0f : 1.0f, g, acc);
     }
   }
   float* vb = &S.vbuf[sweep & 1][0][0];
   *reinterpret_cast<float4*>(vb + w * kResK + lane * 4) = acc;
   __syncthreads();
-  float4 v = *reinterpret_cast<const float4*>(vb + lane * 4);
-#pragma unroll
-  for (int ww = 1; ww < kResWarps; ww++) {
-    const float4 o = *reinterpret_cast<const float4*>(vb + ww * kResK + lane * 4);
-    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-  }
-  return v;
+  const float4 v0 = *reinterpret_cast<const float4*>(vb + lane * 4);
+  const float4 v1 = *reinterpret_cast<const float4*>(vb + 1 * kResK + lane * 4);
+  const float4 v2 = *reinterpret_cast<const float4*>(vb + 2 * kResK + lane * 4);
+  const float4 v3 = *reinterpret_cast<const float4*>(vb + 3 * kResK + lane * 4);
+  return add4(add4(add4(v0, v1), v2), v3);   // fixed order: identical in all four warps
 }
 
-// kStage: 0 = cp.async.bulk (TMA engine, UBLKCP; one 512-byte copy per owner lane, serialised through the
-// uniform datapath), 1 = cp.async 16 B per thread (LDGSTS; one warp-wide instruction per gathered row).
 // kCtas: resident CTAs per SM the register allocation is sized for (3: 168 registers, no spills; 4: 128
 // registers with ~170 B of spills per thread that stay in L1).
 template <bool kFullG, int kStage, int kCtas>
@@ -271,6 +282,7 @@ __global__ void __launch_bounds__(kResThreads, kCtas) als_cg_resident_kernel(Res
 
   float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
   if (!kFullG && implicit) dg = ldg_f4(P.diag + lane * 4);
+  const float4 ndg = neg4(dg);
   double warp_loss = 0.0;
   int sweep = 0;
 
@@ -302,9 +314,9 @@ __global__ void __launch_bounds__(kResThreads, kCtas) als_cg_resident_kernel(Res
     float4 r;
     if (implicit) {
       if (kFullG) r = v;
-      else r = make_float4(fmaf(-dg.x, x.x, v.x), fmaf(-dg.y, x.y, v.y), fmaf(-dg.z, x.z, v.z), fmaf(-dg.w, x.w, v.w));
+      else r = fma4(ndg, x, v);          // v - d (.) x
     } else {
-      r = make_float4(fmaf(-lam_use, x.x, v.x), fmaf(-lam_use, x.y, v.y), fmaf(-lam_use, x.z, v.z), fmaf(-lam_use, x.w, v.w));
+      r = axpy4(-lam_use, x, v);         // v - lambda_use x
     }
     float4 p = r;
     float rsold = warp_sum(dot4(r, r));
@@ -316,19 +328,19 @@ __global__ void __launch_bounds__(kResThreads, kCtas) als_cg_resident_kernel(Res
       float4 Ap;
       if (implicit) {
         if (kFullG) Ap = v;
-        else Ap = make_float4(fmaf(dg.x, p.x, v.x), fmaf(dg.y, p.y, v.y), fmaf(dg.z, p.z, v.z), fmaf(dg.w, p.w, v.w));
+        else Ap = fma4(dg, p, v);
       } else {
-        Ap = make_float4(fmaf(lam_use, p.x, v.x), fmaf(lam_use, p.y, v.y), fmaf(lam_use, p.z, v.z), fmaf(lam_use, p.w, v.w));
+        Ap = axpy4(lam_use, p, v);
       }
       const float pAp = warp_sum(dot4(p, Ap));
       const float a = (pAp != 0.0f) ? __fdiv_rn(rsold, pAp) : 0.0f;
-      x.x = fmaf(a, p.x, x.x); x.y = fmaf(a, p.y, x.y); x.z = fmaf(a, p.z, x.z); x.w = fmaf(a, p.w, x.w);
-      r.x = fmaf(-a, Ap.x, r.x); r.y = fmaf(-a, Ap.y, r.y); r.z = fmaf(-a, Ap.z, r.z); r.w = fmaf(-a, Ap.w, r.w);
+      x = axpy4(a, p, x);
+      r = axpy4(-a, Ap, r);
       uy = fmaf(a, u_own, uy);
       const float rsnew = warp_sum(dot4(r, r));
       if (rsnew < (float)B200ALS_CG_TOL) break;   // identical in all four warps (same data, same order)
       const float bt = __fdiv_rn(rsnew, rsold);
-      p.x = fmaf(p.x, bt, r.x); p.y = fmaf(p.y, bt, r.y); p.z = fmaf(p.z, bt, r.z); p.w = fmaf(p.w, bt, r.w);
+      p = axpy4(bt, p, r);
       rsold = rsnew;
     }
     if (w == 0) *reinterpret_cast<float4*>(P.Y + (size_t)rid0 * kResK + lane * 4) = x;
