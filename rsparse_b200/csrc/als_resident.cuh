@@ -60,6 +60,7 @@ struct __align__(128) ResidentSmem {
   // per-warp tile slot: rows 0..19 = this warp's gathered rows (item j = w + 4q), row 20 = the warm-start y
   float tile[kResWarps][(kResIPW + 1) * kResK];
   float vbuf[2][kResWarps][kResK];         // cross-warp partial sums (double buffered per sweep)
+  float sbuf[2][kResWarps];                // per-warp scalar partials riding the same exchange (p'Ap terms)
   float2 wbuf[kResWarps][32];              // per-warp (w_j, w_j) broadcast: 4 blocks of 5 pairs, each padded to 8
   uint64_t bar[kResWarps];                 // one mbarrier per warp slot
   double red[32];
@@ -140,27 +141,26 @@ __device__ __forceinline__ float4 add4(const float4& a, const float4& b) {
 }
 __device__ __forceinline__ float4 neg4(const float4& a) { return make_float4(-a.x, -a.y, -a.z, -a.w); }
 
-// mode: 0 r0-implicit  w = c - (c-1)u ; 1 Ap-implicit  w = (c-1)u ; 2 r0-explicit  w = c - u ; 3 Ap-explicit  w = u
-template <bool kFullG>
-__device__ __forceinline__ float4 resident_sweep(const float4 (&xt)[kResIPW], const float4& vec, float cq, int mode,
-                                                 int slot, ResidentSmem& S, int sweep, const float* __restrict__ G,
-                                                 float& u_own) {
-  const int lane = lane_id(), w = warp_id();
+// ---- one CG sweep, in two halves -------------------------------------------------------------------------
+// (A) u_j = x_j . vec for this warp's 20 rows; the owner lane of slot q returns the full sum (0 on padding lanes)
+__device__ __forceinline__ float sweep_dots(const float4 (&xt)[kResIPW], const float4& vec) {
   float t[kResIPW];
 #pragma unroll
   for (int q = 0; q < kResIPW; q++) t[q] = dot4(xt[q], vec);
-  const float u = Halver<kResIPW>::template run<16, 2>(t, lane);
-  u_own = u;
-  float wq;
-  switch (mode) {
-    case 0: wq = cq - (cq - 1.0f) * u; break;
-    case 1: wq = (cq - 1.0f) * u; break;
-    case 2: wq = cq - u; break;
-    default: wq = u; break;
-  }
+  return Halver<kResIPW>::template run<16, 2>(t, lane_id());
+}
+// (B) acc = sum_j wq_j x_j over the warp's rows (+ this warp's slab of XtX * vec when kFullG), 4-way cross-warp
+//     sum through shared memory; `spart` (a per-warp scalar, identical in all lanes) is summed across the four
+//     warps on the way and returned in `ssum`.
+template <bool kFullG>
+__device__ __forceinline__ float4 sweep_apply(const float4 (&xt)[kResIPW], float wq, int slot, const float4& vec,
+                                              int gmode /* 0: none, 1: acc - G vec, 2: acc + G vec */,
+                                              ResidentSmem& S, int sweep, const float* __restrict__ G, float spart,
+                                              float& ssum) {
+  const int lane = lane_id(), w = warp_id();
   if (slot >= 0) S.wbuf[w][(slot / 5) * 8 + (slot % 5)] = make_float2(wq, wq);
   __syncwarp();
-  // acc = sum_j w_j x_j over this warp's rows: two independent accumulator sets (even / odd rows)
+  // two independent accumulator sets (even / odd rows)
   float2 a0l = make_float2(0.f, 0.f), a0h = a0l, a1l = a0l, a1h = a0l;
   const int bsel = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);  // this lane's register blocks hold natural blocks blk ^ bsel
 #pragma unroll
@@ -184,29 +184,31 @@ __device__ __forceinline__ float4 resident_sweep(const float4 (&xt)[kResIPW], co
   float4 acc = join4(__fadd2_rn(a0l, a1l), __fadd2_rn(a0h, a1h));
   __syncwarp();
   if constexpr (kFullG) {
-    // (mode 0/1 only) this warp's slab of XtX * vec: columns j in [32w, 32w+32); vec_j lives in lane j/4 of
-    // every warp (component j%4).  The slabs are summed with the tile partials below.
-    if (mode <= 1) {
+    // this warp's slab of XtX * vec: columns j in [32w, 32w+32); vec_j lives in lane j/4 (component j%4)
+    if (gmode != 0) {
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 2
       for (int g4 = 0; g4 < 8; g4++) {
-        const int src = w * 8 + g4;  // lane holding vec[4*src .. 4*src+3]
+        const int src = w * 8 + g4;
         const float vj[4] = {__shfl_sync(kFull, vec.x, src), __shfl_sync(kFull, vec.y, src),
                              __shfl_sync(kFull, vec.z, src), __shfl_sync(kFull, vec.w, src)};
 #pragma unroll
         for (int c = 0; c < 4; c++) g = axpy4(vj[c], ldg_f4(G + (size_t)(src * 4 + c) * kResK + lane * 4), g);
       }
-      // r0: acc - G x ; Ap: acc + G p
-      acc = axpy4((mode == 0) ? -1.0f : 1.0f, g, acc);
+      acc = axpy4((gmode == 1) ? -1.0f : 1.0f, g, acc);
+      spart += warp_sum(dot4(vec, g));   // vec' (G_slab vec): this warp's share of vec' XtX vec
     }
   }
   float* vb = &S.vbuf[sweep & 1][0][0];
   *reinterpret_cast<float4*>(vb + w * kResK + lane * 4) = acc;
+  if (lane == 0) S.sbuf[sweep & 1][w] = spart;
   __syncthreads();
   const float4 v0 = *reinterpret_cast<const float4*>(vb + lane * 4);
   const float4 v1 = *reinterpret_cast<const float4*>(vb + 1 * kResK + lane * 4);
   const float4 v2 = *reinterpret_cast<const float4*>(vb + 2 * kResK + lane * 4);
   const float4 v3 = *reinterpret_cast<const float4*>(vb + 3 * kResK + lane * 4);
+  const float4 sv = *reinterpret_cast<const float4*>(&S.sbuf[sweep & 1][0]);
+  ssum = ((sv.x + sv.y) + sv.z) + sv.w;
   return add4(add4(add4(v0, v1), v2), v3);   // fixed order: identical in all four warps
 }
 
@@ -303,14 +305,23 @@ __global__ void __launch_bounds__(kResThreads, kCtas) als_cg_resident_kernel(Res
     if (valid(i + 1)) issue_tile(rid1, n1, idx1);
     int idx2 = 0, p3 = 0, p3e = 0, rid4 = -1;
     float val2 = 0.f;
-    if (valid(i + 2) && my_j < n2) { idx2 = __ldg(P.idx + p2 + my_j); val2 = __ldg(P.val + p2 + my_j); }
-    if (valid(i + 3)) { p3 = __ldg(P.ptr + rid3) - P.ptr_base; p3e = __ldg(P.ptr + rid3 + 1) - P.ptr_base; }
-    if (valid(i + 4)) rid4 = row_of(i + 4);
+    if (valid(i + 2) && my_j < n2) { idx2 = ld_pinned_i32(P.idx + p2 + my_j); val2 = ld_pinned_f32(P.val + p2 + my_j); }
+    if (valid(i + 3)) { p3 = ld_pinned_i32(P.ptr + rid3); p3e = ld_pinned_i32(P.ptr + rid3 + 1); }
+    if (valid(i + 4)) rid4 = P.row_list ? ld_pinned_i32(P.row_list + ((long long)blockIdx.x + (long long)(i + 4) * stride))
+                                        : row_of(i + 4);
     // ---- CG ---------------------------------------------------------------------------------------------
+    // Same iterates as cg_solver_implicit / cg_solver_explicit, with the dependent chain shortened:
+    //   * p'Ap = p'(XtX p) + sum_j (c_j-1) u_j^2   (u = X_nnz' p is already reduced per row; the XtX term is
+    //     d.p^2 in the eigenbasis, lambda p.p for explicit feedback) -- no dot(p, Ap) after the exchange;
+    //   * X_nnz' p_new = X_nnz' r_new + beta X_nnz' p_old, so the next sweep's row dots start from r_new while the
+    //     |r_new|^2 reduction and the division for beta are still in flight.
     const float lam_use = implicit ? P.lambda : (P.lambda * (P.dynamic_lambda ? (float)n : 1.0f));
-    float u_own;
-    float4 v = resident_sweep<kFullG>(xt, x, cq, implicit ? 0 : 2, slot, S, sweep++, P.G, u_own);
-    float uy = u_own;  // running X_nnz' y for the loss
+    const bool mine = (my_j < n);
+    float dummy;
+    float u_p = sweep_dots(xt, x);   // u_x = X_nnz' x0 (owner lanes)
+    float uy = u_p;                  // running X_nnz' y for the loss
+    float4 v = sweep_apply<kFullG>(xt, implicit ? (cq - (cq - 1.0f) * u_p) : (cq - u_p), slot, x,
+                                   (kFullG && implicit) ? 1 : 0, S, sweep++, P.G, 0.0f, dummy);
     float4 r;
     if (implicit) {
       if (kFullG) r = v;
@@ -323,8 +334,19 @@ __global__ void __launch_bounds__(kResThreads, kCtas) als_cg_resident_kernel(Res
     // Guard the reference does not have (wrmf_implicit.hpp:23 computes rsold / (p'Ap) = 0/0 -> NaN once a row
     // has converged exactly, e.g. when the same half-iteration is repeated): a zero residual skips the loop.
     const int n_steps = (rsold > 0.0f) ? P.cg_steps : 0;
+    if (n_steps > 0) u_p = sweep_dots(xt, p);
     for (int it = 0; it < n_steps; it++) {
-      v = resident_sweep<kFullG>(xt, p, cq, implicit ? 1 : 3, slot, S, sweep++, P.G, u_own);
+      // p' XtX p without the tile part (independent of the sweep below => overlaps with it)
+      float pGp = 0.0f;
+      if (implicit) {
+        if (!kFullG) pGp = warp_sum(dot4(p, make_float4(dg.x * p.x, dg.y * p.y, dg.z * p.z, dg.w * p.w)));
+      } else {
+        pGp = lam_use * warp_sum(dot4(p, p));
+      }
+      const float cw = implicit ? (cq - 1.0f) : 1.0f;
+      const float spart = warp_sum(mine ? cw * u_p * u_p : 0.0f);
+      float ssum;
+      v = sweep_apply<kFullG>(xt, cw * u_p, slot, p, (kFullG && implicit) ? 2 : 0, S, sweep++, P.G, spart, ssum);
       float4 Ap;
       if (implicit) {
         if (kFullG) Ap = v;
@@ -332,15 +354,18 @@ __global__ void __launch_bounds__(kResThreads, kCtas) als_cg_resident_kernel(Res
       } else {
         Ap = axpy4(lam_use, p, v);
       }
-      const float pAp = warp_sum(dot4(p, Ap));
+      const float pAp = pGp + ssum;
       const float a = (pAp != 0.0f) ? __fdiv_rn(rsold, pAp) : 0.0f;
       x = axpy4(a, p, x);
       r = axpy4(-a, Ap, r);
-      uy = fmaf(a, u_own, uy);
-      const float rsnew = warp_sum(dot4(r, r));
-      if (rsnew < (float)B200ALS_CG_TOL) break;   // identical in all four warps (same data, same order)
+      uy = fmaf(a, u_p, uy);
+      if (it + 1 == n_steps) break;                       // nothing after the last step needs |r|^2 (cf. :26-28)
+      const float rsnew = warp_sum(dot4(r, r));           // in flight ...
+      const float u_r = sweep_dots(xt, r);                // ... while the next sweep's row dots run
+      if (rsnew < (float)B200ALS_CG_TOL) break;           // identical in all four warps (same data, same order)
       const float bt = __fdiv_rn(rsnew, rsold);
       p = axpy4(bt, p, r);
+      u_p = fmaf(bt, u_p, u_r);
       rsold = rsnew;
     }
     if (w == 0) *reinterpret_cast<float4*>(P.Y + (size_t)rid0 * kResK + lane * 4) = x;
@@ -358,7 +383,7 @@ __global__ void __launch_bounds__(kResThreads, kCtas) als_cg_resident_kernel(Res
     // ---- advance the pipeline ------------------------------------------------------------------------------
     n0 = n1; cq = val1; rid0 = rid1;
     n1 = n2; idx1 = idx2; val1 = val2; rid1 = rid2;
-    p2 = p3; n2 = p3e - p3; rid2 = rid3;
+    p2 = p3 - P.ptr_base; n2 = p3e - p3; rid2 = rid3;
     rid3 = rid4;
   }
   const double tot = block_sum_double((lane == 0) ? warp_loss : 0.0, S.red);

@@ -74,6 +74,18 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Loads pinned in program order (asm volatile + memory clobber): used for software-pipelined prefetches whose
+// results are consumed a whole row later -- a plain __ldg would be sunk by ptxas to just before its use.
+__device__ __forceinline__ int ld_pinned_i32(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_pinned_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // block-wide sum of one double per thread into thread 0 (fixed order: warp shuffle tree, then warps in order)
