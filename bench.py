@@ -246,7 +246,7 @@ def main():
     achieved = n_local * BYTES_PER_ROW(nnz, k) / (solve_ms / 1e3) / 1e9
     if solver == L.CHOLESKY:   # compute-bound path: 2nk^2 + 2nk + k^3/3 + 2k^2 flop per row
         fl = 2 * nnz * k * k + 2 * nnz * k + k ** 3 / 3 + 2 * k * k
-        roofline = {"bound": "tensor", "kernel": "als_chol_generic_kernel (fp32 FMA; no tensor cores yet)",
+        roofline = {"bound": "tensor", "kernel": "als_chol_tile_kernel (fp32 FFMA2 Gram + smem Cholesky; no tensor cores yet)",
                     "achieved": n_local * fl / (solve_ms / 1e3) / 1e12, "peak": None, "unit": "TFLOP/s", "frac": None,
                     "traffic": None, "kernel_ms": solve_ms}
     else:

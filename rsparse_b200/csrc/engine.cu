@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/b200als.h"
+#include "als_chol_tile.cuh"
 #include "als_generic.cuh"
 #include "als_resident.cuh"
 #include "eig.cuh"
@@ -389,18 +390,54 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
   };
 
   if (o.solver == B200ALS_CHOLESKY) {
-    const size_t smem = chol_generic_smem_bytes<T>(k);
-    if (smem > c.smem_optin)
-      return fail(B200ALS_EUNSUPPORTED, "cholesky: rank too large for the shared-memory factorisation (needs " +
-                                           std::to_string(smem) + " B)");
-    CU(cudaFuncSetAttribute(als_chol_generic_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (smem + 1024)));
-    const int grid = std::min(c.sm_count * per_sm, std::max(1, n_rows_here));
-    CU(cudaMemsetAsync(c.ticket.p, 0, sizeof(unsigned long long), c.stream));
-    als_chol_generic_kernel<T><<<grid, 256, smem, c.stream>>>(P);
-    LAUNCHED(); CU(cudaGetLastError());
-    sum_partials_kernel<<<1, 32, 0, c.stream>>>(P.loss_partials, grid, c.loss_acc.f64(), 1);
-    LAUNCHED(); CU(cudaGetLastError());
+    auto run_generic_chol = [&](const int32_t* list, int n_list) -> int {
+      P.row_list = list;
+      P.n_list = n_list;
+      const int n_work = list ? n_list : n_rows_here;
+      if (n_work == 0) return B200ALS_OK;
+      const size_t smem = chol_generic_smem_bytes<T>(k);
+      if (smem > c.smem_optin)
+        return fail(B200ALS_EUNSUPPORTED, "cholesky: rank too large for the shared-memory factorisation (needs " +
+                                             std::to_string(smem) + " B)");
+      CU(cudaFuncSetAttribute(als_chol_generic_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (smem + 1024)));
+      const int grid = std::min(c.sm_count * per_sm, std::max(1, n_work));
+      CU(cudaMemsetAsync(c.ticket.p, 0, sizeof(unsigned long long), c.stream));
+      als_chol_generic_kernel<T><<<grid, 256, smem, c.stream>>>(P);
+      LAUNCHED(); CU(cudaGetLastError());
+      sum_partials_kernel<<<1, 32, 0, c.stream>>>(P.loss_partials, grid, c.loss_acc.f64(), 1);
+      LAUNCHED(); CU(cudaGetLastError());
+      return B200ALS_OK;
+    };
+    bool tiled = false;
+    if constexpr (sizeof(T) == 4) tiled = (k == 64 || k == 128) && o.kernel != 1 && !sub_range;
+    if (!tiled) return run_generic_chol(nullptr, 0);
+    if constexpr (sizeof(T) == 4) {
+      // rows with 1..80 non-zeros: tile kernel; longer rows: generic kernel; empty rows: zero
+      TRY(classify_rows(c, A));
+      if (A.n_empty > 0) {
+        zero_empty_rows_kernel<T><<<(unsigned)(((long long)A.n_cols * k + 255) / 256), 256, 0, c.stream>>>(P.ptr, A.n_cols, k, Y);
+        LAUNCHED(); CU(cudaGetLastError());
+      }
+      if (A.n_short > 0) {
+        P.row_list = A.all_short ? nullptr : A.short_list.i32();
+        P.n_list = A.n_short;
+        const size_t smem = (k == 64) ? sizeof(CholTileSmem<64>) : sizeof(CholTileSmem<128>);
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (227 * 1024) / (smem + 1024)));
+        const int grid = std::min(c.sm_count * per_sm, A.n_short);
+        if (k == 64) {
+          CU(cudaFuncSetAttribute(als_chol_tile_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          als_chol_tile_kernel<64><<<grid, 256, smem, c.stream>>>(P);
+        } else {
+          CU(cudaFuncSetAttribute(als_chol_tile_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          als_chol_tile_kernel<128><<<grid, 256, smem, c.stream>>>(P);
+        }
+        LAUNCHED(); CU(cudaGetLastError());
+        sum_partials_kernel<<<1, 32, 0, c.stream>>>(P.loss_partials, grid, c.loss_acc.f64(), 1);
+        LAUNCHED(); CU(cudaGetLastError());
+      }
+      if (A.n_long > 0) TRY(run_generic_chol(A.long_list.i32(), A.n_long));
+    }
     return B200ALS_OK;
   }
 

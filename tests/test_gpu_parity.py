@@ -245,3 +245,26 @@ def test_pipelined_stateless_path(name, vals, cases, golden_half, monkeypatch):
         assert relF(Y, ref) < TOL_F32, (xtx, relF(Y, ref))
         assert abs(loss - float(golden_half[name + "/loss_f64"])) <= TOL_F32 * abs(loss)
         assert np.all(Y[np.diff(c["ptr"]) == 0] == 0)
+
+
+@pytest.mark.parametrize("name,kernel", [("synth_implicit_cg_k128", 0), ("synth_ragged_implicit_cg_k128", 0),
+                                         ("synth_explicit_cg_k128", 0), ("synth_ragged_explicit_cg_k64", 0),
+                                         ("synth_long_implicit_cg_k128", 0), ("synth_implicit_chol_k64", 1)])
+def test_tiled_cholesky_vs_oracle(name, kernel, cases):
+    """The rank-64/128 tile Cholesky kernel (rows <= 80 nnz; longer and empty rows through the generic kernel)
+    against the fp64 oracle, implicit and explicit, and against the generic kernel (kernel=1)."""
+    c = dict(cases[name])
+    X64, Y64 = c["X"].astype(np.float64), c["Y0"].astype(np.float64).copy()
+    if c["feedback"] == "implicit":
+        G = X64.T @ X64 + c["lam"] * np.eye(X64.shape[1])
+        lo = oracle.als_implicit(c["ptr"], c["idx"], c["val"], X64, Y64, G, c["lam"], wc.CHOL, 3, 2)
+    else:
+        lo = oracle.als_explicit(c["ptr"], c["idx"], c["val"], X64, Y64, c["cnt_X"].astype(np.float64), c["lam"], wc.CHOL,
+                                 3, c["dynamic_lambda"], 2)
+    s = _session_for(c, kernel, solver=wc.CHOL)
+    loss = s.half_iteration(L.USERS)
+    Y = s.get_factors(L.USERS)
+    s.close()
+    assert relF(Y, Y64) < TOL_F32, relF(Y, Y64)
+    assert abs(loss - lo) <= TOL_F32 * abs(lo)
+    assert np.all(Y[np.diff(c["ptr"]) == 0] == 0)
