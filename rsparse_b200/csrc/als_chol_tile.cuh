@@ -19,15 +19,15 @@ namespace b200als {
 constexpr int kCholMaxN = 80;
 
 template <int K>
-struct CholTileSmem {
+struct alignas(16) CholTileSmem {
   static constexpr int LDA = K + 1;     // odd: column reads of the factorisation are conflict-free
   float A[(K + 1) * LDA];               // lower triangle (+ rhs in row K)
-  float tile[kCholMaxN * K];
+  alignas(16) float tile[kCholMaxN * K];   // 16-byte cp.async destinations / float4 reads
   float cs[kCholMaxN], ws[kCholMaxN];
   int idx[kCholMaxN];
   float rs[K];                          // 1 / sqrt(d_j)
-  float zz[K];
-  double red[32];
+  alignas(16) float zz[K];
+  alignas(8) double red[32];
   int fail;
 };
 
