@@ -259,8 +259,9 @@ def test_tiled_cholesky_vs_oracle(name, kernel, cases):
         G = X64.T @ X64 + c["lam"] * np.eye(X64.shape[1])
         lo = oracle.als_implicit(c["ptr"], c["idx"], c["val"], X64, Y64, G, c["lam"], wc.CHOL, 3, 2)
     else:
-        lo = oracle.als_explicit(c["ptr"], c["idx"], c["val"], X64, Y64, c["cnt_X"].astype(np.float64), c["lam"], wc.CHOL,
-                                 3, c["dynamic_lambda"], 2)
+        # a session counts cnt_X itself (nnz per row of the fixed matrix, R/model_WRMF.R:305-315)
+        cnt = np.bincount(c["idx"], minlength=X64.shape[0]).astype(np.float64)
+        lo = oracle.als_explicit(c["ptr"], c["idx"], c["val"], X64, Y64, cnt, c["lam"], wc.CHOL, 3, c["dynamic_lambda"], 2)
     s = _session_for(c, kernel, solver=wc.CHOL)
     loss = s.half_iteration(L.USERS)
     Y = s.get_factors(L.USERS)
