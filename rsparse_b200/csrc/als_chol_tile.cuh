@@ -7,9 +7,12 @@
 //   2. Gram: every thread owns a (K/16) x (K/16) register block of the K x K system (interleaved 4-wide groups so
 //      both operand reads are conflict-free 128-bit loads), one rank-1 update per gathered row, packed FFMA2;
 //      the rhs rides along as an extra row;  XtX (or lambda_u I) is added when the block is written to smem;
-//   3. right-looking Cholesky on the unscaled matrix: A[a][b] -= A[a][j] A[b][j] / d_j for j < b <= a -- column j is
-//      only read, so ONE __syncthreads per column; the appended rhs row is forward-substituted for free;
-//   4. back substitution by one warp, loss by warp-per-gathered-row dots on the staged tile.
+//   3. right-looking Cholesky with the matrix STILL IN THOSE REGISTERS: at column j the owning threads publish the
+//      (unscaled) column into row j of a K x K shared array, one __syncthreads, then every thread applies
+//      A[a][b] -= A[a][j] A[b][j] / d_j to its whole register block (symmetric-full, rows/cols <= j masked to zero)
+//      with packed FFMA2 -- no address arithmetic, no shared-memory read-modify-write; the rhs is carried along
+//      (forward substitution for free);
+//   4. back substitution by one warp on the published columns, loss by warp-per-gathered-row dots on the tile.
 // Algorithmic work per row: 2nK^2 (Gram, computed symmetric-full = 2x) + K^3/3 flop; bytes as the CG path.
 #pragma once
 #include "als_generic.cuh"
@@ -20,12 +23,12 @@ constexpr int kCholMaxN = 80;
 
 template <int K>
 struct alignas(16) CholTileSmem {
-  static constexpr int LDA = K + 1;     // odd: column reads of the factorisation are conflict-free
-  float A[(K + 1) * LDA];               // lower triangle (+ rhs in row K)
+  alignas(16) float Lt[K * K];          // row j = unscaled column j of the factor (entries a > j), published at step j
   alignas(16) float tile[kCholMaxN * K];   // 16-byte cp.async destinations / float4 reads
   float cs[kCholMaxN], ws[kCholMaxN];
   int idx[kCholMaxN];
   float rs[K];                          // 1 / sqrt(d_j)
+  float rj[2];                          // rhs entry of the current column (double buffered)
   alignas(16) float zz[K];
   alignas(8) double red[32];
   int fail;
@@ -36,7 +39,6 @@ __global__ void __launch_bounds__(256) als_chol_tile_kernel(SolveParams<float> P
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using SM = CholTileSmem<K>;
   SM& S = *reinterpret_cast<SM*>(smem_raw);
-  constexpr int LDA = SM::LDA;
   constexpr int G = K / 64;            // 4-wide groups per thread and dimension (1 at K = 64, 2 at K = 128)
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
   const bool implicit = (P.feedback == 0);
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(256) als_chol_tile_kernel(SolveParams<float> P
         racc[i] = fmaf(cj, a[i], racc[i]);
       }
     }
-    // ---- block -> shared memory (+ XtX, or lambda_u on the diagonal) ---------------------------------------
+    // ---- + XtX (or lambda_u on the diagonal), still in registers ------------------------------------------------
     const float lam_use = implicit ? 0.0f : (float)(P.lambda * (P.dynamic_lambda ? (double)(float)n : 1.));
 #pragma unroll
     for (int i = 0; i < G * 4; i++) {
@@ -98,46 +100,89 @@ __global__ void __launch_bounds__(256) als_chol_tile_kernel(SolveParams<float> P
 #pragma unroll
       for (int jj = 0; jj < G * 2; jj++) {
         const int bc = (jj / 2) * 64 + tx * 4 + (jj % 2) * 2;
-        float v0 = acc[i][jj].x, v1 = acc[i][jj].y;
         if (implicit) {
           const float2 g = __ldg(reinterpret_cast<const float2*>(P.G + (size_t)ar * K + bc));
-          v0 += g.x; v1 += g.y;
+          acc[i][jj].x += g.x;
+          acc[i][jj].y += g.y;
         } else {
-          if (ar == bc) v0 += lam_use;
-          if (ar == bc + 1) v1 += lam_use;
+          if (ar == bc) acc[i][jj].x += lam_use;
+          if (ar == bc + 1) acc[i][jj].y += lam_use;
         }
-        S.A[ar * LDA + bc] = v0;
-        S.A[ar * LDA + bc + 1] = v1;
       }
-      if (tx == 0) S.A[K * LDA + ar] = racc[i];
     }
-    // ---- right-looking Cholesky, one barrier per column ---------------------------------------------------
-    for (int j = 0; j < K; j++) {
-      __syncthreads();
-      const float d = S.A[j * LDA + j];
-      if (!(d > 0.0f)) {
-        if (tid == 0) { S.fail = 1; atomicExch(P.status, 1); }
-        break;
-      }
-      const float dinv = 1.0f / d;
-      if (tid == 0) S.rs[j] = 1.0f / sqrtf(d);
-      for (int a = j + 1 + ty; a <= K; a += 16) {
-        const float aj = S.A[a * LDA + j] * dinv;
-        const int bmax = (a < K) ? a : (K - 1);
-        for (int b = j + 1 + tx; b <= bmax; b += 16) S.A[a * LDA + b] = fmaf(-aj, S.A[b * LDA + j], S.A[a * LDA + b]);
+    // ---- right-looking Cholesky on the register blocks, one barrier per column --------------------------------
+    bool failed = false;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      for (int J = 0; J < 16 && !failed; J++) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const int j = g * 64 + J * 4 + c;
+          if (tx == J) {   // owners of column j publish it (all their rows; readers mask rows <= j)
+#pragma unroll
+            for (int gi = 0; gi < G; gi++) {
+              float4 col;
+              col.x = (c % 2 == 0) ? acc[gi * 4 + 0][g * 2 + c / 2].x : acc[gi * 4 + 0][g * 2 + c / 2].y;
+              col.y = (c % 2 == 0) ? acc[gi * 4 + 1][g * 2 + c / 2].x : acc[gi * 4 + 1][g * 2 + c / 2].y;
+              col.z = (c % 2 == 0) ? acc[gi * 4 + 2][g * 2 + c / 2].x : acc[gi * 4 + 2][g * 2 + c / 2].y;
+              col.w = (c % 2 == 0) ? acc[gi * 4 + 3][g * 2 + c / 2].x : acc[gi * 4 + 3][g * 2 + c / 2].y;
+              *reinterpret_cast<float4*>(&S.Lt[j * K + gi * 64 + ty * 4]) = col;
+            }
+          }
+          if (tx == 0 && ty == J) S.rj[j & 1] = racc[g * 4 + c];
+          __syncthreads();
+          const float d = S.Lt[j * K + j];
+          if (!(d > 0.0f)) {   // same value in every thread
+            if (tid == 0) { S.fail = 1; atomicExch(P.status, 1); }
+            failed = true;
+            break;
+          }
+          const float dinv = 1.0f / d;
+          const float rjv = S.rj[j & 1];
+          if (tid == 0) {
+            const float r = 1.0f / sqrtf(d);
+            S.rs[j] = r;
+            S.zz[j] = rjv * r;   // z_j = (L^-1 rhs)_j
+          }
+          // my block needs updating only if it has a row > j and a column > j
+          const int max_row = (G - 1) * 64 + ty * 4 + 3, max_col = (G - 1) * 64 + tx * 4 + 3;
+          if (max_row > j && (max_col > j || tx == 0)) {   // tx == 0 threads also carry the rhs row
+            float ca[G * 4];
+            float2 cb[G * 2];
+#pragma unroll
+            for (int gi = 0; gi < G; gi++) {
+              const float4 av = *reinterpret_cast<const float4*>(&S.Lt[j * K + gi * 64 + ty * 4]);
+              const float4 bv = *reinterpret_cast<const float4*>(&S.Lt[j * K + gi * 64 + tx * 4]);
+              const int a0 = gi * 64 + ty * 4, b0 = gi * 64 + tx * 4;
+              ca[gi * 4 + 0] = (a0 + 0 > j) ? av.x : 0.f; ca[gi * 4 + 1] = (a0 + 1 > j) ? av.y : 0.f;
+              ca[gi * 4 + 2] = (a0 + 2 > j) ? av.z : 0.f; ca[gi * 4 + 3] = (a0 + 3 > j) ? av.w : 0.f;
+              cb[gi * 2 + 0] = make_float2((b0 + 0 > j) ? bv.x : 0.f, (b0 + 1 > j) ? bv.y : 0.f);
+              cb[gi * 2 + 1] = make_float2((b0 + 2 > j) ? bv.z : 0.f, (b0 + 3 > j) ? bv.w : 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < G * 4; i++) {
+              const float sneg = -ca[i] * dinv;
+              const float2 s2 = make_float2(sneg, sneg);
+#pragma unroll
+              for (int jj = 0; jj < G * 2; jj++) acc[i][jj] = __ffma2_rn(s2, cb[jj], acc[i][jj]);
+              racc[i] = fmaf(-rjv * dinv, ca[i], racc[i]);   // rhs row (meaningful in the tx == 0 threads)
+            }
+          }
+        }
       }
     }
     __syncthreads();
     if (S.fail) continue;   // Y row untouched; status reports B200ALS_ENOTSPD
-    // ---- back substitution (warp 0): L = A[:, j] * rs[j], z_j = A[K][j] * rs[j] --------------------------------
+    // ---- back substitution (warp 0):  y_i = (z_i - rs_i * sum_{l>i} Lt[i][l] y_l) * rs_i --------------------------
     if (warp == 0) {
-      for (int f = lane; f < K; f += 32) S.zz[f] = S.A[K * LDA + f] * S.rs[f];
-      __syncwarp();
       for (int i = K - 1; i >= 0; i--) {
-        const float yi = S.zz[i] * S.rs[i];
+        float part = 0.0f;
+        for (int l = i + 1 + lane; l < K; l += 32) part = fmaf(S.Lt[i * K + l], S.zz[l], part);
+        part = warp_sum(part);
+        const float r = S.rs[i];
+        const float yi = (S.zz[i] - r * part) * r;
         __syncwarp();
         if (lane == 0) S.zz[i] = yi;
-        for (int l = lane; l < i; l += 32) S.zz[l] = fmaf(-S.A[i * LDA + l] * S.rs[l], yi, S.zz[l]);
         __syncwarp();
       }
     }
