@@ -423,15 +423,18 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
         P.row_list = A.all_short ? nullptr : A.short_list.i32();
         P.n_list = A.n_short;
         const size_t smem = (k == 64) ? sizeof(CholTileSmem<64>) : sizeof(CholTileSmem<128>);
-        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (227 * 1024) / (smem + 1024)));
-        const int grid = std::min(c.sm_count * per_sm, A.n_short);
+        // persistent CTAs: exactly as many as are co-resident (registers AND shared memory), else a second wave
+        int per_sm = 1;
         if (k == 64) {
           CU(cudaFuncSetAttribute(als_chol_tile_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          als_chol_tile_kernel<64><<<grid, 256, smem, c.stream>>>(P);
+          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, als_chol_tile_kernel<64>, 256, smem));
         } else {
           CU(cudaFuncSetAttribute(als_chol_tile_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          als_chol_tile_kernel<128><<<grid, 256, smem, c.stream>>>(P);
+          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, als_chol_tile_kernel<128>, 256, smem));
         }
+        const int grid = std::min(c.sm_count * std::max(1, per_sm), A.n_short);
+        if (k == 64) als_chol_tile_kernel<64><<<grid, 256, smem, c.stream>>>(P);
+        else als_chol_tile_kernel<128><<<grid, 256, smem, c.stream>>>(P);
         LAUNCHED(); CU(cudaGetLastError());
         sum_partials_kernel<<<1, 32, 0, c.stream>>>(P.loss_partials, grid, c.loss_acc.f64(), 1);
         LAUNCHED(); CU(cudaGetLastError());
