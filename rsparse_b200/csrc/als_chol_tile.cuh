@@ -23,7 +23,8 @@ constexpr int kCholMaxN = 80;
 
 template <int K>
 struct alignas(16) CholTileSmem {
-  alignas(16) float Lt[K * K];          // row j = unscaled column j of the factor (entries a > j), published at step j
+  static constexpr int LDT = K + 4;     // rows stay 16-byte aligned, consecutive rows are 4 banks apart
+  alignas(16) float Lt[K * LDT];        // row j = unscaled column j of the factor (entries a > j), published at step j
   alignas(16) float tile[kCholMaxN * K];   // 16-byte cp.async destinations / float4 reads
   float cs[kCholMaxN], ws[kCholMaxN];
   int idx[kCholMaxN];
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(256) als_chol_tile_kernel(SolveParams<float> P
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using SM = CholTileSmem<K>;
   SM& S = *reinterpret_cast<SM*>(smem_raw);
+  constexpr int LDT = SM::LDT;
   constexpr int G = K / 64;            // 4-wide groups per thread and dimension (1 at K = 64, 2 at K = 128)
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
   const bool implicit = (P.feedback == 0);
@@ -126,12 +128,12 @@ __global__ void __launch_bounds__(256) als_chol_tile_kernel(SolveParams<float> P
               col.y = (c % 2 == 0) ? acc[gi * 4 + 1][g * 2 + c / 2].x : acc[gi * 4 + 1][g * 2 + c / 2].y;
               col.z = (c % 2 == 0) ? acc[gi * 4 + 2][g * 2 + c / 2].x : acc[gi * 4 + 2][g * 2 + c / 2].y;
               col.w = (c % 2 == 0) ? acc[gi * 4 + 3][g * 2 + c / 2].x : acc[gi * 4 + 3][g * 2 + c / 2].y;
-              *reinterpret_cast<float4*>(&S.Lt[j * K + gi * 64 + ty * 4]) = col;
+              *reinterpret_cast<float4*>(&S.Lt[j * LDT + gi * 64 + ty * 4]) = col;
             }
           }
           if (tx == 0 && ty == J) S.rj[j & 1] = racc[g * 4 + c];
           __syncthreads();
-          const float d = S.Lt[j * K + j];
+          const float d = S.Lt[j * LDT + j];
           if (!(d > 0.0f)) {   // same value in every thread
             if (tid == 0) { S.fail = 1; atomicExch(P.status, 1); }
             failed = true;
@@ -151,8 +153,8 @@ __global__ void __launch_bounds__(256) als_chol_tile_kernel(SolveParams<float> P
             float2 cb[G * 2];
 #pragma unroll
             for (int gi = 0; gi < G; gi++) {
-              const float4 av = *reinterpret_cast<const float4*>(&S.Lt[j * K + gi * 64 + ty * 4]);
-              const float4 bv = *reinterpret_cast<const float4*>(&S.Lt[j * K + gi * 64 + tx * 4]);
+              const float4 av = *reinterpret_cast<const float4*>(&S.Lt[j * LDT + gi * 64 + ty * 4]);
+              const float4 bv = *reinterpret_cast<const float4*>(&S.Lt[j * LDT + gi * 64 + tx * 4]);
               const int a0 = gi * 64 + ty * 4, b0 = gi * 64 + tx * 4;
               ca[gi * 4 + 0] = (a0 + 0 > j) ? av.x : 0.f; ca[gi * 4 + 1] = (a0 + 1 > j) ? av.y : 0.f;
               ca[gi * 4 + 2] = (a0 + 2 > j) ? av.z : 0.f; ca[gi * 4 + 3] = (a0 + 3 > j) ? av.w : 0.f;
@@ -173,20 +175,42 @@ __global__ void __launch_bounds__(256) als_chol_tile_kernel(SolveParams<float> P
     }
     __syncthreads();
     if (S.fail) continue;   // Y row untouched; status reports B200ALS_ENOTSPD
-    // ---- back substitution (warp 0):  y_i = (z_i - rs_i * sum_{l>i} Lt[i][l] y_l) * rs_i --------------------------
-    if (warp == 0) {
-      for (int i = K - 1; i >= 0; i--) {
-        float part = 0.0f;
-        for (int l = i + 1 + lane; l < K; l += 32) part = fmaf(S.Lt[i * K + l], S.zz[l], part);
-        part = warp_sum(part);
-        const float r = S.rs[i];
-        const float yi = (S.zz[i] - r * part) * r;
-        __syncwarp();
-        if (lane == 0) S.zz[i] = yi;
-        __syncwarp();
+    // ---- blocked back substitution  L' y = z,  L[l][i] = Lt[i][l] * rs_i  (l > i) --------------------------------
+    // 32-row blocks from the bottom: (1) all 8 warps subtract the already solved part, 4 rows per warp (row dots +
+    // shuffle reductions, independent chains); (2) warp 0 solves the 32 x 32 triangle with one broadcast per step.
+    for (int b0 = K - 32; b0 >= 0; b0 -= 32) {
+      if (b0 + 32 < K) {
+        float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r4 = 0; r4 < 4; r4++) {
+          const int i = b0 + warp * 4 + r4;
+          for (int l = b0 + 32 + lane; l < K; l += 32) part[r4] = fmaf(S.Lt[i * LDT + l], S.zz[l], part[r4]);
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+#pragma unroll
+          for (int r4 = 0; r4 < 4; r4++) part[r4] += __shfl_xor_sync(kFull, part[r4], m);
+        }
+        if (lane < 4) {
+          const int i = b0 + warp * 4 + lane;
+          const float pv = (lane == 0) ? part[0] : (lane == 1) ? part[1] : (lane == 2) ? part[2] : part[3];
+          S.zz[i] -= S.rs[i] * pv;
+        }
+        __syncthreads();
       }
+      if (warp == 0) {
+        const int i = b0 + lane;
+        const float ri = S.rs[i];
+        float zi = S.zz[i];
+#pragma unroll 8
+        for (int sidx = 31; sidx >= 0; sidx--) {
+          const float ys = __shfl_sync(kFull, zi * ri, sidx);            // y_s, final once step s is reached
+          if (lane < sidx) zi = fmaf(-S.Lt[i * LDT + b0 + sidx] * ri, ys, zi);
+        }
+        S.zz[i] = zi * ri;
+      }
+      __syncthreads();
     }
-    __syncthreads();
     float* y = P.Y + (size_t)row * K;
     if (tid < K / 4) *reinterpret_cast<float4*>(y + tid * 4) = *reinterpret_cast<const float4*>(&S.zz[tid * 4]);
     // ---- loss (wrmf_implicit.hpp:259-261 / wrmf_explicit.hpp:131-132) on the staged tile --------------------
