@@ -139,8 +139,8 @@ __global__ void set_identity_kernel(double* __restrict__ B, int k) {
 constexpr int kRotK = 128;
 constexpr int kRotRows = 64;
 struct RotSmem {
-  float R[kRotK][kRotK];      // 64 KB
-  float Xs[kRotRows][kRotK + 4];  // padded: conflict-free column-broadcast reads
+  float R[kRotK][kRotK];           // 64 KB
+  float Xt[kRotK][kRotRows + 4];   // the row block TRANSPOSED: Xt[f][r]; one 128-bit read = 4 rows of feature f
 };
 __global__ void __launch_bounds__(256) rotate_rows_kernel(const float* __restrict__ X, float* __restrict__ Z,
                                                           const float* __restrict__ R, long long n) {
@@ -155,35 +155,40 @@ __global__ void __launch_bounds__(256) rotate_rows_kernel(const float* __restric
     const long long r0 = blk * kRotRows;
     __syncthreads();
     for (int t = tid; t < kRotRows * (kRotK / 4); t += 256) {
-      const int rr = t / (kRotK / 4), c4 = t % (kRotK / 4);
+      const int c4 = t / kRotRows, rr = t % kRotRows;   // consecutive threads -> consecutive rows: conflict-free stores
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r0 + rr < n) v = __ldg(reinterpret_cast<const float4*>(X + (size_t)(r0 + rr) * kRotK) + c4);
-      *reinterpret_cast<float4*>(&S.Xs[rr][c4 * 4]) = v;
+      S.Xt[c4 * 4 + 0][rr] = v.x;
+      S.Xt[c4 * 4 + 1][rr] = v.y;
+      S.Xt[c4 * 4 + 2][rr] = v.z;
+      S.Xt[c4 * 4 + 3][rr] = v.w;
     }
     __syncthreads();
-    float acc[4][8];
+    float2 acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
-      for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+      for (int j = 0; j < 4; j++) acc[i][j] = make_float2(0.f, 0.f);
 #pragma unroll 4
     for (int f = 0; f < kRotK; f++) {
       const float4 b0 = *reinterpret_cast<const float4*>(&S.R[f][tx * 4]);
       const float4 b1 = *reinterpret_cast<const float4*>(&S.R[f][64 + tx * 4]);
-      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const float4 a4 = *reinterpret_cast<const float4*>(&S.Xt[f][ty * 4]);
+      const float2 bv[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        const float a = S.Xs[ty * 4 + i][f];
+        const float2 a2 = make_float2(av[i], av[i]);
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc[i][j] = fmaf(a, bv[j], acc[i][j]);
+        for (int j = 0; j < 4; j++) acc[i][j] = __ffma2_rn(a2, bv[j], acc[i][j]);
       }
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const long long r = r0 + ty * 4 + i;
       if (r < n) {
-        *reinterpret_cast<float4*>(Z + (size_t)r * kRotK + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-        *reinterpret_cast<float4*>(Z + (size_t)r * kRotK + 64 + tx * 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+        *reinterpret_cast<float4*>(Z + (size_t)r * kRotK + tx * 4) = make_float4(acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y);
+        *reinterpret_cast<float4*>(Z + (size_t)r * kRotK + 64 + tx * 4) = make_float4(acc[i][2].x, acc[i][2].y, acc[i][3].x, acc[i][3].y);
       }
     }
   }

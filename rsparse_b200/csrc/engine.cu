@@ -1174,7 +1174,7 @@ static int gather_ranges(b200als_session* s, int which) {
   DevBuf d;
   CU(d.ensure(sizeof(int32_t) * 3 * g_comm.world));
   int32_t mine[3] = {s->shard_begin[which], s->shard_end[which],
-                     (s->csc[which].all_short && s->csc[which].n_cols >= 4 * 4096) ? 1 : 0};
+                     (s->csc[which].all_short && s->csc[which].n_cols >= 8 * 4096) ? 1 : 0};
   CU(cudaMemcpyAsync(d.i32() + 3 * g_comm.rank, mine, sizeof(mine), cudaMemcpyHostToDevice, c.stream));
   NC(g_nccl.AllGather(d.i32() + 3 * g_comm.rank, d.p, 3, ncclInt32, g_comm.comm, c.stream));
   CU(cudaMemcpyAsync(ranges.data(), d.p, sizeof(int32_t) * 3 * g_comm.world, cudaMemcpyDeviceToHost, c.stream));
@@ -1265,7 +1265,10 @@ static int session_half(b200als_session* s, int which, int solver, float* Yout, 
   CU(cudaEventRecord(s->ev[2], c.stream));
   if (g_comm.world > 1 && !Yout) {
     // the block is solved in chunks; chunk c travels to the other ranks (priority stream) while chunk c+1 is solved
-    int n_ch = 4;   // every rank must take the same decision: chunk only if every block qualifies
+    // every rank must take the same decision: chunk only if every block qualifies.  More chunks = shorter
+    // exposed tail of the exchange (only the last chunk's broadcast is not hidden behind a solve)
+    int n_ch = 8;
+    if (const char* ev = getenv("B200ALS_EXCHANGE_CHUNKS")) n_ch = std::max(1, std::min(8, atoi(ev)));
     for (int r = 0; r < g_comm.world; r++)
       if (!s->ranges[which][3 * r + 2]) n_ch = 1;
     for (int ch = 0; ch < n_ch; ch++) {
