@@ -2,7 +2,9 @@
 // rows with 1..80 non-zeros); rows outside that go to als_chol_generic_kernel.
 // Reference: lhs = XtX + X_nnz diag(c-1) X_nnz', rhs = X_nnz c, solve(lhs, rhs)   (wrmf_implicit.hpp:207-236)
 //            lhs = X_nnz X_nnz' + lambda_u I, rhs = X_nnz r, solve(lhs, rhs)      (wrmf_explicit.hpp:103-108)
-// One CTA of 256 threads per row (static interleave over a row list), several CTAs per SM:
+// One CTA of 160 threads per row (static interleave over a row list), several CTAs per SM.  Only the 136 lower-
+// triangular (K/16) x (K/16) blocks of the symmetric system are kept (one per thread, triangular index decode), so
+// no issue slot is spent on mirror blocks:
 //   1. the gathered tile X_nnz (n x K) is staged once into shared memory with 16-byte cp.async;
 //   2. Gram: every thread owns a (K/16) x (K/16) register block of the K x K system (interleaved 4-wide groups so
 //      both operand reads are conflict-free 128-bit loads), one rank-1 update per gathered row, packed FFMA2;
@@ -20,6 +22,8 @@
 namespace b200als {
 
 constexpr int kCholMaxN = 80;
+constexpr int kCholThreads = 160;   // 136 lower-triangular 16 x 16 block positions + 24 idle lanes
+constexpr int kCholWarps = kCholThreads / 32;
 
 template <int K>
 struct alignas(16) CholTileSmem {
@@ -36,13 +40,19 @@ struct alignas(16) CholTileSmem {
 };
 
 template <int K>
-__global__ void __launch_bounds__(256) als_chol_tile_kernel(SolveParams<float> P) {
+__global__ void __launch_bounds__(kCholThreads, (K == 64) ? 5 : 2) als_chol_tile_kernel(SolveParams<float> P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using SM = CholTileSmem<K>;
   SM& S = *reinterpret_cast<SM*>(smem_raw);
   constexpr int LDT = SM::LDT;
   constexpr int G = K / 64;            // 4-wide groups per thread and dimension (1 at K = 64, 2 at K = 128)
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // thread -> block (ty, tx) of the lower triangle, row-major: t = ty (ty + 1) / 2 + tx, tx <= ty < 16
+  int ty = (int)((sqrtf(8.0f * (float)tid + 1.0f) - 1.0f) * 0.5f);
+  while ((ty + 1) * (ty + 2) / 2 <= tid) ty++;
+  while (ty * (ty + 1) / 2 > tid) ty--;
+  const int tx = tid - ty * (ty + 1) / 2;
+  const bool has_block = (tid < 136);
   const bool implicit = (P.feedback == 0);
   const int total = P.n_list_dev ? __ldg(P.n_list_dev) : P.n_list;
   double cta_loss = 0.0;
@@ -58,7 +68,7 @@ __global__ void __launch_bounds__(256) als_chol_tile_kernel(SolveParams<float> P
     }
     if (tid == 0) S.fail = 0;
     __syncthreads();
-    for (int e = tid; e < n * (K / 4); e += 256) {
+    for (int e = tid; e < n * (K / 4); e += kCholThreads) {
       const int j = e / (K / 4), c4 = e - j * (K / 4);
       cp_async_16(&S.tile[j * K + c4 * 4], P.X + (size_t)S.idx[j] * K + c4 * 4);
     }
@@ -73,7 +83,7 @@ __global__ void __launch_bounds__(256) als_chol_tile_kernel(SolveParams<float> P
 #pragma unroll
       for (int j = 0; j < G * 2; j++) acc[i][j] = make_float2(0.f, 0.f);
     }
-    for (int j = 0; j < n; j++) {
+    for (int j = 0; j < (has_block ? n : 0); j++) {
       const float wj = S.ws[j], cj = S.cs[j];
       float a[G * 4];
       float2 b[G * 2];
@@ -98,10 +108,11 @@ __global__ void __launch_bounds__(256) als_chol_tile_kernel(SolveParams<float> P
     const float lam_use = implicit ? 0.0f : (float)(P.lambda * (P.dynamic_lambda ? (double)(float)n : 1.));
 #pragma unroll
     for (int i = 0; i < G * 4; i++) {
-      const int ar = (i / 4) * 64 + ty * 4 + (i % 4);
+      const int ar = (i / 4) * 64 + (has_block ? ty : 0) * 4 + (i % 4);
 #pragma unroll
       for (int jj = 0; jj < G * 2; jj++) {
-        const int bc = (jj / 2) * 64 + tx * 4 + (jj % 2) * 2;
+        const int bc = (jj / 2) * 64 + (has_block ? tx : 0) * 4 + (jj % 2) * 2;
+        if (!has_block) continue;
         if (implicit) {
           const float2 g = __ldg(reinterpret_cast<const float2*>(P.G + (size_t)ar * K + bc));
           acc[i][jj].x += g.x;
@@ -120,7 +131,7 @@ __global__ void __launch_bounds__(256) als_chol_tile_kernel(SolveParams<float> P
 #pragma unroll
         for (int c = 0; c < 4; c++) {
           const int j = g * 64 + J * 4 + c;
-          if (tx == J) {   // owners of column j publish it (all their rows; readers mask rows <= j)
+          if (has_block && tx == J) {   // owners of column j publish it (all their rows; readers mask rows <= j)
 #pragma unroll
             for (int gi = 0; gi < G; gi++) {
               float4 col;
@@ -131,7 +142,16 @@ __global__ void __launch_bounds__(256) als_chol_tile_kernel(SolveParams<float> P
               *reinterpret_cast<float4*>(&S.Lt[j * LDT + gi * 64 + ty * 4]) = col;
             }
           }
-          if (tx == 0 && ty == J) S.rj[j & 1] = racc[g * 4 + c];
+          if (G > 1 && has_block && ty == J && tx < J) {
+            // interleaved groups (K = 128): entries (a, j) with a in an EARLIER 16-block than j but a later group are
+            // kept transposed, as row j of block (J, tx) -- publish those too (disjoint from the columns above)
+#pragma unroll
+            for (int gj = 0; gj < G; gj++) {
+              const float2 r0 = acc[g * 4 + c][gj * 2 + 0], r1 = acc[g * 4 + c][gj * 2 + 1];
+              *reinterpret_cast<float4*>(&S.Lt[j * LDT + gj * 64 + tx * 4]) = make_float4(r0.x, r0.y, r1.x, r1.y);
+            }
+          }
+          if (has_block && tx == 0 && ty == J) S.rj[j & 1] = racc[g * 4 + c];
           __syncthreads();
           const float d = S.Lt[j * LDT + j];
           if (!(d > 0.0f)) {   // same value in every thread
@@ -148,7 +168,7 @@ __global__ void __launch_bounds__(256) als_chol_tile_kernel(SolveParams<float> P
           }
           // my block needs updating only if it has a row > j and a column > j
           const int max_row = (G - 1) * 64 + ty * 4 + 3, max_col = (G - 1) * 64 + tx * 4 + 3;
-          if (max_row > j && (max_col > j || tx == 0)) {   // tx == 0 threads also carry the rhs row
+          if (has_block && max_row > j && (max_col > j || tx == 0)) {   // tx == 0 threads also carry the rhs row
             float ca[G * 4];
             float2 cb[G * 2];
 #pragma unroll
@@ -176,25 +196,14 @@ __global__ void __launch_bounds__(256) als_chol_tile_kernel(SolveParams<float> P
     __syncthreads();
     if (S.fail) continue;   // Y row untouched; status reports B200ALS_ENOTSPD
     // ---- blocked back substitution  L' y = z,  L[l][i] = Lt[i][l] * rs_i  (l > i) --------------------------------
-    // 32-row blocks from the bottom: (1) all 8 warps subtract the already solved part, 4 rows per warp (row dots +
-    // shuffle reductions, independent chains); (2) warp 0 solves the 32 x 32 triangle with one broadcast per step.
+    // 32-row blocks from the bottom: (1) all warps subtract the already solved part (row dots + shuffle reductions); (2) warp 0 solves the 32 x 32 triangle with one broadcast per step.
     for (int b0 = K - 32; b0 >= 0; b0 -= 32) {
       if (b0 + 32 < K) {
-        float part[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int r4 = 0; r4 < 4; r4++) {
-          const int i = b0 + warp * 4 + r4;
-          for (int l = b0 + 32 + lane; l < K; l += 32) part[r4] = fmaf(S.Lt[i * LDT + l], S.zz[l], part[r4]);
-        }
-#pragma unroll
-        for (int m = 16; m > 0; m >>= 1) {
-#pragma unroll
-          for (int r4 = 0; r4 < 4; r4++) part[r4] += __shfl_xor_sync(kFull, part[r4], m);
-        }
-        if (lane < 4) {
-          const int i = b0 + warp * 4 + lane;
-          const float pv = (lane == 0) ? part[0] : (lane == 1) ? part[1] : (lane == 2) ? part[2] : part[3];
-          S.zz[i] -= S.rs[i] * pv;
+        for (int i = b0 + warp; i < b0 + 32; i += kCholWarps) {
+          float part = 0.f;
+          for (int l = b0 + 32 + lane; l < K; l += 32) part = fmaf(S.Lt[i * LDT + l], S.zz[l], part);
+          part = warp_sum(part);
+          if (lane == 0) S.zz[i] -= S.rs[i] * part;
         }
         __syncthreads();
       }
@@ -215,7 +224,7 @@ __global__ void __launch_bounds__(256) als_chol_tile_kernel(SolveParams<float> P
     if (tid < K / 4) *reinterpret_cast<float4*>(y + tid * 4) = *reinterpret_cast<const float4*>(&S.zz[tid * 4]);
     // ---- loss (wrmf_implicit.hpp:259-261 / wrmf_explicit.hpp:131-132) on the staged tile --------------------
     float l = 0.0f;
-    for (int j = warp; j < n; j += 8) {
+    for (int j = warp; j < n; j += kCholWarps) {
       float dsum = 0.0f;
       for (int f = lane; f < K; f += 32) dsum = fmaf(S.tile[j * K + f], S.zz[f], dsum);
       dsum = warp_sum(dsum);

@@ -427,14 +427,14 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
         int per_sm = 1;
         if (k == 64) {
           CU(cudaFuncSetAttribute(als_chol_tile_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, als_chol_tile_kernel<64>, 256, smem));
+          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, als_chol_tile_kernel<64>, kCholThreads, smem));
         } else {
           CU(cudaFuncSetAttribute(als_chol_tile_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, als_chol_tile_kernel<128>, 256, smem));
+          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, als_chol_tile_kernel<128>, kCholThreads, smem));
         }
         const int grid = std::min(c.sm_count * std::max(1, per_sm), A.n_short);
-        if (k == 64) als_chol_tile_kernel<64><<<grid, 256, smem, c.stream>>>(P);
-        else als_chol_tile_kernel<128><<<grid, 256, smem, c.stream>>>(P);
+        if (k == 64) als_chol_tile_kernel<64><<<grid, kCholThreads, smem, c.stream>>>(P);
+        else als_chol_tile_kernel<128><<<grid, kCholThreads, smem, c.stream>>>(P);
         LAUNCHED(); CU(cudaGetLastError());
         sum_partials_kernel<<<1, 32, 0, c.stream>>>(P.loss_partials, grid, c.loss_acc.f64(), 1);
         LAUNCHED(); CU(cudaGetLastError());
