@@ -145,6 +145,13 @@ int b200als_create(b200als_session** out, const b200als_csc* c_ui, const b200als
                    int32_t n_user, int32_t n_item, int rank, const b200als_options* opts);
 int b200als_destroy(b200als_session* s);
 
+/* Format ingest on the device (the host-side MatrixExtra::as.csr.matrix / t_shallow of
+ * R/model_WRMF.R:184-189): a session created with ONE orientation builds the other one in HBM with a stable
+ * radix sort, ascending indices inside every column.  Single GPU only.
+ * b200als_get_orientation copies an orientation back (ptr[n_cols+1], idx[nnz], val[nnz]; any may be NULL). */
+int b200als_build_missing_orientation(b200als_session* s);
+int b200als_get_orientation(b200als_session* s, int which, int32_t* ptr, int32_t* idx, float* val, int64_t* nnz_out);
+
 /* Copy a full factor matrix (rank x n, host memory) to / from the session. */
 int b200als_set_factors(b200als_session* s, int which, const float* host);
 int b200als_get_factors(b200als_session* s, int which, float* host);

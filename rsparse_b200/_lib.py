@@ -61,6 +61,8 @@ _PROTOS = {
     "b200als_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(Csc), C.POINTER(Csc), C.c_int32, C.c_int32, C.c_int,
                                  C.POINTER(Options)]),
     "b200als_destroy": (C.c_int, [C.c_void_p]),
+    "b200als_build_missing_orientation": (C.c_int, [C.c_void_p]),
+    "b200als_get_orientation": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
     "b200als_set_factors": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "b200als_get_factors": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "b200als_init_factors": (C.c_int, [C.c_void_p, C.c_uint64]),

@@ -5,6 +5,7 @@
 //   session / fit     R/model_WRMF.R:173-360 (outer loop :318-338, final transform_ :412-452)
 // No CPU fallback anywhere: every compute entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include <cub/cub.cuh>
 #include <dlfcn.h>
 #include <nccl.h>  // types and prototypes only: the library is resolved lazily with dlopen (see NcclApi)
 
@@ -1062,6 +1063,109 @@ extern "C" int b200als_create(b200als_session** out, const b200als_csc* c_ui, co
     return rc;
   }
   *out = s;
+  return B200ALS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Format ingest on the device: build the other orientation of the sparse matrix, i.e. what
+// `MatrixExtra::as.csr.matrix` / `t_shallow` do on the host in R/model_WRMF.R:184-189.  A stable LSD radix sort
+// (CUB) of the entries by their row id keeps, inside every new column, the source order = ascending source
+// column, so the result satisfies the dgCMatrix invariant and is bit-reproducible.
+// ------------------------------------------------------------------------------------------------------
+__global__ void expand_columns_kernel(const int32_t* __restrict__ ptr, int n_cols, int32_t* __restrict__ col_of) {
+  const int cidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cidx >= n_cols) return;
+  for (int e = ptr[cidx]; e < ptr[cidx + 1]; e++) col_of[e] = cidx;
+}
+__global__ void iota_kernel(int32_t* __restrict__ a, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = (int32_t)i;
+}
+__global__ void gather_transposed_kernel(const int32_t* __restrict__ perm, const int32_t* __restrict__ col_of,
+                                         const float* __restrict__ val, long long nnz, int32_t* __restrict__ idx_out,
+                                         float* __restrict__ val_out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nnz) return;
+  const int32_t e = perm[t];
+  idx_out[t] = col_of[e];
+  val_out[t] = val[e];
+}
+// ptr_out[r] = first position in the sorted key array with key >= r  (r = 0 .. n_rows)
+__global__ void row_starts_kernel(const int32_t* __restrict__ sorted_keys, long long nnz, int n_rows, int32_t* __restrict__ ptr_out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n_rows) return;
+  long long lo = 0, hi = nnz;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (sorted_keys[mid] < r) lo = mid + 1; else hi = mid;
+  }
+  ptr_out[r] = (int32_t)lo;
+}
+static int transpose_on_device(Ctx& c, const CscDev<float>& src, CscDev<float>& dst) {
+  dst.n_rows = src.n_cols;
+  dst.n_cols = src.n_rows;
+  dst.nnz = src.nnz;
+  dst.n_short = -1;
+  const long long nnz = src.nnz;
+  CU(dst.ptr.ensure(sizeof(int32_t) * ((size_t)dst.n_cols + 1)));
+  CU(dst.idx.ensure(sizeof(int32_t) * (size_t)nnz));
+  CU(dst.val.ensure(sizeof(float) * (size_t)nnz));
+  if (nnz == 0) {
+    CU(cudaMemsetAsync(dst.ptr.p, 0, sizeof(int32_t) * ((size_t)dst.n_cols + 1), c.stream));
+    return B200ALS_OK;
+  }
+  DevBuf col_of, iota, perm, keys_out, temp;
+  CU(col_of.ensure(sizeof(int32_t) * (size_t)nnz));
+  CU(iota.ensure(sizeof(int32_t) * (size_t)nnz));
+  CU(perm.ensure(sizeof(int32_t) * (size_t)nnz));
+  CU(keys_out.ensure(sizeof(int32_t) * (size_t)nnz));
+  expand_columns_kernel<<<(src.n_cols + 255) / 256, 256, 0, c.stream>>>(src.ptr.i32(), src.n_cols, col_of.i32());
+  LAUNCHED(); CU(cudaGetLastError());
+  iota_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, c.stream>>>(iota.i32(), nnz);
+  LAUNCHED(); CU(cudaGetLastError());
+  int bits = 1;
+  while (bits < 31 && (1ll << bits) < (long long)std::max(1, src.n_rows)) bits++;
+  size_t temp_bytes = 0;
+  CU(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, src.idx.i32(), keys_out.i32(), iota.i32(), perm.i32(), (int)nnz, 0,
+                                     bits, c.stream));
+  CU(temp.ensure(temp_bytes));
+  CU(cub::DeviceRadixSort::SortPairs(temp.p, temp_bytes, src.idx.i32(), keys_out.i32(), iota.i32(), perm.i32(), (int)nnz, 0,
+                                     bits, c.stream));
+  LAUNCHED();
+  gather_transposed_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, c.stream>>>(perm.i32(), col_of.i32(), src.val.f32(), nnz,
+                                                                              dst.idx.i32(), dst.val.f32());
+  LAUNCHED(); CU(cudaGetLastError());
+  row_starts_kernel<<<(dst.n_cols + 1 + 255) / 256, 256, 0, c.stream>>>(keys_out.i32(), nnz, dst.n_cols, dst.ptr.i32());
+  LAUNCHED(); CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c.stream));
+  return B200ALS_OK;
+}
+
+extern "C" int b200als_build_missing_orientation(b200als_session* s) {
+  Ctx& c = ctx();
+  if (!s) return fail(B200ALS_EINVAL, "null session");
+  if (s->has[0] && s->has[1]) return B200ALS_OK;
+  if (!s->has[0] && !s->has[1]) return fail(B200ALS_EINVAL, "the session holds no sparse matrix");
+  if (g_comm.world > 1) return fail(B200ALS_EUNSUPPORTED, "device-side transpose of a sharded matrix is not implemented");
+  const int have = s->has[0] ? 0 : 1, need = 1 - have;
+  TRY(transpose_on_device(c, s->csc[have], s->csc[need]));
+  s->has[need] = true;
+  s->shard_begin[need] = 0;
+  s->shard_end[need] = s->csc[need].n_cols;
+  s->nnz_global[need] = s->csc[need].nnz;
+  s->ranges[need].clear();
+  return session_counts(s);
+}
+// copy one orientation back to the host (tests / export): ptr[n_cols+1], idx[nnz], val[nnz]
+extern "C" int b200als_get_orientation(b200als_session* s, int which, int32_t* ptr, int32_t* idx, float* val, int64_t* nnz_out) {
+  Ctx& c = ctx();
+  if (!s || which < 0 || which > 1 || !s->has[which]) return fail(B200ALS_EINVAL, "orientation not present");
+  const CscDev<float>& A = s->csc[which];
+  if (nnz_out) *nnz_out = A.nnz;
+  if (ptr) CU(cudaMemcpyAsync(ptr, A.ptr.p, sizeof(int32_t) * ((size_t)A.n_cols + 1), cudaMemcpyDeviceToHost, c.stream));
+  if (idx && A.nnz) CU(cudaMemcpyAsync(idx, A.idx.p, sizeof(int32_t) * (size_t)A.nnz, cudaMemcpyDeviceToHost, c.stream));
+  if (val && A.nnz) CU(cudaMemcpyAsync(val, A.val.p, sizeof(float) * (size_t)A.nnz, cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaStreamSynchronize(c.stream));
   return B200ALS_OK;
 }
 

@@ -77,6 +77,19 @@ class Session:
 
     __del__ = close
 
+    def build_missing_orientation(self):
+        L.check(L.lib().b200als_build_missing_orientation(self._h))
+
+    def get_orientation(self, which):
+        nnz = C.c_int64(0)
+        L.check(L.lib().b200als_get_orientation(self._h, which, None, None, None, C.byref(nnz)))
+        n_cols = self.n_item if which == L.ITEMS else self.n_user
+        ptr = np.empty(n_cols + 1, np.int32)
+        idx = np.empty(nnz.value, np.int32)
+        val = np.empty(nnz.value, np.float32)
+        L.check(L.lib().b200als_get_orientation(self._h, which, L.vp(ptr), L.vp(idx), L.vp(val), None))
+        return ptr, idx, val
+
     def set_factors(self, which, a):
         a = np.ascontiguousarray(a, dtype=np.float32)
         n = self.n_item if which == L.ITEMS else self.n_user

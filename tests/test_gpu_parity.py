@@ -269,3 +269,42 @@ def test_tiled_cholesky_vs_oracle(name, kernel, cases):
     assert relF(Y, Y64) < TOL_F32, relF(Y, Y64)
     assert abs(loss - lo) <= TOL_F32 * abs(lo)
     assert np.all(Y[np.diff(c["ptr"]) == 0] == 0)
+
+
+def test_device_side_transpose_matches_scipy_and_fit_is_bit_identical():
+    """a session given ONE orientation builds the other on the device (stable radix sort); the
+    result equals scipy's transpose index for index, and a fit on it is bit-identical to a fit on host-built
+    orientations."""
+    M = wc.load_movielens()
+    users, items = wc.targets_csc(M), wc.targets_csc(M.T)
+    k = 16
+    U0, I0 = wc.det_factors(M.shape[0], k, 31), wc.det_factors(M.shape[1], k, 32)
+    out = []
+    for mode in ("both", "users_only", "items_only"):
+        s = Session(items if mode != "users_only" else None, users if mode != "items_only" else None, M.shape[0],
+                    M.shape[1], k, "implicit", L.CONJUGATE_GRADIENT, 3, True, 0.1)
+        s.build_missing_orientation()
+        for which, ref in ((L.ITEMS, items), (L.USERS, users)):
+            ptr, idx, val = s.get_orientation(which)
+            assert np.array_equal(ptr, ref[0]) and np.array_equal(idx, ref[1])
+            assert np.array_equal(val, ref[2].astype(np.float32))
+        s.set_factors(L.USERS, U0)
+        s.set_factors(L.ITEMS, I0)
+        trace, _ = s.fit(2, -1.0)
+        out.append((trace, s.get_factors(L.ITEMS), s.get_factors(L.USERS)))
+        s.close()
+    for o in out[1:]:
+        assert np.array_equal(o[0], out[0][0]) and np.array_equal(o[1], out[0][1]) and np.array_equal(o[2], out[0][2])
+
+
+def test_device_side_transpose_larger_ragged():
+    ptr, idx, val = wc.det_csr(5000, 3000, 30, 77, ragged=True, empty_every=11)
+    import scipy.sparse as sp
+    A = sp.csr_matrix((val, idx, ptr), shape=(5000, 3000))   # users x items (rows = users)
+    s = Session(None, (ptr, idx, val), 5000, 3000, 8, "implicit", L.CONJUGATE_GRADIENT, 3, True, 0.1)
+    s.build_missing_orientation()
+    p2, i2, v2 = s.get_orientation(L.ITEMS)
+    s.close()
+    T = sp.csr_matrix(A.T)
+    T.sort_indices()
+    assert np.array_equal(p2, T.indptr) and np.array_equal(i2, T.indices) and np.array_equal(v2, T.data.astype(np.float32))
