@@ -23,6 +23,7 @@
 #include "als_resident.cuh"
 #include "eig.cuh"
 #include "gram.cuh"
+#include "gram_tc.cuh"
 
 using namespace b200als;
 
@@ -268,8 +269,28 @@ static int upload_csc(const b200als_csc* A, CscDev<T>& D, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------------
 // Gram
 // ------------------------------------------------------------------------------------------------------
+// B200ALS_GRAM=ffma forces the fp32 FMA kernel; default at rank 128 / fp32 is the tcgen05 3xTF32 kernel
+static bool gram_use_tensor_cores() {
+  const char* e = getenv("B200ALS_GRAM");
+  return !(e && (e[0] == 'f' || e[0] == 'F'));
+}
 template <typename T>
 static int run_gram(Ctx& c, const T* X, int k, long long n, double lambda, T* G, double* G64) {
+  if constexpr (sizeof(T) == 4) {
+    if (k == kTcK && n > 0 && gram_use_tensor_cores()) {
+      long long rows_per = std::max<long long>(1024, (n + 887) / 888);
+      rows_per = ((rows_per + 255) / 256) * 256;   // whole drain windows
+      const long long n_cta = (n + rows_per - 1) / rows_per;
+      CU(c.gram_partials.ensure(sizeof(double) * (size_t)n_cta * kTcK * kTcK));
+      const size_t smem = sizeof(GramTcSmem);
+      CU(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      gram_tc_kernel<<<(unsigned)n_cta, 128, smem, c.stream>>>((const float*)X, n, rows_per, c.gram_partials.f64());
+      LAUNCHED(); CU(cudaGetLastError());
+      gram_reduce_kernel<T><<<(k * k + 255) / 256, 256, 0, c.stream>>>(c.gram_partials.f64(), (int)n_cta, 1, k, lambda, G, G64);
+      LAUNCHED(); CU(cudaGetLastError());
+      return B200ALS_OK;
+    }
+  }
   const int nt1 = (k + kGramTile - 1) / kGramTile, n_tiles = nt1 * (nt1 + 1) / 2;
   long long n_cta = std::min<long long>((long long)c.sm_count * 2 / std::max(1, n_tiles) + 1, (n + 255) / 256);
   n_cta = std::max<long long>(1, n_cta);
