@@ -277,7 +277,7 @@ static bool gram_use_tensor_cores() {
 template <typename T>
 static int run_gram(Ctx& c, const T* X, int k, long long n, double lambda, T* G, double* G64) {
   if constexpr (sizeof(T) == 4) {
-    if (k == kTcK && n > 0 && gram_use_tensor_cores()) {
+    if (k == kTcK && n >= 8192 && gram_use_tensor_cores()) {   // small inputs: the exact fp32 FMA kernel
       long long rows_per = std::max<long long>(1024, (n + 887) / 888);
       rows_per = ((rows_per + 255) / 256) * 256;   // whole drain windows
       const long long n_cta = (n + rows_per - 1) / rows_per;

@@ -10,10 +10,12 @@
 //   layout ((8,n),2):((1,SBO),LBO) in 16-byte units, cute/atom/mma_traits_sm100.hpp)
 // One CTA of 128 threads per slice of rows: stage 32 rows (4 x LDG.128 per lane -> 8 x STS.128 hi/lo), one thread
 // issues 3 x 4 `tcgen05.mma.cta_group::1.kind::tf32` (M128 N128 K8) per 32 rows, double-buffered tiles released by
-// `tcgen05.commit` -> mbarrier.  Every 256 rows the 128 x 128 fp32 accumulator is drained from TMEM
-// (`tcgen05.ld.32x32b`) and added to per-thread registers with round-to-nearest adds, bounding the length of the
-// tensor core's own fp32 accumulation chain; per-CTA partials go out in double and are summed in a fixed order by
-// gram_reduce_kernel (bit-reproducible).
+// `tcgen05.commit` -> mbarrier.  The tensor core adds into its fp32 accumulator with truncation, a bias of ~3e-8
+// per add that grows with the length of the chain (measured: 5.4e-6 relative after 96 adds).  Two measures keep
+// it at ~1e-6: the large hi'hi products and the small cross terms use SEPARATE TMEM accumulators (the cross terms
+// then truncate at their own, 1000x smaller magnitude), and every 256 rows both accumulators are drained
+// (`tcgen05.ld.32x32b`) into per-thread registers with round-to-nearest adds.  Per-CTA partials go out in double
+// and are summed in a fixed order by gram_reduce_kernel (bit-reproducible).
 #pragma once
 #include "common.cuh"
 
@@ -67,8 +69,8 @@ __global__ void __launch_bounds__(128) gram_tc_kernel(const float* __restrict__ 
     mbar_init(&S.acc_ready, 1);
     mbar_fence_init();
   }
-  if (warp == 0) {  // 128 TMEM columns (128 lanes x 128 fp32) for the accumulator
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
+  if (warp == 0) {  // 2 x 128 TMEM columns (128 lanes x 128 fp32 each): hi'hi accumulator and cross-term accumulator
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -125,9 +127,9 @@ __global__ void __launch_bounds__(128) gram_tc_kernel(const float* __restrict__ 
         const uint64_t dh = tc_smem_desc(&S.tile[b][0][ks * 2 * kTcLBO]);
         const uint64_t dl = tc_smem_desc(&S.tile[b][1][ks * 2 * kTcLBO]);
         const uint32_t first = ((t % kTcDrainTiles) == 0 && ks == 0) ? 0u : 1u;
-        tc_mma_tf32(tmem, dh, dh, first);   // hi' hi
-        tc_mma_tf32(tmem, dh, dl, 1u);      // hi' lo
-        tc_mma_tf32(tmem, dl, dh, 1u);      // lo' hi
+        tc_mma_tf32(tmem, dh, dh, first);            // hi' hi          -> accumulator 0
+        tc_mma_tf32(tmem + kTcK, dh, dl, first);     // hi' lo          -> accumulator 1
+        tc_mma_tf32(tmem + kTcK, dl, dh, 1u);        // lo' hi          -> accumulator 1
       }
       tc_commit(&S.mma_done[b]);
       if (last_of_window) tc_commit(&S.acc_ready);
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(128) gram_tc_kernel(const float* __restrict__ 
       phase_acc ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-      for (int c0 = 0; c0 < kTcK; c0 += 32) {
+      for (int c0 = 0; c0 < 2 * kTcK; c0 += 32) {   // columns [0,128): hi'hi ; [128,256): cross terms
         uint32_t r[32];
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
         asm volatile(
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(128) gram_tc_kernel(const float* __restrict__ 
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int c = 0; c < 32; c++) acc[c0 + c] += __uint_as_float(r[c]);
+        for (int c = 0; c < 32; c++) acc[(c0 + c) & (kTcK - 1)] += __uint_as_float(r[c]);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();   // every warp has read its quadrant before the next window overwrites the accumulator
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(128) gram_tc_kernel(const float* __restrict__ 
   for (int c = 0; c < kTcK; c++) out[c] = (double)acc[c];
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
 
 }  // namespace b200als
