@@ -24,6 +24,7 @@
 #include "eig.cuh"
 #include "gram.cuh"
 #include "gram_tc.cuh"
+#include "rotate_tc.cuh"
 
 using namespace b200als;
 
@@ -193,7 +194,7 @@ struct Ctx {
   int sm_count = 148;
   size_t smem_optin = 0;
   cudaStream_t stream = nullptr;
-  DevBuf ticket, loss_partials, loss_acc, status, gram_partials, reg_partials;
+  DevBuf ticket, loss_partials, loss_acc, status, gram_partials, reg_partials, rot_rt;
   bool attrs_set = false;
   int init() {
     if (stream) return B200ALS_OK;
@@ -1215,6 +1216,22 @@ extern "C" int b200als_set_shard(b200als_session* s, int which, int32_t begin, i
 
 static int rotate_matrix(Ctx& c, float* M, long long n, const float* R) {
   if (n <= 0) return B200ALS_OK;
+  // large matrices: tcgen05 3xTF32 kernel (B200ALS_ROTATE=ffma forces the fp32 FMA kernel)
+  const char* env = getenv("B200ALS_ROTATE");
+  const bool force_tc = env && (env[0] == 't' || env[0] == 'T');   // tests
+  const bool tc = force_tc || (!(env && (env[0] == 'f' || env[0] == 'F')) && n >= 65536);
+  if (tc) {
+    CU(c.rot_rt.ensure(sizeof(float) * kTcK * kTcK));
+    transpose_128_kernel<<<(kTcK * kTcK + 255) / 256, 256, 0, c.stream>>>(R, c.rot_rt.f32());
+    LAUNCHED(); CU(cudaGetLastError());
+    const size_t smem = sizeof(RotTcSmem);
+    CU(cudaFuncSetAttribute(rotate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long tiles = (n + 127) / 128;
+    const int grid = (int)std::min<long long>(tiles, c.sm_count);
+    rotate_tc_kernel<<<grid, 128, smem, c.stream>>>(M, M, c.rot_rt.f32(), n);
+    LAUNCHED(); CU(cudaGetLastError());
+    return B200ALS_OK;
+  }
   const size_t smem = sizeof(RotSmem);
   CU(cudaFuncSetAttribute(rotate_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long blocks = (n + kRotRows - 1) / kRotRows;

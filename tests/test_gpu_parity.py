@@ -308,3 +308,40 @@ def test_device_side_transpose_larger_ragged():
     T = sp.csr_matrix(A.T)
     T.sort_indices()
     assert np.array_equal(p2, T.indptr) and np.array_equal(i2, T.indices) and np.array_equal(v2, T.data.astype(np.float32))
+
+
+def test_tensor_core_gram_and_rotation_paths(cases, golden_half, monkeypatch):
+    """tcgen05 3xTF32 kernels (XtX and the change of basis; used automatically for >= 8k / 64k rows): forced on the
+    small golden case and on a 150k-row synthetic, against the reference golden / the fp32 oracle."""
+    monkeypatch.setenv("B200ALS_ROTATE", "tc")
+    c = cases["synth_implicit_cg_k128"]
+    s = _session_for(c, 3)
+    loss = s.half_iteration(L.USERS)
+    Y, X = s.get_factors(L.USERS), s.get_factors(L.ITEMS)
+    s.close()
+    assert relF(Y, golden_half["synth_implicit_cg_k128/Y_f64"]) < TOL_F32
+    assert abs(loss - float(golden_half["synth_implicit_cg_k128/loss_f64"])) <= TOL_F32 * abs(loss)
+    assert relF(X, c["X"]) < 2e-6
+    # larger: Gram on tensor cores too (n_item >= 8192)
+    n_user, n_item, nnz, k, lam = 150000, 70000, 80, 128, 0.1
+    ptr = np.zeros(n_user + 1, np.int32)
+    idx = np.zeros(n_user * nnz, np.int32)
+    v64 = np.zeros(n_user * nnz, np.float64)
+    L.check(L.lib().b200als_synth_csr_host(n_user, n_item, nnz, 43, 0, 0, L.vp(ptr), L.vp(idx), None, L.vp(v64)))
+    X = np.ascontiguousarray(wc.det_factors(n_item, k, 903, 0.1) * (1.0 + np.arange(k, dtype=np.float32)) ** -0.5)
+    Y0 = wc.det_factors(n_user, k, 904)
+    Yo = Y0.copy()
+    lo = oracle.als_implicit(ptr, idx, v64, X, Yo, oracle.gram(X, lam), lam, wc.CG, 3, oracle.max_threads())
+    res = {}
+    for mode in ("tc", "ffma"):
+        monkeypatch.setenv("B200ALS_ROTATE", mode)
+        monkeypatch.setenv("B200ALS_GRAM", mode)
+        s = Session.synthetic(n_user, 0, n_user, n_item, nnz, 43, k, "implicit", L.CONJUGATE_GRADIENT, 3, True, lam, 3)
+        s.set_factors(L.ITEMS, X)
+        s.set_factors(L.USERS, Y0)
+        loss = s.half_iteration(L.USERS)
+        res[mode] = (s.get_factors(L.USERS), loss, s.get_factors(L.ITEMS))
+        s.close()
+        assert relF(res[mode][0], Yo) < TOL_F32, (mode, relF(res[mode][0], Yo))
+        assert abs(loss - lo) <= TOL_F32 * abs(lo), mode
+        assert relF(res[mode][2], X) < 2e-6, mode
