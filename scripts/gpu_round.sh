@@ -30,6 +30,6 @@ echo "== ncu --set full of the tiled Cholesky kernel (C2)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:als_chol_tile -s 1 -c 1 -f -o $OUT/prof_chol \
     python bench.py --workload c2 --steps 1 --warmup 3 > $OUT/prof_chol.log 2>&1
 echo "== ncu --set full of rotate / gram / jacobi (1M-user slice)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"rotate_rows|gram_partial|jacobi" -s 9 -c 4 -f -o $OUT/prof_aux \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"rotate_tc|gram_tc|jacobi" -s 6 -c 4 -f -o $OUT/prof_aux \
     python bench.py --workload c3-small --steps 1 --warmup 3 --no-e2e --no-cpu > $OUT/prof_aux.log 2>&1
 ls -la $OUT
