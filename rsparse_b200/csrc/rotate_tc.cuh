@@ -118,22 +118,36 @@ __global__ void __launch_bounds__(128) rotate_tc_kernel(const float* __restrict_
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   };
 
+  // global loads of a quarter (8 x 16 B per thread: 8 lanes cover the 128 contiguous bytes of a row); issued one
+  // stage ahead so their latency hides behind the staging / MMA issue / drain of the current stage
+  auto load_quarter = [&](long long tile, int q, float4 (&v)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int rr = warp * 32 + i * 4 + (lane >> 3), c4 = lane & 7;
+      const long long row = tile * 128 + rr;
+      v[i] = (tile < n_tiles && row < n) ? __ldg(reinterpret_cast<const float4*>(X + (size_t)row * kTcK + q * 32) + c4)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  float4 nxt[8];
+  load_quarter(blockIdx.x, 0, nxt);
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
     const int tb = it & 1;
-    const long long r0 = tile * 128;
     for (int q = 0; q < 4; q++, stage++) {
       const int b = (int)(stage & 1);
+      float4 cur[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) cur[i] = nxt[i];
+      if (q < 3) load_quarter(tile, q + 1, nxt);
+      else load_quarter(tile + gridDim.x, 0, nxt);   // the next tile's rows are not written by anyone before we read them
       if (stage >= 2) {
         mbar_wait(&S.mma_done[b], ph_buf[b]);
         ph_buf[b] ^= 1;
       }
-      // stage features [32q, 32q+32) of the 128 rows: 8 lanes cover the 128 contiguous bytes of a row
 #pragma unroll
       for (int i = 0; i < 8; i++) {
         const int rr = warp * 32 + i * 4 + (lane >> 3), c4 = lane & 7;
-        const long long row = r0 + rr;
-        const float4 v = (row < n) ? __ldg(reinterpret_cast<const float4*>(X + (size_t)row * kTcK + q * 32) + c4)
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 v = cur[i];
         const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
         const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
         const int off = (rr >> 3) * kRtSBOA + c4 * kRtLBOA + (rr & 7) * 16;
