@@ -112,6 +112,18 @@ int b200als_als_explicit_double(const b200als_csc* m_csc, int rank, const double
 /* XtX = tcrossprod(X) + lambda*I  (R/model_WRMF.R:474-486, :347-353); X is rank x n host memory. */
 int b200als_gram_float(const float* X, int rank, int64_t n, double lambda, float* XtX);
 
+/* top-k recommendation: `top_product` (src/matrix_top_product.cpp:20-102, called through
+ * find_top_product R/utils.R:31-59 by MatrixFactorizationRecommender$predict).  R conventions are kept at the
+ * boundary: `exclude` and the returned indices are 1-based, missing entries are NA (INT_MIN / R's NA_real_),
+ * outputs are n_user x top_k column-major, `glob_mean` is added to every score.  Scores are accumulated in double
+ * like the reference (which converts float factors to double, R/utils.R:35-36).  user_emb is rank x n_user
+ * (what transform_ produces before R's t()); not_recommend is a CSR over users with ascending 0-based column
+ * indices (the @p / @j slots of a dgRMatrix) or NULL.  Limits of this engine: rank <= 128, top_k <= 128. */
+int b200als_top_product(const float* user_emb, int64_t n_user, const float* item_emb, int32_t n_item, int rank,
+                        int top_k, const int32_t* not_recommend_ptr, const int32_t* not_recommend_idx,
+                        const int32_t* exclude, int n_exclude, double glob_mean, int32_t* idx_out,
+                        double* scores_out);
+
 /* ------------------------------------------------------------------------------------------------
  * 2. Session API -- the device-resident form of WRMF$fit_transform (R/model_WRMF.R:173-360).
  *    The sparse matrix is uploaded once in both orientations, both factor matrices stay in HBM,

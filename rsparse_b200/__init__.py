@@ -9,5 +9,5 @@ include/b200als.h).  This package is the host-side mirror of the reference's R l
     model.components          # rank x n_item
 """
 from . import _lib  # noqa: F401
-from .ops import als_explicit, als_implicit, gram  # noqa: F401
+from .ops import als_explicit, als_implicit, gram, top_product  # noqa: F401
 from .wrmf import WRMF, Session  # noqa: F401

@@ -57,6 +57,8 @@ _PROTOS = {
                                               C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int,
                                               C.POINTER(C.c_double)]),
     "b200als_gram_float": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_void_p]),
+    "b200als_top_product": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     "b200als_default_options": (None, [C.POINTER(Options)]),
     "b200als_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(Csc), C.POINTER(Csc), C.c_int32, C.c_int32, C.c_int,
                                  C.POINTER(Options)]),

@@ -63,3 +63,35 @@ def als_explicit(ptr, idx, val, X, Y, cnt_X, lambda_, solver_code, cg_steps=3, d
                C.byref(loss)))
     del keep
     return loss.value
+
+
+def top_product(user_emb, item_emb, k, not_recommend=None, exclude=(), glob_mean=0.0):
+    """Top-k items per user (mirror of find_top_product / top_product, R/utils.R:31-59,
+    src/matrix_top_product.cpp:20-102) on the GPU.  `user_emb` (n_user, rank) and `item_emb` (n_item, rank) float32;
+    `not_recommend`: scipy sparse (n_user x n_item) or None; `exclude`: 0-based item ids excluded for everyone.
+    Returns (indices int32 (n_user, k), 0-based, -1 = NA; scores float64 (n_user, k), NaN = NA)."""
+    import scipy.sparse as sp
+    user_emb = _dense(np.ascontiguousarray(user_emb, dtype=np.float32), np.float32, "user_emb")
+    item_emb = _dense(np.ascontiguousarray(item_emb, dtype=np.float32), np.float32, "item_emb")
+    n_user, rank = user_emb.shape
+    n_item = item_emb.shape[0]
+    if item_emb.shape[1] != rank:
+        raise ValueError("ncol(x) == nrow(y) is not TRUE")                 # R/utils.R:50
+    ptr = idx = None
+    if not_recommend is not None:
+        nr = sp.csr_matrix(not_recommend)
+        if nr.shape != (n_user, n_item):
+            raise ValueError("not_recommend must be n_user x n_item")       # R/utils.R:55-56
+        nr.sort_indices()
+        ptr, idx = nr.indptr.astype(np.int32), nr.indices.astype(np.int32)
+    ex = np.ascontiguousarray(np.unique(np.asarray(exclude, dtype=np.int64)) + 1, dtype=np.int32)   # R is 1-based
+    if len(ex) and ex.max() > n_item:
+        raise ValueError("some of items_exclude indices are bigger than number of items")
+    out_idx = np.empty((k, n_user), np.int32)      # column-major n_user x k
+    out_sc = np.empty((k, n_user), np.float64)
+    L.check(L.lib().b200als_top_product(L.vp(user_emb), n_user, L.vp(item_emb), n_item, rank, int(k), L.vp(ptr), L.vp(idx),
+                                        L.vp(ex) if len(ex) else None, len(ex), float(glob_mean), L.vp(out_idx),
+                                        L.vp(out_sc)))
+    idx0 = out_idx.T.astype(np.int64)
+    idx0 = np.where(idx0 == -2147483648, -1, idx0 - 1).astype(np.int32)
+    return idx0, np.ascontiguousarray(out_sc.T)

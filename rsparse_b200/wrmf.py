@@ -269,5 +269,15 @@ class WRMF:
             raise ValueError("ncol(x) == ncol(self$components) is not TRUE")   # R/model_WRMF.R:367
         return self._transform(_targets_csc(x))
 
-    def predict(self, x, k, not_recommend=None, items_exclude=None):
-        raise NotImplementedError("top-k recommendation is the next row of the scope table (SURVEY 8f-2)")
+    def predict(self, x, k, not_recommend="x", items_exclude=(), return_scores=False):
+        """MatrixFactorizationRecommender$predict (R/MatrixFactorizationRecommender.R:24-78): transform(x), then the
+        top-k items per user, excluding `not_recommend` (default: the interactions in x) and `items_exclude`.
+        Returns 0-based item indices (n_user, k), -1 where fewer than k candidates exist."""
+        from .ops import top_product
+        if items_exclude is not None and len(items_exclude) and not np.issubdtype(np.asarray(items_exclude).dtype, np.integer):
+            raise TypeError("items_exclude should be one of character/integer")
+        emb = self.transform(x)
+        nr = x if isinstance(not_recommend, str) and not_recommend == "x" else not_recommend
+        idx, scores = top_product(emb.astype(np.float32), self._comp_rows.astype(np.float32), k, nr,
+                                  () if items_exclude is None else items_exclude, glob_mean=self.global_bias)
+        return (idx, scores) if return_scores else idx

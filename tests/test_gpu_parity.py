@@ -345,3 +345,63 @@ def test_tensor_core_gram_and_rotation_paths(cases, golden_half, monkeypatch):
         assert relF(res[mode][0], Yo) < TOL_F32, (mode, relF(res[mode][0], Yo))
         assert abs(loss - lo) <= TOL_F32 * abs(lo), mode
         assert relF(res[mode][2], X) < 2e-6, mode
+
+
+def _topk_case(n_user, n_item, rank, seed, density=0.1):
+    import scipy.sparse as sp
+    x = wc.det_factors(n_user, rank, seed, 1.0)
+    y = wc.det_factors(n_item, rank, seed + 1, 1.0)
+    u = wc.det_uniform(n_user * n_item, seed + 2).reshape(n_user, n_item)
+    nr = sp.csr_matrix((u < density).astype(np.float64))
+    nr.sort_indices()
+    return x, y, nr
+
+
+@pytest.mark.parametrize("n_user,n_item,rank,k", [(100, 50, 10, 10), (70, 333, 16, 7), (33, 1000, 128, 40), (5, 20, 4, 20)])
+def test_top_product_matches_reference_semantics(n_user, n_item, rank, k):
+    """`top_product` (src/matrix_top_product.cpp:20-102): indices bit-exact against the pure-Python restatement,
+    with per-user and global exclusions, NA padding when fewer than k candidates remain."""
+    from oracle.topk import NA_INTEGER, top_product as ref_top
+    from rsparse_b200 import top_product
+    x, y, nr = _topk_case(n_user, n_item, rank, 100 + n_item)
+    exclude0 = [1, 3, n_item - 1]
+    for (nr_use, ex) in ((None, []), (nr, []), (nr, exclude0)):
+        idx, sc = top_product(x, y, k, nr_use, ex, glob_mean=0.25 if ex else 0.0)
+        ridx, rsc = ref_top(x, y, k, None if nr_use is None else nr_use.indptr, None if nr_use is None else nr_use.indices,
+                            [e + 1 for e in ex], 0.25 if ex else 0.0)
+        ref0 = np.where(ridx == NA_INTEGER, -1, ridx - 1)
+        assert np.array_equal(idx, ref0)
+        ok = ref0 >= 0
+        assert np.allclose(sc[ok], rsc[ok], rtol=1e-13, atol=0) and np.all(np.isnan(sc[~ok]))
+    # the reference's own test (tests/testthat/test-top-product.R:3-14): equals order(scores, decreasing = TRUE)[1:k]
+    idx, _ = top_product(x, y, min(k, n_item), None, [])
+    full = x.astype(np.float64) @ y.astype(np.float64).T
+    assert np.array_equal(idx[0], np.argsort(-full[0], kind="stable")[:min(k, n_item)])
+
+
+def test_top_product_ties_follow_the_heap_rule():
+    """All-zero user embeddings give equal scores everywhere: the heap keeps the FIRST k items and emits them by
+    decreasing index (src/matrix_top_product.cpp:80-95)."""
+    from oracle.topk import top_product as ref_top
+    from rsparse_b200 import top_product
+    x = np.zeros((3, 8), np.float32)
+    y = wc.det_factors(40, 8, 5, 1.0)
+    idx, _ = top_product(x, y, 6, None, [0])
+    ridx, _ = ref_top(x, y, 6, None, None, [1])
+    assert np.array_equal(idx, ridx - 1)
+    assert list(idx[0]) == [6, 5, 4, 3, 2, 1]
+
+
+def test_wrmf_predict_like_reference_test():
+    """tests/testthat/test-wrmf.R:59-61: predict(cv, k) has shape (n_cv, k); recommended items exclude the seen ones."""
+    M = wc.load_movielens()
+    train, cv = M[:900], M[900:]
+    model = WRMF(rank=8, lambda_=0.1, feedback="implicit", solver="conjugate_gradient", precision="float", seed=1)
+    model.fit_transform(train, n_iter=3, convergence_tol=-1)
+    K = 7
+    preds = model.predict(cv, k=K)
+    assert preds.shape == (cv.shape[0], K) and preds.min() >= 0 and preds.max() < M.shape[1]
+    seen = cv.tolil().rows
+    for u in range(cv.shape[0]):
+        assert not set(preds[u]) & set(seen[u])
+        assert len(set(preds[u])) == K
