@@ -40,6 +40,8 @@ WORKLOADS = {
     "c4": (10_000_000, 1_000_000, 80, 128, 3, 0.1),        # BASELINE configs[3]: explicit feedback (MMMF)
     "c2": (1_000_000, 100_000, 50, 64, 3, 0.1),            # BASELINE configs[1]: implicit, rank 64, Cholesky
 }
+# side workload "topk": MatrixFactorizationRecommender$predict's top_product
+TOPK = dict(n_user=65536, n_item=1_000_000, rank=128, k=10, nnz=80)
 # (feedback, solver) per workload; everything not listed is implicit CG
 WORKLOAD_MODE = {"c4": ("explicit", 1), "c2": ("implicit", 0)}
 BYTES_PER_ROW = lambda n, k: 4 * n * k + 8 * n + 4 + 4 * k + 4 * k   # 42,628 at n=80, k=128
@@ -165,13 +167,55 @@ def run_reference(args, rank, world):
     print(json.dumps(out), flush=True)
 
 
+def run_topk(args):
+    """Side workload: top-10 of 65,536 users x 1 M items at rank 128 with each user's 80 interactions excluded,
+    through b200als_top_product (host buffers, copies inside the timed region)."""
+    from rsparse_b200 import _lib as L
+    from rsparse_b200 import top_product
+    import scipy.sparse as sp
+    T = TOPK
+    rng = np.random.default_rng(7)
+    x = (rng.standard_normal((T["n_user"], T["rank"]), dtype=np.float32) / 10)
+    y = (rng.standard_normal((T["n_item"], T["rank"]), dtype=np.float32) / 10)
+    ptr = np.empty(T["n_user"] + 1, np.int32)
+    idx = np.empty(T["n_user"] * T["nnz"], np.int32)
+    L.check(L.lib().b200als_synth_csr_host(T["n_user"], T["n_item"], T["nnz"], 42, 0, 0, L.vp(ptr), L.vp(idx), None, None))
+    nr = sp.csr_matrix((np.ones(len(idx), np.float32), idx, ptr), shape=(T["n_user"], T["n_item"]))
+    top_product(x[:4096], y, T["k"], nr[:4096], [])        # warm-up
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ids, sc = top_product(x, y, T["k"], nr, [])
+    dt = (time.perf_counter() - t0) / args.steps
+    flops = 2.0 * T["n_user"] * T["n_item"] * T["rank"]
+    # CPU stand-in for the reference's loop on a sample of users: BLAS scores + partial sort (numpy), all cores
+    m = 512
+    t0 = time.perf_counter()
+    s64 = x[:m].astype(np.float64) @ y.astype(np.float64).T
+    s64[nr[:m].nonzero()] = -np.inf
+    part = np.argpartition(-s64, T["k"], axis=1)[:, :T["k"]]
+    cpu_dt = time.perf_counter() - t0
+    same = float(np.mean([set(part[u]) == set(ids[u]) for u in range(m)]))
+    out = {"metric": "top-k recommendation users/sec (top_product, k=10, rank=128, 1M items)", "value": T["n_user"] / dt,
+           "unit": "users/s", "n_gpus": 1, "steps": args.steps, "warmup": 1, "ms_per_step": 1e3 * dt, "higher_is_better": True,
+           "dtype": "f64 accumulate of f32 factors", "data": "synthetic",
+           "config": {"workload": "topk: %(n_user)d users x %(n_item)d items, rank %(rank)d, k %(k)d, %(nnz)d excluded per user" % T},
+           "roofline": {"bound": "fp64", "achieved": flops / dt / 1e12, "peak": 40.0, "unit": "TFLOP/s",
+                        "frac": flops / dt / 1e12 / 40.0, "traffic": None, "peak_source": "nominal B200 fp64 (no measured value)"},
+           "cpu_baseline": {"value": m / cpu_dt, "unit": "users/s", "cores": os.cpu_count(), "kind": "port",
+                            "sample": "numpy: dgemm scores + argpartition on %d users (not the reference's heap loop)" % m,
+                            "top_k_sets_equal_frac": same},
+           "e2e": {"value": T["n_user"] / dt, "unit": "users/s", "h2d_bytes_per_step": int(x.nbytes + y.nbytes + ptr.nbytes + idx.nbytes),
+                   "d2h_bytes_per_step": int(ids.size * 12)}}
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("B200ALS_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("B200ALS_WORKLOAD", "c3"), choices=sorted(WORKLOADS) + ["topk"])
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 resident full-XtX, 3 resident eigenbasis")
     ap.add_argument("--stage", type=int, default=0, help="resident-kernel tile staging: 0 default, 1 cp.async.bulk, 2 cp.async")
     ap.add_argument("--ctas", type=int, default=0, help="resident-kernel CTAs per SM: 0 default, 3, 4")
@@ -187,6 +231,8 @@ def main():
     if args.impl == "reference":
         return run_reference(args, rank, world)
 
+    if args.workload == "topk":
+        return run_topk(args)
     from rsparse_b200 import Session
     from rsparse_b200 import _lib as L
     n_user, n_item, nnz, k, cg, lam = WORKLOADS[args.workload]
