@@ -88,7 +88,7 @@ unsigned long long b200als_launch_count(void);
  *    back and retains nothing.  `*loss` receives the reference's return value (loss / nnz).
  *    `n_threads` is accepted for signature compatibility and ignored.
  *    with_biases / global_bias are not implemented: a non-zero value returns
- *    B200ALS_EUNSUPPORTED.  solver = B200ALS_NNLS likewise (section 8f-4).
+ *    B200ALS_EUNSUPPORTED.  solver = B200ALS_NNLS runs c_nnls (inst/include/nnls.hpp:10-48) on the GPU.
  * ---------------------------------------------------------------------------------------------- */
 int b200als_als_implicit_float(const b200als_csc* m_csc, int rank, const float* X, float* Y,
                                const float* XtX, double lambda, int n_threads, unsigned solver,

@@ -7,6 +7,8 @@
 //                  loop body         wrmf_implicit.hpp:175-282 / wrmf_explicit.hpp:71-146
 //   als_chol_generic_kernel  CTA per row, per-row Gram + Cholesky in shared memory
 //       reference: wrmf_implicit.hpp:207-208,231,236 / wrmf_explicit.hpp:103-108
+//       the same kernel runs solver = "nnls": c_nnls / scd_ls_update, inst/include/nnls.hpp:10-48, on the system it
+//       has just assembled (wrmf_implicit.hpp:233-234, wrmf_explicit.hpp:110)
 // Scheduling is a persistent grid with an atomic row ticket -- the GPU analogue of the reference's
 // `omp for schedule(dynamic)` (wrmf_implicit.hpp:172-174).
 #pragma once
@@ -27,6 +29,7 @@ struct SolveParams {
   int feedback;        // 0 implicit, 1 explicit
   int cg_steps;
   int dynamic_lambda;
+  int solver;          // als_chol_generic_kernel only: 0 Cholesky, 2 sequential coordinate-wise NNLS (wrmf.hpp:16-18)
   double lambda;
   const int32_t* row_list;  // optional subset of rows to solve
   int n_list;
@@ -242,6 +245,8 @@ __global__ void __launch_bounds__(256) als_chol_generic_kernel(SolveParams<T> P)
   T* colj = tile + (size_t)kCholTN * k;           // k + 1
   T* wts = colj + (k + 1);                        // kCholTN
   T* cs = wts + kCholTN;                          // kCholTN
+  T* Bm = cs + kCholTN;                           // k * ks, NNLS only: XtX = lhs' * lhs
+  T* muv = Bm + ((P.solver == 2) ? (size_t)k * ks : 0);  // k, NNLS only
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const bool implicit = (P.feedback == 0);
   const int total = P.n_list_dev ? __ldg(P.n_list_dev) : (P.row_list ? P.n_list : P.n_targets);
@@ -298,6 +303,47 @@ __global__ void __launch_bounds__(256) als_chol_generic_kernel(SolveParams<T> P)
         }
       __syncthreads();
     }
+    if (P.solver == 2) {
+      // ---- c_nnls (nnls.hpp:37-48): X = lhs (symmetric, lower triangle + mirror), y = rhs (row k of A) -----------
+      auto lhs = [&](int a, int b) -> T { return (b <= a) ? A[a * ks + b] : A[b * ks + a]; };
+      for (int a = ty; a < k; a += 16)
+        for (int b = tx; b < k; b += 16) {
+          T sacc = T(0);
+          for (int m = 0; m < k; m++) sacc += lhs(m, a) * lhs(m, b);    // XtX = Xt * X
+          if (a == b) sacc += (T)1e-16;                                // XtX.diag() += EPS
+          Bm[a * ks + b] = sacc;
+        }
+      for (int f = tid; f < k; f += 256) colj[f] = y[f];                // res = initial = Y.col(i)
+      __syncthreads();
+      for (int a = tid; a < k; a += 256) {                               // mu = XtX * init - Xt * y
+        T sacc = T(0);
+        for (int m = 0; m < k; m++) sacc += Bm[a * ks + m] * colj[m] - lhs(m, a) * A[k * ks + m];
+        muv[a] = sacc;
+      }
+      __syncthreads();
+      // ---- scd_ls_update (nnls.hpp:10-34): sequential over coordinates, warp 0, mu updated lane-parallel -------
+      if (tid < 32) {
+        for (int t = 0; t < 10000; t++) {                               // SCD_MAX_ITER
+          T rel_diff = T(0);
+          for (int c = 0; c < k; c++) {
+            const T old_value = colj[c];
+            T new_value = old_value - muv[c] / Bm[c * ks + c];
+            if (new_value < T(0)) new_value = T(0);
+            const T diff = new_value - old_value;
+            __syncwarp();
+            if (diff != T(0)) {                                         // same value in every lane
+              if (tid == 0) colj[c] = new_value;
+              for (int l = tid; l < k; l += 32) muv[l] += diff * Bm[c * ks + l];   // XtX.unsafe_col(c), symmetric
+              const T step_err = (T)(fabs((double)diff) / (fabs((double)old_value) + 1e-16));
+              if (step_err > rel_diff) rel_diff = step_err;
+            }
+            __syncwarp();
+          }
+          if (rel_diff <= (T)1e-4) break;                                // SCD_TOL
+        }
+      }
+      __syncthreads();
+    } else {
     // right-looking Cholesky on rows 0..k (row k = rhs => ends up holding z = L^-1 rhs)
     for (int j = 0; j < k; j++) {
       const T d = A[j * ks + j];
@@ -334,6 +380,7 @@ __global__ void __launch_bounds__(256) als_chol_generic_kernel(SolveParams<T> P)
       }
     }
     __syncthreads();
+    }
     for (int f = tid; f < k; f += 256) y[f] = colj[f];
     // loss: warp per gathered row
     T l = T(0);
@@ -358,8 +405,9 @@ __global__ void __launch_bounds__(256) als_chol_generic_kernel(SolveParams<T> P)
 }
 
 template <typename T>
-inline size_t chol_generic_smem_bytes(int k) {
-  return sizeof(T) * ((size_t)(k + 1) * (k + 1) + (size_t)kCholTN * k + (k + 1) + 2 * kCholTN) + 16;
+inline size_t chol_generic_smem_bytes(int k, int solver = 0) {
+  const size_t nnls = (solver == 2) ? ((size_t)k * (k + 1) + k) : 0;
+  return sizeof(T) * ((size_t)(k + 1) * (k + 1) + (size_t)kCholTN * k + (k + 1) + 2 * kCholTN + nnls) + 16;
 }
 
 }  // namespace b200als

@@ -361,8 +361,8 @@ static int launch_cg_generic(Ctx& c, const SolveParams<T>& P, int n_work, int* g
 // (sum over solved rows) into c.loss_acc[0].
 template <typename T>
 static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const float* diag, int k, const HalfOpts& o) {
-  if (o.solver == B200ALS_NNLS) return fail(B200ALS_EUNSUPPORTED, "solver = nnls is not implemented (SURVEY 8f-4)");
-  if (o.solver != B200ALS_CHOLESKY && o.solver != B200ALS_CONJUGATE_GRADIENT) return fail(B200ALS_EINVAL, "unknown solver code");
+  if (o.solver != B200ALS_CHOLESKY && o.solver != B200ALS_CONJUGATE_GRADIENT && o.solver != B200ALS_NNLS)
+    return fail(B200ALS_EINVAL, "unknown solver code");
   if (o.feedback == B200ALS_IMPLICIT && !G && !diag) return fail(B200ALS_EINVAL, "implicit feedback needs XtX");
   if (o.reset_loss) {
     CU(cudaMemsetAsync(c.loss_acc.p, 0, sizeof(double), c.stream));
@@ -385,6 +385,7 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
   P.feedback = o.feedback;
   P.cg_steps = o.cg_steps;
   P.dynamic_lambda = o.dynamic_lambda;
+  P.solver = o.solver;
   P.lambda = o.lambda;
   P.row_list = nullptr;
   P.n_list = 0;
@@ -413,15 +414,15 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
     return B200ALS_OK;
   };
 
-  if (o.solver == B200ALS_CHOLESKY) {
+  if (o.solver == B200ALS_CHOLESKY || o.solver == B200ALS_NNLS) {
     auto run_generic_chol = [&](const int32_t* list, int n_list) -> int {
       P.row_list = list;
       P.n_list = n_list;
       const int n_work = list ? n_list : n_rows_here;
       if (n_work == 0) return B200ALS_OK;
-      const size_t smem = chol_generic_smem_bytes<T>(k);
+      const size_t smem = chol_generic_smem_bytes<T>(k, o.solver);
       if (smem > c.smem_optin)
-        return fail(B200ALS_EUNSUPPORTED, "cholesky: rank too large for the shared-memory factorisation (needs " +
+        return fail(B200ALS_EUNSUPPORTED, "cholesky / nnls: rank too large for the shared-memory factorisation (needs " +
                                              std::to_string(smem) + " B)");
       CU(cudaFuncSetAttribute(als_chol_generic_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (smem + 1024)));
@@ -434,7 +435,7 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
       return B200ALS_OK;
     };
     bool tiled = false;
-    if constexpr (sizeof(T) == 4) tiled = (k == 64 || k == 128) && o.kernel != 1 && !sub_range;
+    if constexpr (sizeof(T) == 4) tiled = (o.solver == B200ALS_CHOLESKY) && (k == 64 || k == 128) && o.kernel != 1 && !sub_range;
     if (!tiled) return run_generic_chol(nullptr, 0);
     if constexpr (sizeof(T) == 4) {
       // rows with 1..80 non-zeros: tile kernel; longer rows: generic kernel; empty rows: zero
@@ -761,7 +762,7 @@ static int stateless_pipelined(const b200als_csc* A, const float* X, float* Y, c
       SolveParams<float> P;
       P.ptr = b.ptr.i32(); P.idx = b.idx.i32(); P.val = b.val32.f32(); P.X = pc.X.f32(); P.Y = b.Y.f32();
       P.G = implicit ? Glong : nullptr; P.k = k; P.n_targets = nr; P.feedback = o.feedback; P.cg_steps = o.cg_steps;
-      P.dynamic_lambda = o.dynamic_lambda; P.lambda = o.lambda; P.row_list = b.long_list.i32(); P.n_list = 0;
+      P.dynamic_lambda = o.dynamic_lambda; P.solver = 0; P.lambda = o.lambda; P.row_list = b.long_list.i32(); P.n_list = 0;
       P.n_list_dev = b.counts.i32() + 1; P.ptr_base = (int)e0; P.row_begin = 0; P.ticket = c.ticket.u64();
       P.loss_partials = c.loss_partials.f64(); P.status = c.status.i32();
       CU(cudaMemsetAsync(c.ticket.p, 0, sizeof(unsigned long long), c.stream));

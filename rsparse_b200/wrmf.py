@@ -138,7 +138,7 @@ class WRMF:
     """Weighted Regularized Matrix Factorization (mirror of R/model_WRMF.R:35-454).
 
     Parameters are the reference's (`lambda` is spelled `lambda_`).  Not implemented by the engine
-    yet: with_user_item_bias / with_global_bias, solver="nnls" -- these raise."""
+    yet: with_user_item_bias / with_global_bias -- these raise."""
 
     def __init__(self, rank=10, lambda_=0.0, dynamic_lambda=True, init=None, preprocess=None, feedback="implicit",
                  solver="conjugate_gradient", with_user_item_bias=False, with_global_bias=False, cg_steps=3,
@@ -155,8 +155,6 @@ class WRMF:
             raise TypeError("cg_steps must be an integer")               # stopifnot(is.integer(cg_steps))
         if with_user_item_bias or with_global_bias:
             raise NotImplementedError("bias terms are outside this engine's hot-path scope (SURVEY 8f-3)")
-        if solver == "nnls":
-            raise NotImplementedError("solver='nnls' is outside this engine's hot-path scope (SURVEY 8f-4)")
         self._solver_code = _SOLVER_CODES[solver]
         self._non_negative = solver == "nnls"
         self._precision = precision
@@ -205,6 +203,9 @@ class WRMF:
             if self.components.shape != (k, n_item):
                 raise ValueError("init must be rank x n_item")
             comp = np.ascontiguousarray(self.components.T, dtype=dt)
+        if self._non_negative:                                              # R/model_WRMF.R:251-255
+            comp = np.abs(comp)
+            U = np.abs(U)
         cnt_u = np.diff(items[0]).astype(dt)   # diff(c_ui@p): nnz per item -> cnt_X of the user half (:311)
         cnt_i = np.diff(users[0]).astype(dt)   # diff(c_iu@p): nnz per user -> cnt_X of the item half (:312)
         self._cnt_u = cnt_u

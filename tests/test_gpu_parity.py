@@ -140,20 +140,30 @@ def test_session_fit_matches_reference_trace(name, golden_traces):
 
 
 @pytest.mark.parametrize("precision", ["float", "double"])
-@pytest.mark.parametrize("feedback,solver", [("implicit", "conjugate_gradient"), ("implicit", "cholesky"),
-                                             ("explicit", "conjugate_gradient"), ("explicit", "cholesky")])
-def test_wrmf_class_like_reference_tests(precision, feedback, solver):
-    """tests/testthat/test-wrmf.R:29-64: shapes, fit_transform(train) == transform(train), transform(cv) shape."""
+@pytest.mark.parametrize("feedback,solver,lam", [
+    ("implicit", "conjugate_gradient", 0.1), ("implicit", "cholesky", 0.1), ("implicit", "nnls", 0.1),
+    ("explicit", "conjugate_gradient", 0.1), ("explicit", "cholesky", 0.1), ("explicit", "nnls", 0.1),
+    ("implicit", "cholesky", 0.0), ("implicit", "conjugate_gradient", 1000.0), ("implicit", "nnls", 1000.0),
+    ("explicit", "cholesky", 1000.0), ("explicit", "nnls", 1000.0)])
+def test_wrmf_class_like_reference_tests(precision, feedback, solver, lam):
+    """tests/testthat/test-wrmf.R:9-71: shapes, fit_transform(train) == transform(train), transform(cv) shape,
+    non-negative embeddings for solver = "nnls"."""
     M = wc.load_movielens()
     train, cv = M[:900], M[900:]
-    model = WRMF(rank=8, lambda_=0.1, feedback=feedback, solver=solver, precision=precision, seed=1)
+    model = WRMF(rank=8, lambda_=lam, feedback=feedback, solver=solver, precision=precision, seed=1)
     emb = model.fit_transform(train, n_iter=5, convergence_tol=-1)
     assert emb.shape == (900, 8)
     assert model.components.shape == (8, M.shape[1])
     emb2 = model.transform(train)
-    assert relF(emb2, emb) < (3e-5 if precision == "float" else 1e-9)
-    assert model.transform(cv).shape == (cv.shape[0], 8)
+    # nnls is a coordinate descent stopped at a relative step of 1e-4 (inst/include/nnls.hpp:44) from a different
+    # start in transform() than in the last fit sweep: equal only to that tolerance.
+    tol = 2e-3 if solver == "nnls" else (3e-5 if precision == "float" else 1e-9)
+    assert relF(emb2, emb) < tol
+    emb_cv = model.transform(cv)
+    assert emb_cv.shape == (cv.shape[0], 8)
     assert np.all(np.isfinite(emb))
+    if solver == "nnls":
+        assert np.all(emb >= 0) and np.all(emb_cv >= 0) and np.all(model.components >= 0)
 
 
 def test_wrmf_rejects_what_the_reference_rejects():
@@ -220,8 +230,8 @@ def test_explicit_larger_synthetic_vs_oracle():
 def test_unsupported_options_fail_loudly(cases):
     c = cases["synth_cg_early_exit_k16"]
     with pytest.raises(L.B200AlsError) as e:
-        als_implicit(c["ptr"], c["idx"], c["val"], c["X"], c["Y0"].copy(), 0.1, L.NNLS)
-    assert e.value.code == L.EUNSUPPORTED
+        als_implicit(c["ptr"], c["idx"], c["val"], c["X"], c["Y0"].copy(), 0.1, 7)
+    assert e.value.code == L.EINVAL
     with pytest.raises(L.B200AlsError) as e:
         als_implicit(c["ptr"], c["idx"], c["val"], c["X"], c["Y0"].copy(), 0.1, L.CHOLESKY, with_user_item_bias=True)
     assert e.value.code == L.EUNSUPPORTED

@@ -107,4 +107,11 @@ def half_iteration_cases():
     add("synth_long_implicit_cg_k128", det_csr(24, 1000, 350, 18, ragged=True), 1000, 128, "implicit", CG, 0.1, 18)
     add("synth_cg_early_exit_k16", det_csr(200, 300, 10, 19), 300, 16, "implicit", CG, 10.0, 19, scale=1e-5)
     add("synth_implicit_cg5_k32", det_csr(300, 300, 20, 20), 300, 32, "implicit", CG, 0.1, 20, cg_steps=5)
+    # solver = "nnls" (inst/include/nnls.hpp): non-negative warm start as R does (abs(), R/model_WRMF.R:251-255)
+    add("ml100k_user_implicit_nnls_k10", users, n_item, 10, "implicit", NNLS, 0.1, 21)
+    add("ml100k_item_explicit_nnls_k8", items, n_user, 8, "explicit", NNLS, 0.1, 22, cnt_X=cnt_users)
+    add("synth_ragged_implicit_nnls_k32", rag, 900, 32, "implicit", NNLS, 0.5, 23)
+    for name in ("ml100k_user_implicit_nnls_k10", "ml100k_item_explicit_nnls_k8", "synth_ragged_implicit_nnls_k32"):
+        C[name]["X"] = np.abs(C[name]["X"])
+        C[name]["Y0"] = np.abs(C[name]["Y0"])
     return C
