@@ -87,8 +87,18 @@ unsigned long long b200als_launch_count(void);
  *    All pointers are HOST pointers; the call copies in, computes on the current device, copies Y
  *    back and retains nothing.  `*loss` receives the reference's return value (loss / nnz).
  *    `n_threads` is accepted for signature compatibility and ignored.
- *    with_biases / global_bias are not implemented: a non-zero value returns
- *    B200ALS_EUNSUPPORTED.  solver = B200ALS_NNLS runs c_nnls (inst/include/nnls.hpp:10-48) on the GPU.
+ *    solver = B200ALS_NNLS runs c_nnls (inst/include/nnls.hpp:10-48) on the GPU.
+ *    Bias terms, with the reference's conventions:
+ *      with_biases: X and Y carry `rank` = R's private$rank rows (user rank + 2, R/model_WRMF.R:162-166),
+ *        is_x_bias_last_row:  X = [1, ..., x_bias]   Y = [y_bias, ..., 1]
+ *        otherwise:           X = [x_bias, ..., 1]   Y = [1, ..., y_bias]       (wrmf_implicit.hpp:96-101)
+ *        the solved system has rank-1 unknowns and XtX is (rank-1) x (rank-1), built from X without its bias row
+ *        (R/model_WRMF.R:474-486); the row of ones in Y is left untouched.
+ *      global_bias (implicit only): values below sqrt(epsilon) count as 0 (wrmf_implicit.hpp:108-109);
+ *        without with_biases `global_bias_base` ([rank], host) is rewritten when initialize_bias_base is set
+ *        (:111-112) and read otherwise.
+ *      One deliberate difference: implicit + CONJUGATE_GRADIENT + with_biases raises a dimension error in the
+ *      reference (`init` loses a row twice, :191 and :199); here it is solved with `init` dropped once.
  * ---------------------------------------------------------------------------------------------- */
 int b200als_als_implicit_float(const b200als_csc* m_csc, int rank, const float* X, float* Y,
                                const float* XtX, double lambda, int n_threads, unsigned solver,
@@ -108,6 +118,23 @@ int b200als_als_explicit_double(const b200als_csc* m_csc, int rank, const double
                                 const double* cnt_X, double lambda, unsigned n_threads,
                                 unsigned solver, unsigned cg_steps, int dynamic_lambda,
                                 int with_biases, int is_x_bias_last_row, double* loss);
+
+/* initialize_biases<T> (inst/include/wrmf_utils.hpp:170-183; Rcpp exports src/wrmf_init.cpp:6-34; called by
+ * R/model_WRMF.R:260-289): five alternating sweeps that seed the user and item biases.  (csc_ptr [n_item+1],
+ * csc_idx, csc_val) is the user x item matrix by item column (@p, @i, @x of c_ui), (csr_ptr [n_user+1], csr_idx,
+ * csr_val) the same entries by user (c_iu).  user_bias [n_user] / item_bias [n_item] are in/out host vectors.  For
+ * explicit feedback with calculate_global_bias both value arrays are shifted by the mean rating IN PLACE, as the
+ * reference does (:48-51).  *global_bias receives the return value (0 unless calculate_global_bias). */
+int b200als_initialize_biases_float(int32_t n_user, int32_t n_item, int64_t nnz, const int32_t* csc_ptr,
+                                    const int32_t* csc_idx, double* csc_val, const int32_t* csr_ptr,
+                                    const int32_t* csr_idx, double* csr_val, float* user_bias, float* item_bias,
+                                    double lambda, int dynamic_lambda, int non_negative, int calculate_global_bias,
+                                    int is_explicit_feedback, double* global_bias);
+int b200als_initialize_biases_double(int32_t n_user, int32_t n_item, int64_t nnz, const int32_t* csc_ptr,
+                                     const int32_t* csc_idx, double* csc_val, const int32_t* csr_ptr,
+                                     const int32_t* csr_idx, double* csr_val, double* user_bias, double* item_bias,
+                                     double lambda, int dynamic_lambda, int non_negative, int calculate_global_bias,
+                                     int is_explicit_feedback, double* global_bias);
 
 /* XtX = tcrossprod(X) + lambda*I  (R/model_WRMF.R:474-486, :347-353); X is rank x n host memory. */
 int b200als_gram_float(const float* X, int rank, int64_t n, double lambda, float* XtX);

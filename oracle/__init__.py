@@ -42,7 +42,10 @@ def lib():
         build()
         _lib = C.CDLL(os.path.join(_HERE, "liboracle_wrmf.so"))
         for name in ("oracle_als_implicit_f32", "oracle_als_implicit_f64",
-                     "oracle_als_explicit_f32", "oracle_als_explicit_f64"):
+                     "oracle_als_explicit_f32", "oracle_als_explicit_f64",
+                     "oracle_als_implicit_bias_f32", "oracle_als_implicit_bias_f64",
+                     "oracle_als_explicit_bias_f32", "oracle_als_explicit_bias_f64",
+                     "oracle_initialize_biases_f32", "oracle_initialize_biases_f64"):
             getattr(_lib, name).restype = C.c_double
         _lib.oracle_max_threads.restype = C.c_int
     return _lib
@@ -58,7 +61,8 @@ def ref():
         build()
         _ref = C.CDLL(os.path.join(_HERE, "_ref", "libref_wrmf.so"))
         for name in ("ref_als_implicit_f32", "ref_als_implicit_f64",
-                     "ref_als_explicit_f32", "ref_als_explicit_f64"):
+                     "ref_als_explicit_f32", "ref_als_explicit_f64",
+                     "ref_initialize_biases_f32", "ref_initialize_biases_f64"):
             getattr(_ref, name).restype = C.c_double
     return _ref
 
@@ -121,3 +125,68 @@ def als_explicit(ptr, idx, val, X, Y, cnt_X, lam, solver, cg_steps=3, dynamic_la
               C.c_int(k), C.c_int(n_src), _p(Y), _p(cnt_X), C.c_int(len(cnt_X)), C.c_double(lam),
               C.c_int(n_threads), C.c_uint(solver), C.c_uint(cg_steps), C.c_int(int(dynamic_lambda)),
               C.c_int(0), C.c_int(0))
+
+
+def als_implicit_bias(ptr, idx, val, X, Y, XtX, lam, solver, cg_steps=3, with_biases=False, is_bias_last_row=False,
+                      global_bias=0.0, global_bias_base=None, initialize_bias_base=True, n_threads=1, impl="oracle"):
+    """Implicit half-iteration with user/item and/or global bias (wrmf_implicit.hpp:90-305, every branch).
+    X, Y have rank+2 columns when with_biases; XtX is (rank+1)^2 then.  global_bias_base (length = XtX side) is
+    updated in place when initialize_bias_base.  Returns loss."""
+    k, n_src, nc, sfx = _check(ptr, idx, val, X, Y)
+    ks = k - int(bool(with_biases))
+    assert XtX.shape == (ks, ks) and XtX.dtype == X.dtype
+    if global_bias_base is None:
+        global_bias_base = np.zeros(ks, dtype=X.dtype)
+    assert global_bias_base.dtype == X.dtype and len(global_bias_base) >= (0 if with_biases else ks)
+    if impl == "oracle":
+        fn = getattr(lib(), "oracle_als_implicit_bias_" + sfx)
+        return fn(C.c_int(nc), C.c_size_t(len(idx)), _p(ptr), _p(idx), _p(val), _p(X), C.c_int(k), C.c_int(n_src),
+                  _p(Y), _p(XtX), C.c_double(lam), C.c_int(n_threads), C.c_int(solver), C.c_int(cg_steps),
+                  C.c_int(int(with_biases)), C.c_int(int(is_bias_last_row)), C.c_double(global_bias),
+                  _p(global_bias_base), C.c_int(int(initialize_bias_base)))
+    fn = getattr(ref(), "ref_als_implicit_" + sfx)
+    return fn(C.c_int(n_src), C.c_int(nc), C.c_size_t(len(idx)), _p(idx), _p(ptr), _p(val), _p(X),
+              C.c_int(k), C.c_int(n_src), _p(Y), _p(np.ascontiguousarray(XtX)), C.c_int(ks),
+              C.c_double(lam), C.c_int(n_threads), C.c_uint(solver), C.c_uint(cg_steps), C.c_int(int(with_biases)),
+              C.c_int(int(is_bias_last_row)), C.c_double(global_bias), _p(global_bias_base),
+              C.c_int(len(global_bias_base)), C.c_int(int(initialize_bias_base)))
+
+
+def als_explicit_bias(ptr, idx, val, X, Y, cnt_X, lam, solver, cg_steps=3, dynamic_lambda=True, with_biases=False,
+                      is_bias_last_row=False, n_threads=1, impl="oracle"):
+    """Explicit half-iteration with user/item biases (wrmf_explicit.hpp:33-174, every branch)."""
+    k, n_src, nc, sfx = _check(ptr, idx, val, X, Y)
+    if cnt_X is None:
+        cnt_X = np.zeros(n_src, dtype=X.dtype)
+    cnt_X = np.ascontiguousarray(cnt_X, dtype=X.dtype)
+    if impl == "oracle":
+        fn = getattr(lib(), "oracle_als_explicit_bias_" + sfx)
+        return fn(C.c_int(nc), C.c_size_t(len(idx)), _p(ptr), _p(idx), _p(val), _p(X), C.c_int(k), C.c_int(n_src),
+                  _p(Y), _p(cnt_X), C.c_double(lam), C.c_int(n_threads), C.c_int(solver), C.c_int(cg_steps),
+                  C.c_int(int(dynamic_lambda)), C.c_int(int(with_biases)), C.c_int(int(is_bias_last_row)))
+    fn = getattr(ref(), "ref_als_explicit_" + sfx)
+    return fn(C.c_int(n_src), C.c_int(nc), C.c_size_t(len(idx)), _p(idx), _p(ptr), _p(val), _p(X),
+              C.c_int(k), C.c_int(n_src), _p(Y), _p(cnt_X), C.c_int(len(cnt_X)), C.c_double(lam),
+              C.c_int(n_threads), C.c_uint(solver), C.c_uint(cg_steps), C.c_int(int(dynamic_lambda)),
+              C.c_int(int(with_biases)), C.c_int(int(is_bias_last_row)))
+
+
+def initialize_biases(csc, csr, user_bias, item_bias, lam, dynamic_lambda, non_negative, calculate_global_bias,
+                      is_explicit, impl="oracle"):
+    """initialize_biases<T> (wrmf_utils.hpp:170-183).  csc = (ptr[n_item+1], idx(users), val) of the user x item
+    matrix, csr = (ptr[n_user+1], idx(items), val) of the same entries by user; val arrays (float64) are modified in
+    place for explicit feedback with calculate_global_bias.  Biases are filled in place; returns global_bias."""
+    cp, ci, cv = csc
+    rp, ri, rv = csr
+    n_items, n_users = len(cp) - 1, len(rp) - 1
+    assert user_bias.dtype == item_bias.dtype and len(user_bias) == n_users and len(item_bias) == n_items
+    sfx = "f32" if user_bias.dtype == np.float32 else "f64"
+    tail = (_p(user_bias), _p(item_bias), C.c_double(lam), C.c_int(int(dynamic_lambda)), C.c_int(int(non_negative)),
+            C.c_int(int(calculate_global_bias)), C.c_int(int(is_explicit)))
+    if impl == "oracle":
+        fn = getattr(lib(), "oracle_initialize_biases_" + sfx)
+        return fn(C.c_int(n_items), C.c_int(n_users), C.c_size_t(len(ci)), _p(cp), _p(ci), _p(cv), _p(rp), _p(ri),
+                  _p(rv), *tail)
+    fn = getattr(ref(), "ref_initialize_biases_" + sfx)
+    return fn(C.c_int(n_users), C.c_int(n_items), C.c_size_t(len(ci)), _p(ci), _p(cp), _p(cv), _p(ri), _p(rp), _p(rv),
+              *tail)

@@ -36,6 +36,20 @@ static double run_implicit(int n_rows, int n_cols, size_t nnz, int* ri, int* cp,
                                  initialize_bias_base != 0);
 }
 
+// initialize_biases<T> (wrmf_utils.hpp:170-183) as src/wrmf_init.cpp:6-34 calls it: csc = user x item matrix by
+// item column, csr = the same entries by user row (a CSC of the transpose); values may be modified in place.
+template <class T>
+static double run_init_biases(int n_users, int n_items, size_t nnz, int* csc_ri, int* csc_cp, double* csc_v,
+                              int* csr_ri, int* csr_cp, double* csr_v, T* user_bias, T* item_bias, double lambda,
+                              int dynamic_lambda, int non_negative, int calc_global, int is_explicit) {
+  dMappedCSC csc((arma::uword)n_users, (arma::uword)n_items, nnz, (arma::uword*)csc_ri, (arma::uword*)csc_cp, csc_v);
+  dMappedCSC csr((arma::uword)n_items, (arma::uword)n_users, nnz, (arma::uword*)csr_ri, (arma::uword*)csr_cp, csr_v);
+  arma::Col<T> ub(user_bias, (arma::uword)n_users, false, true);
+  arma::Col<T> ib(item_bias, (arma::uword)n_items, false, true);
+  return initialize_biases<T>(csc, csr, ub, ib, (T)lambda, dynamic_lambda != 0, non_negative != 0, calc_global != 0,
+                              is_explicit != 0);
+}
+
 #endif
 #ifdef REF_EXPLICIT
 template <class T>
@@ -75,6 +89,18 @@ double ref_als_implicit_f64(int n_rows, int n_cols, size_t nnz, int* ri, int* cp
   return run_implicit<double>(n_rows, n_cols, nnz, ri, cp, vals, X, k, n_src, Y, XtX, k_xtx, lambda,
                               n_threads, solver, cg_steps, with_biases, is_x_bias_last_row,
                               global_bias, gbb, gbb_len, initialize_bias_base);
+}
+double ref_initialize_biases_f32(int n_users, int n_items, size_t nnz, int* csc_ri, int* csc_cp, double* csc_v,
+                                 int* csr_ri, int* csr_cp, double* csr_v, float* user_bias, float* item_bias,
+                                 double lambda, int dynamic_lambda, int non_negative, int calc_global, int is_explicit) {
+  return run_init_biases<float>(n_users, n_items, nnz, csc_ri, csc_cp, csc_v, csr_ri, csr_cp, csr_v, user_bias,
+                                item_bias, lambda, dynamic_lambda, non_negative, calc_global, is_explicit);
+}
+double ref_initialize_biases_f64(int n_users, int n_items, size_t nnz, int* csc_ri, int* csc_cp, double* csc_v,
+                                 int* csr_ri, int* csr_cp, double* csr_v, double* user_bias, double* item_bias,
+                                 double lambda, int dynamic_lambda, int non_negative, int calc_global, int is_explicit) {
+  return run_init_biases<double>(n_users, n_items, nnz, csc_ri, csc_cp, csc_v, csr_ri, csr_cp, csr_v, user_bias,
+                                 item_bias, lambda, dynamic_lambda, non_negative, calc_global, is_explicit);
 }
 #endif
 #ifdef REF_EXPLICIT

@@ -6,9 +6,10 @@
 // A dependency-free C++17/OpenMP restatement of the reference's WRMF ALS half-iteration,
 // following the reference's loop structure line by line (citations relative to
 // /root/reference/):
-//   als_implicit<T>        inst/include/wrmf_implicit.hpp:90-305   (no-bias branches only)
+//   als_implicit<T>        inst/include/wrmf_implicit.hpp:90-305   (no-bias branches; als_implicit_bias: all branches)
 //   cg_solver_implicit<T>  inst/include/wrmf_implicit.hpp:8-32
-//   als_explicit<T>        inst/include/wrmf_explicit.hpp:33-174   (no-bias branches only)
+//   als_explicit<T>        inst/include/wrmf_explicit.hpp:33-174   (no-bias branches; als_explicit_bias: all branches)
+//   initialize_biases<T>   inst/include/wrmf_utils.hpp:32-183
 //   cg_solver_explicit<T>  inst/include/wrmf_explicit.hpp:8-31
 //   c_nnls / scd_ls_update inst/include/nnls.hpp:10-48
 //   XtX = tcrossprod(X)+lambda*I   R/model_WRMF.R:474-486
@@ -26,6 +27,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <limits>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -395,6 +397,313 @@ double als_explicit(int nc, size_t nnz_total, const int* col_ptrs, const int* ro
   return (double)(T)(loss / nnz_total);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Bias variants (with_user_item_bias / with_global_bias).  Kept apart from the hot no-bias functions
+// above (those are the timed CPU baseline).  Layout, wrmf_implicit.hpp:96-101 / wrmf_explicit.hpp:38-52:
+//   is_x_bias_last_row:  X = [1, ..., x_bias]   Y = [y_bias, ..., 1]
+//   otherwise:           X = [x_bias, ..., 1]   Y = [1, ..., y_bias]
+// `kf` = rows of X / Y (rank + 2 with biases), k = kf - with_biases = size of the solved system.
+struct BiasLayout {
+  int k, xo, xb, io, oo;
+  BiasLayout(int kf, bool with_biases, bool is_last) {
+    k = kf - (with_biases ? 1 : 0);
+    xo = (with_biases && !is_last) ? 1 : 0;   // drop_row(X_nnz, is_x_bias_last_row)      (:190 / :88)
+    xb = is_last ? kf - 1 : 0;                // x_biases = last / first row of X           (:116-119)
+    io = (with_biases && is_last) ? 1 : 0;    // init = drop_row(init, !is_x_bias_last_row) (:191 / :90) -- sic
+    oo = (with_biases && !is_last) ? 1 : 0;   // Y.head(rank-1) / Y.tail(rank-1)            (:246-252)
+  }
+};
+
+// cg_solver_implicit_global_bias (:35-60) and cg_solver_implicit_user_item_bias (:62-88) in one body:
+//   r = X_nnz (c - (c-1) % (X_nnz' x + x_biases + global_bias)) - XtX x + rhs_init
+template <class T>
+void cg_solver_implicit_bias(const T* Xn, const T* conf, const T* conf1, const T* xbn, T gbias, const T* rhs_init,
+                             T* x, int n_iter, const T* XtX, int k, int n, Scratch<T>& s) {
+  T* r = s.r.data(); T* p = s.p.data(); T* Ap = s.Ap.data(); T* u = s.u.data(); T* w = s.w.data();
+  gemv_t(Xn, x, u, k, n);
+  for (int j = 0; j < n; j++) w[j] = conf[j] - conf1[j] * ((xbn ? u[j] + xbn[j] : u[j]) + gbias);
+  gemv_n(Xn, w, r, k, n, false);
+  symv(XtX, x, Ap, k);
+  for (int i = 0; i < k; i++) { r[i] = r[i] - Ap[i] + rhs_init[i]; p[i] = r[i]; }
+  double rsold, rsnew, alpha;
+  rsold = dotT(r, r, k);
+  for (int it = 0; it < n_iter; it++) {
+    symv(XtX, p, Ap, k);
+    gemv_t(Xn, p, u, k, n);
+    for (int j = 0; j < n; j++) w[j] = conf1[j] * u[j];
+    gemv_n(Xn, w, Ap, k, n, true);
+    alpha = rsold / dotT(p, Ap, k);
+    const T a = (T)alpha;
+    for (int i = 0; i < k; i++) { x[i] += a * p[i]; r[i] -= a * Ap[i]; }
+    rsnew = dotT(r, r, k);
+    if (rsnew < CG_TOL) break;
+    const T b = (T)(rsnew / rsold);
+    for (int i = 0; i < k; i++) p[i] = r[i] + p[i] * b;
+    rsold = rsnew;
+  }
+}
+
+// als_implicit<T> with with_biases and/or global_bias (wrmf_implicit.hpp:90-305, all branches).
+// Deviation, on purpose: the reference's CONJUGATE_GRADIENT + with_biases branch drops a row of `init` twice
+// (:191 and :199) and fails with a dimension error; here `init` is dropped once, like for the other solvers.
+template <class T>
+double als_implicit_bias(int nc, size_t nnz_total, const int* col_ptrs, const int* row_indices, const double* values,
+                         const T* X, int kf, int n_src, T* Y, const T* XtX, double lambda, int n_threads, int solver,
+                         int cg_steps, bool with_biases, bool is_last, double global_bias, T* global_bias_base,
+                         bool initialize_bias_base) {
+  const BiasLayout L(kf, with_biases, is_last);
+  const int k = L.k;
+  if (global_bias < std::sqrt(std::numeric_limits<T>::epsilon())) global_bias = 0;          // (:108-109)
+  std::vector<T> rhs_init(k, T(0));
+  if (global_bias && initialize_bias_base && !with_biases) {                                // (:111-112)
+    for (int f = 0; f < k; f++) {
+      T acc = T(0);
+      for (int j = 0; j < n_src; j++) acc += X[(size_t)j * kf + f];
+      global_bias_base[f] = acc * (T)(-global_bias);
+    }
+  }
+  if (with_biases) {                                                                        // (:114-154)
+    for (int j = 0; j < n_src; j++) {
+      const T* xj = X + (size_t)j * kf;
+      const T w = global_bias ? (T)(xj[L.xb] + (T)global_bias) : xj[L.xb];
+      for (int f = 0; f < k; f++) rhs_init[f] += xj[L.xo + f] * w;
+    }
+    for (int f = 0; f < k; f++) rhs_init[f] = -rhs_init[f];
+  } else if (global_bias) {
+    for (int f = 0; f < k; f++) rhs_init[f] = global_bias_base[f];                          // (:155-157)
+  }
+  const T gb = (T)global_bias;
+  double loss = 0;
+#pragma omp parallel num_threads(n_threads)
+  {
+    Scratch<T> s;
+    std::vector<T> spare, xbn;
+#pragma omp for schedule(dynamic) reduction(+ : loss)
+    for (int i = 0; i < nc; i++) {
+      const int p1 = col_ptrs[i], p2 = col_ptrs[i + 1];
+      T* y = Y + (size_t)i * kf;
+      if (with_biases || global_bias || p1 < p2) {                                          // (:179)
+        const int n = p2 - p1;
+        s.size(k, n > 0 ? n : 1);
+        xbn.resize(n > 0 ? n : 1);
+        T* Xn = s.Xn.data(); T* conf = s.conf.data(); T* conf1 = s.conf1.data();
+        for (int j = 0; j < n; j++) {
+          const T* xj = X + (size_t)row_indices[p1 + j] * kf;
+          conf[j] = (T)values[p1 + j];
+          conf1[j] = conf[j] - T(1.0);
+          xbn[j] = with_biases ? xj[L.xb] : T(0);
+          std::memcpy(Xn + (size_t)j * k, xj + L.xo, sizeof(T) * k);
+        }
+        T* ynew = s.x.data();
+        std::memcpy(ynew, y + L.io, sizeof(T) * k);
+        if (solver == CONJUGATE_GRADIENT) {
+          cg_solver_implicit_bias<T>(Xn, conf, conf1, with_biases ? xbn.data() : nullptr, gb, rhs_init.data(), ynew,
+                                     cg_steps, XtX, k, n, s);                               // (:200-205)
+        } else {
+          T* lhs = s.lhs.data(); T* rhs = s.rhs.data();
+          std::memcpy(lhs, XtX, sizeof(T) * (size_t)k * k);
+          weighted_gram(Xn, conf1, lhs, k, n);                                              // (:207-208)
+          T* w = s.w.data();
+          if (with_biases) {
+            for (int j = 0; j < n; j++) w[j] = conf[j] - xbn[j] * conf1[j];                  // (:226)
+          } else {
+            for (int j = 0; j < n; j++) w[j] = conf[j];                                     // (:229)
+          }
+          gemv_n(Xn, w, rhs, k, n, false);
+          for (int f = 0; f < k; f++) rhs[f] += rhs_init[f];
+          if (solver == SEQ_COORDINATE_WISE_NNLS) {
+            c_nnls<T>(lhs, rhs, ynew, k, s);
+          } else {
+            sympd_solve(lhs, rhs, k, spare);
+            std::memcpy(ynew, rhs, sizeof(T) * k);
+          }
+        }
+        std::memcpy(y + L.oo, ynew, sizeof(T) * k);                                         // (:240-255)
+        T acc = T(0);                                                                       // (:257-270)
+        if (p1 < p2) {
+          T* u = s.u.data();
+          gemv_t(Xn, ynew, u, k, n);
+          const T one_g = (T)(1 - global_bias);
+          for (int j = 0; j < n; j++) { const T d = one_g - u[j] - xbn[j]; acc += d * d * conf[j]; }
+        }
+        loss += acc + lambda * dotT(ynew, ynew, k);
+      } else {
+        for (int c = 0; c < k; c++) y[L.oo + c] = T(0);                                     // (:272-282)
+      }
+    }
+  }
+  if (lambda > 0) {                                                                         // (:286-302)
+    // with biases: every learned row of X, i.e. all but the row of ones (first row when is_x_bias_last_row)
+    const int lo = with_biases ? (is_last ? 1 : 0) : 0, hi = with_biases ? (is_last ? kf : kf - 1) : kf;
+    T acc = T(0);
+    for (int j = 0; j < n_src; j++)
+      for (int f = lo; f < hi; f++) acc += X[(size_t)j * kf + f] * X[(size_t)j * kf + f];
+    loss += lambda * acc;
+  }
+  return (double)(T)(loss / nnz_total);
+}
+
+// als_explicit<T> with with_biases (wrmf_explicit.hpp:33-174, all branches).
+template <class T>
+double als_explicit_bias(int nc, size_t nnz_total, const int* col_ptrs, const int* row_indices, const double* values,
+                         const T* X, int kf, int n_src, T* Y, const T* cnt_X, double lambda, int n_threads, int solver,
+                         int cg_steps, bool dynamic_lambda, bool with_biases, bool is_last) {
+  const BiasLayout L(kf, with_biases, is_last);
+  const int k = L.k;
+  double loss = 0;
+#pragma omp parallel num_threads(n_threads)
+  {
+    Scratch<T> s;
+    std::vector<T> spare;
+#pragma omp for schedule(dynamic, GRAIN_SIZE) reduction(+ : loss)
+    for (int i = 0; i < nc; i++) {
+      const int p1 = col_ptrs[i], p2 = col_ptrs[i + 1];
+      T* y = Y + (size_t)i * kf;
+      if (p1 < p2) {
+        const int n = p2 - p1;
+        s.size(k, n);
+        const T lambda_use = (T)(lambda * (dynamic_lambda ? static_cast<T>(p2 - p1) : 1.));
+        T* Xn = s.Xn.data(); T* conf = s.conf.data();
+        for (int j = 0; j < n; j++) {
+          const T* xj = X + (size_t)row_indices[p1 + j] * kf;
+          conf[j] = (T)values[p1 + j];
+          if (with_biases) conf[j] -= xj[L.xb];                                             // (:89)
+          std::memcpy(Xn + (size_t)j * k, xj + L.xo, sizeof(T) * k);
+        }
+        T* ynew = s.x.data();
+        std::memcpy(ynew, y + L.io, sizeof(T) * k);                                         // (:90)
+        if (solver == CONJUGATE_GRADIENT) {
+          cg_solver_explicit<T>(Xn, conf, ynew, lambda_use, cg_steps, k, n, s);
+        } else {
+          T* lhs = s.lhs.data(); T* rhs = s.rhs.data();
+          std::fill(lhs, lhs + (size_t)k * k, T(0));
+          std::vector<T>& ones = s.w;
+          for (int j = 0; j < n; j++) ones[j] = T(1);
+          weighted_gram(Xn, ones.data(), lhs, k, n);
+          for (int c = 0; c < k; c++) lhs[(size_t)c * k + c] += lambda_use;
+          gemv_n(Xn, conf, rhs, k, n, false);
+          if (solver == CHOLESKY) {
+            sympd_solve(lhs, rhs, k, spare);
+            std::memcpy(ynew, rhs, sizeof(T) * k);
+          } else {
+            c_nnls<T>(lhs, rhs, ynew, k, s);
+          }
+        }
+        std::memcpy(y + L.oo, ynew, sizeof(T) * k);                                         // (:115-129)
+        T* u = s.u.data();
+        gemv_t(Xn, ynew, u, k, n);
+        T acc = T(0);
+        for (int j = 0; j < n; j++) { const T d = conf[j] - u[j]; acc += d * d; }
+        loss += acc + lambda_use * dotT(ynew, ynew, k);
+      } else {
+        for (int c = 0; c < k; c++) y[L.oo + c] = T(0);                                     // (:134-145)
+      }
+    }
+  }
+  if (lambda > 0) {                                                                         // (:148-172)
+    const int lo = with_biases ? (is_last ? 1 : 0) : 0, hi = with_biases ? (is_last ? kf : kf - 1) : kf;
+    T acc = T(0);
+    for (int j = 0; j < n_src; j++) {
+      const T c = dynamic_lambda ? cnt_X[j] : T(1);
+      for (int f = lo; f < hi; f++) acc += X[(size_t)j * kf + f] * X[(size_t)j * kf + f] * c;
+    }
+    loss += lambda * acc;
+  }
+  return (double)(T)(loss / nnz_total);
+}
+
+// initialize_biases_explicit (wrmf_utils.hpp:32-82): csc = users x items by item column, csr = the same entries
+// by user; `csc_val` / `csr_val` are modified in place when calculate_global_bias.
+template <class T>
+double initialize_biases_explicit(int n_items, int n_users, size_t nnz, const int* cp, const int* ci, double* cv,
+                                  const int* rp, const int* ri, double* rv, T* user_bias, T* item_bias, T lambda,
+                                  bool dynamic_lambda, bool non_negative, bool calculate_global_bias) {
+  double global_bias = 0;
+  if (calculate_global_bias) {
+    for (size_t ix = 0; ix < nnz; ix++) global_bias += (cv[ix] - global_bias) / (double)(ix + 1);
+    for (size_t ix = 0; ix < nnz; ix++) { cv[ix] -= global_bias; rv[ix] -= global_bias; }
+  }
+  for (int iter = 0; iter < 5; iter++) {
+    for (int col = 0; col < n_items; col++) {
+      item_bias[col] = 0;
+      const T lambda_use = lambda * (dynamic_lambda ? static_cast<T>(cp[col + 1] - cp[col]) : 1.);
+      for (int ix = cp[col]; ix < cp[col + 1]; ix++) item_bias[col] += cv[ix] - user_bias[ci[ix]];
+      item_bias[col] /= lambda_use + static_cast<T>(cp[col + 1] - cp[col]);
+      if (non_negative) item_bias[col] = std::fmax((T)0, item_bias[col]);
+    }
+    for (int row = 0; row < n_users; row++) {
+      user_bias[row] = 0;
+      const T lambda_use = lambda * (dynamic_lambda ? static_cast<T>(rp[row + 1] - rp[row]) : 1.);
+      for (int ix = rp[row]; ix < rp[row + 1]; ix++) user_bias[row] += rv[ix] - item_bias[ri[ix]];
+      user_bias[row] /= lambda_use + static_cast<T>(rp[row + 1] - rp[row]);
+      if (non_negative) user_bias[row] = std::fmax((T)0, user_bias[row]);
+    }
+  }
+  return global_bias;
+}
+
+// initialize_biases_implicit (wrmf_utils.hpp:84-167)
+template <class T>
+double initialize_biases_implicit(int n_items, int n_users, size_t nnz, const int* cp, const int* ci, const double* cv,
+                                  const int* rp, const int* ri, const double* rv, T* user_bias, T* item_bias, T lambda,
+                                  bool calculate_global_bias, bool non_negative) {
+  double global_bias = 0;
+  if (calculate_global_bias) {                                                              // Kahan sum (:12-30)
+    long double err = 0., res = 0.;
+    for (size_t ix = 0; ix < nnz; ix++) {
+      const long double diff = rv[ix] - err, temp = res + diff;
+      err = (temp - res) - diff;
+      res = temp;
+    }
+    global_bias = res / (res + (long double)n_items * (long double)n_users - (long double)nnz);
+  }
+  if (non_negative) global_bias = std::fmax(0., global_bias);
+  std::vector<double> um(n_users), im(n_items), ua(n_users), ia(n_items);
+  auto means = [&](int n_rows, int n_other, const int* p, const double* v, std::vector<double>& m, std::vector<double>& a) {
+    for (int row = 0; row < n_rows; row++) {
+      const int cnt = p[row + 1] - p[row];
+      if (cnt > 0) {
+        for (int ix = p[row]; ix < p[row + 1]; ix++) a[row] += v[ix];
+        m[row] = a[row] / (a[row] + (double)(n_other - cnt));
+        a[row] += (double)(n_other - cnt);
+        a[row] /= a[row] + lambda;
+      } else {
+        m[row] = 0;
+        a[row] = (double)n_other / ((double)n_other + lambda);
+      }
+    }
+  };
+  means(n_users, n_items, rp, rv, um, ua);
+  means(n_items, n_users, cp, cv, im, ia);
+  double bias_mean, bias_this, wsum;
+  for (int iter = 0; iter < 5; iter++) {
+    bias_mean = 0;
+    if (iter > 0)
+      for (int row = 0; row < n_users; row++) bias_mean += (user_bias[row] - bias_mean) / (T)(row + 1);
+    for (int col = 0; col < n_items; col++) {
+      wsum = n_users;
+      bias_this = bias_mean;
+      for (int ix = cp[col]; ix < cp[col + 1]; ix++)
+        bias_this += ((cv[ix] - 1) * (user_bias[ci[ix]] - bias_this)) / (wsum += (cv[ix] - 1));
+      item_bias[col] = (im[col] - bias_this - global_bias) * ia[col];
+    }
+    if (non_negative)
+      for (int col = 0; col < n_items; col++) item_bias[col] = std::fmax((T)0, item_bias[col]);
+    bias_mean = 0;
+    for (int col = 0; col < n_items; col++) bias_mean += (item_bias[col] - bias_mean) / (T)(col + 1);
+    for (int row = 0; row < n_users; row++) {
+      wsum = n_items;
+      bias_this = bias_mean;
+      for (int ix = rp[row]; ix < rp[row + 1]; ix++)
+        bias_this += ((rv[ix] - 1) * (item_bias[ri[ix]] - bias_this)) / (wsum += (rv[ix] - 1));
+      user_bias[row] = (um[row] - bias_this - global_bias) * ua[row];
+    }
+    if (non_negative)
+      for (int row = 0; row < n_users; row++) user_bias[row] = std::fmax((T)0, user_bias[row]);
+  }
+  return global_bias;
+}
+
 // XtX = tcrossprod(X) + diag(lambda)   (R/model_WRMF.R:474-486); BLAS syrk/gemm in R.
 template <class T>
 void gram(const T* X, int k, int n_src, double lambda, T* XtX, int n_threads) {
@@ -466,5 +775,32 @@ void oracle_gram_f32(const float* X, int k, int n_src, double lambda, float* XtX
 void oracle_gram_f64(const double* X, int k, int n_src, double lambda, double* XtX, int n_threads) {
   gram<double>(X, k, n_src, lambda, XtX, n_threads);
 }
+
+#define ORACLE_BIAS_EXPORTS(T, SFX)                                                                                    \
+  double oracle_als_implicit_bias_##SFX(int nc, size_t nnz, const int* p, const int* idx, const double* v, const T* X,  \
+                                        int kf, int n_src, T* Y, const T* XtX, double lambda, int n_threads,           \
+                                        int solver, int cg_steps, int with_biases, int is_last, double global_bias,    \
+                                        T* gbb, int init_base) {                                                       \
+    return als_implicit_bias<T>(nc, nnz, p, idx, v, X, kf, n_src, Y, XtX, lambda, n_threads, solver, cg_steps,         \
+                                with_biases != 0, is_last != 0, global_bias, gbb, init_base != 0);                     \
+  }                                                                                                                    \
+  double oracle_als_explicit_bias_##SFX(int nc, size_t nnz, const int* p, const int* idx, const double* v, const T* X,  \
+                                        int kf, int n_src, T* Y, const T* cnt_X, double lambda, int n_threads,         \
+                                        int solver, int cg_steps, int dynamic_lambda, int with_biases, int is_last) {  \
+    return als_explicit_bias<T>(nc, nnz, p, idx, v, X, kf, n_src, Y, cnt_X, lambda, n_threads, solver, cg_steps,       \
+                                dynamic_lambda != 0, with_biases != 0, is_last != 0);                                  \
+  }                                                                                                                    \
+  double oracle_initialize_biases_##SFX(int n_items, int n_users, size_t nnz, const int* cp, const int* ci, double* cv, \
+                                        const int* rp, const int* ri, double* rv, T* user_bias, T* item_bias,          \
+                                        double lambda, int dynamic_lambda, int non_negative, int calc_global,          \
+                                        int is_explicit) {                                                             \
+    if (is_explicit)                                                                                                   \
+      return initialize_biases_explicit<T>(n_items, n_users, nnz, cp, ci, cv, rp, ri, rv, user_bias, item_bias,        \
+                                           (T)lambda, dynamic_lambda != 0, non_negative != 0, calc_global != 0);       \
+    return initialize_biases_implicit<T>(n_items, n_users, nnz, cp, ci, cv, rp, ri, rv, user_bias, item_bias,          \
+                                         (T)lambda, calc_global != 0, non_negative != 0);                              \
+  }
+ORACLE_BIAS_EXPORTS(float, f32)
+ORACLE_BIAS_EXPORTS(double, f64)
 
 }  // extern "C"

@@ -13,6 +13,7 @@
 #include <R.h>
 #include <Rinternals.h>
 #include <R_ext/Rdynload.h>
+#include <string.h>
 
 #include "b200als.h"
 
@@ -43,6 +44,16 @@ static float* float32_vector_or_null(SEXP s4) {
   SEXP d = R_do_slot(s4, Rf_install("Data"));
   return XLENGTH(d) ? (float*)INTEGER(d) : NULL;
 }
+/* global_bias_base: R sizes it rank-1 (R/model_WRMF.R:291-297) while als_implicit<T> reads and writes `rank` entries
+ * (inst/include/wrmf_implicit.hpp:111-112, :155-157).  The engine takes the length the C++ code uses, so a shorter R
+ * vector is staged through a buffer of the right length (zero padded) and copied back as far as it goes. */
+static void* stage_bias_base(void* r_data, R_xlen_t r_len, int need, size_t elem) {
+  if (r_len >= need) return r_data;
+  char* buf = R_alloc((size_t)need, (int)elem);
+  memset(buf, 0, (size_t)need * elem);
+  if (r_len > 0) memcpy(buf, r_data, (size_t)r_len * elem);
+  return buf;
+}
 static void check(int rc) {
   if (rc != B200ALS_OK) Rf_error("b200als: %s (status %d)", b200als_last_error(), rc);
 }
@@ -57,11 +68,14 @@ SEXP _rsparse_als_implicit_float(SEXP m_csc_r, SEXP X_, SEXP Y_, SEXP XtX_, SEXP
   float* Y = float32_matrix(Y_, NULL, NULL); /* updated in place, like arma's aliasing fmat */
   float* XtX = float32_matrix(XtX_, &kx, NULL);
   double loss = 0.0;
+  SEXP gd = R_do_slot(global_bias_base_, Rf_install("Data"));
+  float* base_r = float32_vector_or_null(global_bias_base_);
+  float* base = (float*)stage_bias_base(base_r, XLENGTH(gd), k, sizeof(float));
   check(b200als_als_implicit_float(&A, k, X, Y, XtX, Rf_asReal(lambda), Rf_asInteger(n_threads),
                                    (unsigned)Rf_asInteger(solver), (unsigned)Rf_asInteger(cg_steps),
                                    Rf_asLogical(with_biases), Rf_asLogical(is_x_bias_last_row),
-                                   Rf_asReal(global_bias), float32_vector_or_null(global_bias_base_),
-                                   Rf_asLogical(initialize_bias_base), &loss));
+                                   Rf_asReal(global_bias), base, Rf_asLogical(initialize_bias_base), &loss));
+  if (base != base_r && XLENGTH(gd) > 0) memcpy(base_r, base, (size_t)XLENGTH(gd) * sizeof(float));
   return Rf_ScalarReal(loss);
 }
 
@@ -71,12 +85,15 @@ SEXP _rsparse_als_implicit_double(SEXP m_csc_r, SEXP X, SEXP Y, SEXP XtX, SEXP l
   b200als_csc A;
   csc_from_s4(m_csc_r, &A);
   double loss = 0.0;
+  double* base_r = XLENGTH(global_bias_base) ? REAL(global_bias_base) : NULL;
+  double* base = (double*)stage_bias_base(base_r, XLENGTH(global_bias_base), Rf_nrows(X), sizeof(double));
   check(b200als_als_implicit_double(&A, Rf_nrows(X), REAL(X), REAL(Y), REAL(XtX), Rf_asReal(lambda),
                                     Rf_asInteger(n_threads), (unsigned)Rf_asInteger(solver),
                                     (unsigned)Rf_asInteger(cg_steps), Rf_asLogical(with_biases),
-                                    Rf_asLogical(is_x_bias_last_row), Rf_asReal(global_bias),
-                                    XLENGTH(global_bias_base) ? REAL(global_bias_base) : NULL,
+                                    Rf_asLogical(is_x_bias_last_row), Rf_asReal(global_bias), base,
                                     Rf_asLogical(initialize_bias_base), &loss));
+  if (base != base_r && XLENGTH(global_bias_base) > 0)
+    memcpy(base_r, base, (size_t)XLENGTH(global_bias_base) * sizeof(double));
   return Rf_ScalarReal(loss);
 }
 
@@ -159,11 +176,44 @@ SEXP b200als_R_transform(SEXP ptr, SEXP fl_out) {
   return Rf_ScalarReal(loss);
 }
 
+/* initialize_biases_{double,float} (src/wrmf_init.cpp:6-34; R stubs R/RcppExports.R, caller R/model_WRMF.R:150-155):
+ * m_csc_r = c_ui (user x item, dgCMatrix), m_csr_r = c_iu = t_shallow(csr(c_ui)), i.e. the same entries by user.
+ * The @x slots are modified in place for explicit feedback with calculate_global_bias, as in the reference. */
+SEXP _rsparse_initialize_biases_double(SEXP m_csc_r, SEXP m_csr_r, SEXP user_bias, SEXP item_bias, SEXP lambda,
+                                       SEXP dynamic_lambda, SEXP non_negative, SEXP calculate_global_bias,
+                                       SEXP is_explicit_feedback) {
+  b200als_csc C, R_;
+  csc_from_s4(m_csc_r, &C);
+  csc_from_s4(m_csr_r, &R_);
+  double g = 0.0;
+  check(b200als_initialize_biases_double(R_.n_cols, C.n_cols, C.nnz, C.ptr, C.idx, (double*)C.val_f64, R_.ptr, R_.idx,
+                                         (double*)R_.val_f64, REAL(user_bias), REAL(item_bias), Rf_asReal(lambda),
+                                         Rf_asLogical(dynamic_lambda), Rf_asLogical(non_negative),
+                                         Rf_asLogical(calculate_global_bias), Rf_asLogical(is_explicit_feedback), &g));
+  return Rf_ScalarReal(g);
+}
+SEXP _rsparse_initialize_biases_float(SEXP m_csc_r, SEXP m_csr_r, SEXP user_bias, SEXP item_bias, SEXP lambda,
+                                      SEXP dynamic_lambda, SEXP non_negative, SEXP calculate_global_bias,
+                                      SEXP is_explicit_feedback) {
+  b200als_csc C, R_;
+  csc_from_s4(m_csc_r, &C);
+  csc_from_s4(m_csr_r, &R_);
+  double g = 0.0;
+  check(b200als_initialize_biases_float(R_.n_cols, C.n_cols, C.nnz, C.ptr, C.idx, (double*)C.val_f64, R_.ptr, R_.idx,
+                                        (double*)R_.val_f64, float32_matrix(user_bias, NULL, NULL),
+                                        float32_matrix(item_bias, NULL, NULL), Rf_asReal(lambda),
+                                        Rf_asLogical(dynamic_lambda), Rf_asLogical(non_negative),
+                                        Rf_asLogical(calculate_global_bias), Rf_asLogical(is_explicit_feedback), &g));
+  return Rf_ScalarReal(g);
+}
+
 static const R_CallMethodDef CallEntries[] = {
     {"_rsparse_als_implicit_float", (DL_FUNC)&_rsparse_als_implicit_float, 13},
     {"_rsparse_als_implicit_double", (DL_FUNC)&_rsparse_als_implicit_double, 13},
     {"_rsparse_als_explicit_float", (DL_FUNC)&_rsparse_als_explicit_float, 11},
     {"_rsparse_als_explicit_double", (DL_FUNC)&_rsparse_als_explicit_double, 11},
+    {"_rsparse_initialize_biases_double", (DL_FUNC)&_rsparse_initialize_biases_double, 9},
+    {"_rsparse_initialize_biases_float", (DL_FUNC)&_rsparse_initialize_biases_float, 9},
     {"b200als_R_create", (DL_FUNC)&b200als_R_create, 8},
     {"b200als_R_set_factors", (DL_FUNC)&b200als_R_set_factors, 3},
     {"b200als_R_get_factors", (DL_FUNC)&b200als_R_get_factors, 3},

@@ -44,6 +44,10 @@ _PROTOS = {
     "b200als_timer_start": (C.c_int, []),
     "b200als_timer_stop": (C.c_int, [C.POINTER(C.c_float)]),
     "b200als_launch_count": (C.c_ulonglong, []),
+    "b200als_initialize_biases_float": (C.c_int, [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 8 +
+                                        [C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "b200als_initialize_biases_double": (C.c_int, [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 8 +
+                                         [C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "b200als_als_implicit_float": (C.c_int, [C.POINTER(Csc), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                              C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_double, C.c_void_p,
                                              C.c_int, C.POINTER(C.c_double)]),

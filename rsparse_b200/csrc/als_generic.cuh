@@ -39,6 +39,13 @@ struct SolveParams {
   unsigned long long* ticket;
   double* loss_partials;  // [gridDim.x]
   int* status;            // != 0: some system was not positive definite
+  // ---- bias terms (with_user_item_bias / with_global_bias).  The engine hands these kernels *compact* matrices:
+  // X without its bias row, Y = the rows being solved, both k wide (see engine.cu, BiasPlan) ----
+  const T* xbias;         // [n_src] x_biases (wrmf_implicit.hpp:115-119, wrmf_explicit.hpp:58-63) or nullptr
+  const T* rhs_init;      // [k] implicit only: rhs_init (wrmf_implicit.hpp:143-157) or nullptr
+  T gbias;                // global_bias (implicit), 0 when unused
+  T one_minus_g;          // (T)(1 - global_bias): the target of the implicit loss (wrmf_implicit.hpp:259-270)
+  int solve_empty;        // implicit with biases / global bias: rows without entries are solved too (:179)
 };
 
 enum PassMode { kR0Implicit = 0, kApImplicit = 1, kR0Explicit = 2, kApExplicit = 3, kLossImplicit = 4, kLossExplicit = 5 };
@@ -57,19 +64,21 @@ __device__ __forceinline__ T fused_pass(const SolveParams<T>& P, int p1, int n, 
   for (int base = 0; base < n; base += 32) {
     const int cnt = min(32, n - base);
     int my_idx = 0;
-    T my_c = T(0);
+    T my_c = T(0), my_b = T(0);
     if (lane < cnt) {
       my_idx = __ldg(P.idx + p1 + base + lane);
       my_c = __ldg(P.val + p1 + base + lane);
+      if (P.xbias) my_b = __ldg(P.xbias + my_idx);
     }
     for (int q = 0; q < cnt; q += 4) {
       T xr[4][KPL];
-      T cj[4];
+      T cj[4], bj[4];
       bool ok[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         const int j = __shfl_sync(kFull, my_idx, q + u);
         cj[u] = __shfl_sync(kFull, my_c, q + u);
+        bj[u] = __shfl_sync(kFull, my_b, q + u);
         ok[u] = (q + u) < cnt;
         const T* xj = P.X + (size_t)j * k;
 #pragma unroll
@@ -86,12 +95,13 @@ __device__ __forceinline__ T fused_pass(const SolveParams<T>& P, int p1, int n, 
         d = warp_sum(d);
         T w;
         switch (mode) {
-          case kR0Implicit: w = cj[u] - (cj[u] - T(1)) * d; break;
+          // bj = gbias = 0 without bias terms: adding them is exact, the plain formulas of :16 / :15 result
+          case kR0Implicit: w = cj[u] - (cj[u] - T(1)) * ((d + bj[u]) + P.gbias); break;   // wrmf_implicit.hpp:46,72
           case kApImplicit: w = (cj[u] - T(1)) * d; break;
-          case kR0Explicit: w = cj[u] - d; break;
+          case kR0Explicit: w = (cj[u] - bj[u]) - d; break;                                // wrmf_explicit.hpp:89
           case kApExplicit: w = d; break;
-          case kLossImplicit: { const T t = T(1) - d; w = T(0); if (ok[u]) loss += t * t * cj[u]; } break;
-          default: { const T t = cj[u] - d; w = T(0); if (ok[u]) loss += t * t; } break;
+          case kLossImplicit: { const T t = (P.one_minus_g - d) - bj[u]; w = T(0); if (ok[u]) loss += t * t * cj[u]; } break;
+          default: { const T t = (cj[u] - bj[u]) - d; w = T(0); if (ok[u]) loss += t * t; } break;
         }
         if (!ok[u]) w = T(0);
 #pragma unroll
@@ -148,7 +158,7 @@ __global__ void __launch_bounds__(256) als_cg_generic_kernel(SolveParams<T> P) {
     const int row = P.row_list ? P.row_list[t] : (int)t + P.row_begin;
     const int p1 = P.ptr[row] - P.ptr_base, p2 = P.ptr[row + 1] - P.ptr_base;
     T* y = P.Y + (size_t)row * k;
-    if (p1 >= p2) {  // wrmf_implicit.hpp:281 / wrmf_explicit.hpp:144
+    if (p1 >= p2 && !P.solve_empty) {  // wrmf_implicit.hpp:281 / wrmf_explicit.hpp:144
 #pragma unroll
       for (int e = 0; e < KPL; e++) {
         const int f = e * 32 + lane;
@@ -171,7 +181,11 @@ __global__ void __launch_bounds__(256) als_cg_generic_kernel(SolveParams<T> P) {
     if (implicit) {
       gemv_sym<T, KPL>(P.G, k, x, Ap);
 #pragma unroll
-      for (int e = 0; e < KPL; e++) r[e] = acc[e] - Ap[e];
+      for (int e = 0; e < KPL; e++) {
+        r[e] = acc[e] - Ap[e];
+        const int f = e * 32 + lane;
+        if (P.rhs_init && f < k) r[e] += __ldg(P.rhs_init + f);   // + rhs_init / global_bias_base (:47, :73)
+      }
     } else {
 #pragma unroll
       for (int e = 0; e < KPL; e++) r[e] = acc[e] - lam_use * x[e];
@@ -263,17 +277,18 @@ __global__ void __launch_bounds__(256) als_chol_generic_kernel(SolveParams<T> P)
     if (row < 0) break;
     const int p1 = P.ptr[row] - P.ptr_base, p2 = P.ptr[row + 1] - P.ptr_base;
     T* y = P.Y + (size_t)row * k;
-    if (p1 >= p2) {
+    if (p1 >= p2 && !P.solve_empty) {
       for (int f = tid; f < k; f += 256) y[f] = T(0);
       continue;
     }
-    const int n = p2 - p1;
+    const int n = max(p2 - p1, 0);
     const T lam_use = implicit ? T(0) : (T)(P.lambda * (P.dynamic_lambda ? (double)static_cast<T>(n) : 1.));
     // lhs = XtX (already + lambda I)      wrmf_implicit.hpp:207 ; or lambda_use I   wrmf_explicit.hpp:103-104
     for (int a = ty; a <= k; a += 16)
       for (int b = tx; b < k; b += 16) {
         T v = T(0);
         if (a < k && b <= a) v = implicit ? __ldg(P.G + (size_t)a * k + b) : ((a == b) ? lam_use : T(0));
+        if (a == k && P.rhs_init) v = __ldg(P.rhs_init + b);   // rhs = rhs_init + ...   (wrmf_implicit.hpp:226,229)
         A[a * ks + b] = v;
       }
     __syncthreads();
@@ -285,7 +300,9 @@ __global__ void __launch_bounds__(256) als_chol_generic_kernel(SolveParams<T> P)
       }
       if (tid < cnt) {
         const T c = __ldg(P.val + p1 + base + tid);
-        cs[tid] = c;
+        const T bj = P.xbias ? __ldg(P.xbias + __ldg(P.idx + p1 + base + tid)) : T(0);
+        // rhs weights: X_nnz c (:231) ; with biases X_nnz (c - x_biases % (c - 1)) (:226) ; explicit c - x_biases (:89)
+        cs[tid] = implicit ? (P.xbias ? c - bj * (c - T(1)) : c) : (c - bj);
         wts[tid] = implicit ? (c - T(1)) : T(1);
       }
       __syncthreads();
@@ -385,12 +402,14 @@ __global__ void __launch_bounds__(256) als_chol_generic_kernel(SolveParams<T> P)
     // loss: warp per gathered row
     T l = T(0);
     for (int j = warp_id(); j < n; j += 8) {
-      const T* xj = P.X + (size_t)__ldg(P.idx + p1 + j) * k;
+      const int src = __ldg(P.idx + p1 + j);
+      const T* xj = P.X + (size_t)src * k;
       T d = T(0);
       for (int f = lane_id(); f < k; f += 32) d += __ldg(xj + f) * colj[f];
       d = warp_sum(d);
       const T c = __ldg(P.val + p1 + j);
-      const T t = implicit ? (T(1) - d) : (c - d);
+      const T bj = P.xbias ? __ldg(P.xbias + src) : T(0);
+      const T t = implicit ? ((P.one_minus_g - d) - bj) : ((c - bj) - d);
       if (lane_id() == 0) l += implicit ? t * t * c : t * t;
     }
     if (warp_id() == 0) {

@@ -15,6 +15,8 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <limits>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/b200als.h"
@@ -26,6 +28,7 @@
 #include "gram_tc.cuh"
 #include "rotate_tc.cuh"
 #include "topk.cuh"
+#include "bias_init.cuh"
 
 using namespace b200als;
 
@@ -144,6 +147,75 @@ __global__ void zero_empty_rows_kernel(const int32_t* __restrict__ ptr, int n_ro
   if (e >= (long long)n_rows * k) return;
   const int r = (int)(e / k);
   if (ptr[r + 1] - ptr[r] <= 0) Y[e] = T(0);
+}
+
+// ---- bias layouts (with_user_item_bias): X / Y carry rank+2 rows, the solve sees rank+1 of them -----------------------
+// dst[r][0..k) = src[r][off .. off+k)   (drop_row, wrmf_utils.hpp:3-10, on the device)
+template <typename T>
+__global__ void pack_cols_kernel(const T* __restrict__ src, int ld, int off, int k, long long n, T* __restrict__ dst) {
+  const long long total = n * (long long)k;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / k;
+    const int f = (int)(e - r * k);
+    dst[e] = src[r * ld + off + f];
+  }
+}
+template <typename T>
+__global__ void unpack_cols_kernel(const T* __restrict__ src, int k, long long n, T* __restrict__ dst, int ld, int off) {
+  const long long total = n * (long long)k;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / k;
+    const int f = (int)(e - r * k);
+    dst[r * ld + off + f] = src[e];
+  }
+}
+// partials[b][f] = sum over the block's rows of X[r][f] * ((w ? w[r] : 0) + wadd): the building block of
+// rhs_init = -X (x_biases + global_bias) and global_bias_base = -global_bias * sum(X, 1)  (wrmf_implicit.hpp:111-154)
+template <typename T>
+__global__ void __launch_bounds__(256) weighted_colsum_kernel(const T* __restrict__ X, int k, long long n, const T* __restrict__ w,
+                                                              T wadd, double* __restrict__ partials) {
+  __shared__ double sh[256];
+  const int rpi = max(1, 256 / k);             // rows per iteration of the block
+  const int f = threadIdx.x % k, rl = threadIdx.x / k;
+  double acc = 0.0;
+  if (rl < rpi && threadIdx.x < rpi * k) {
+    for (long long r = (long long)blockIdx.x * rpi + rl; r < n; r += (long long)gridDim.x * rpi) {
+      const T wr = (w ? w[r] : T(0)) + wadd;
+      acc += (double)(X[r * k + f] * wr);
+    }
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < k) {
+    double t = 0.0;
+    for (int q = 0; q < rpi; q++) t += sh[q * k + threadIdx.x];
+    partials[(size_t)blockIdx.x * k + threadIdx.x] = t;
+  }
+}
+template <typename T>
+__global__ void finish_colsum_kernel(const double* __restrict__ partials, int grid, int k, double scale, T* __restrict__ out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= k) return;
+  double t = 0.0;
+  for (int b = 0; b < grid; b++) t += partials[(size_t)b * k + f];
+  out[f] = (T)(scale * t);
+}
+// sum of squares over columns [lo, hi) of an n x ld matrix, optionally weighted per row (loss regulariser over the
+// learned rows only: wrmf_implicit.hpp:286-302, wrmf_explicit.hpp:148-172)
+template <typename T>
+__global__ void __launch_bounds__(256) sqnorm_cols_kernel(const T* __restrict__ X, int ld, int lo, int hi, long long n,
+                                                          const T* __restrict__ cnt, double* __restrict__ partials) {
+  __shared__ double s_red[32];
+  double acc = 0.0;
+  const int w = hi - lo;
+  const long long total = n * (long long)w;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / w;
+    const double v = (double)X[r * ld + lo + (int)(e - r * w)];
+    acc += v * v * (cnt ? (double)cnt[r] : 1.0);
+  }
+  const double tot = block_sum_double(acc, s_red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = tot;
 }
 
 // synthetic CSR: row r draws exactly nnz_per_row distinct ascending ids -- one per
@@ -319,6 +391,12 @@ struct HalfOpts {
   int ctas = 0;   // resident CTAs per SM the kernel is compiled for: 0 default, 3 or 4
   int row_begin = 0, row_count = -1;  // solve only rows [row_begin, row_begin + row_count) of the block (-1: all)
   bool reset_loss = true;             // zero the loss accumulator first (false: add to it)
+  // bias terms, all on compact matrices (see stateless_half): device pointers of the element type being solved
+  int with_biases = 0;
+  double gbias = 0.0;                 // global_bias after the sqrt(eps) cut-off (wrmf_implicit.hpp:108-109)
+  const void* xbias = nullptr;        // [n_src]
+  const void* rhs_init = nullptr;     // [k]
+  int reg_ld = 0, reg_lo = 0, reg_hi = 0;  // loss regulariser over columns [lo, hi) of the n_src x ld matrix (0: whole matrix)
 };
 constexpr int kDefaultCtas = 3;
 constexpr int kDefaultStage = 1;  // LDGSTS: measured 6 % faster than the UBLKCP variant on C3 (profiles/)
@@ -372,7 +450,13 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
   const bool sub_range = (o.row_count >= 0);
   const int n_rows_here = sub_range ? o.row_count : A.n_cols;
   if (n_rows_here == 0) return B200ALS_OK;
-  SolveParams<T> P;
+  SolveParams<T> P{};
+  const bool biased = o.with_biases || o.gbias != 0.0;
+  P.xbias = static_cast<const T*>(o.xbias);
+  P.rhs_init = (o.feedback == B200ALS_IMPLICIT) ? static_cast<const T*>(o.rhs_init) : nullptr;
+  P.gbias = (T)o.gbias;
+  P.one_minus_g = (T)(1 - o.gbias);
+  P.solve_empty = (o.feedback == B200ALS_IMPLICIT && biased) ? 1 : 0;
   P.ptr = A.ptr.i32();
   P.idx = A.idx.i32();
   P.val = A.val.template as<T>();
@@ -435,7 +519,8 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
       return B200ALS_OK;
     };
     bool tiled = false;
-    if constexpr (sizeof(T) == 4) tiled = (o.solver == B200ALS_CHOLESKY) && (k == 64 || k == 128) && o.kernel != 1 && !sub_range;
+    if constexpr (sizeof(T) == 4)
+      tiled = (o.solver == B200ALS_CHOLESKY) && (k == 64 || k == 128) && o.kernel != 1 && !sub_range && !biased;
     if (!tiled) return run_generic_chol(nullptr, 0);
     if constexpr (sizeof(T) == 4) {
       // rows with 1..80 non-zeros: tile kernel; longer rows: generic kernel; empty rows: zero
@@ -472,7 +557,7 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
   // ---- conjugate gradient ----
   bool resident = false;
   if constexpr (sizeof(T) == 4) {
-    resident = (k == kResK) && (o.kernel != 1) && (o.feedback == B200ALS_EXPLICIT || G || diag);
+    resident = (k == kResK) && (o.kernel != 1) && (o.feedback == B200ALS_EXPLICIT || G || diag) && !biased;
     if (o.kernel == 2 && !resident) return fail(B200ALS_EUNSUPPORTED, "resident kernel requires rank 128 fp32");
   }
   if (!resident) {
@@ -545,7 +630,11 @@ static int finish_loss(Ctx& c, const T* X, int k, long long n_src, const T* cnt_
     const bool weighted = (o.feedback == B200ALS_EXPLICIT) && o.dynamic_lambda;
     const int grid = c.sm_count * 2;
     CU(c.reg_partials.ensure(sizeof(double) * (size_t)grid));
-    sqnorm_kernel<T><<<grid, 256, 0, c.stream>>>(X, k, n_src, weighted ? cnt_X : nullptr, c.reg_partials.f64());
+    if (o.reg_ld > 0)
+      sqnorm_cols_kernel<T><<<grid, 256, 0, c.stream>>>(X, o.reg_ld, o.reg_lo, o.reg_hi, n_src, weighted ? cnt_X : nullptr,
+                                                       c.reg_partials.f64());
+    else
+      sqnorm_kernel<T><<<grid, 256, 0, c.stream>>>(X, k, n_src, weighted ? cnt_X : nullptr, c.reg_partials.f64());
     LAUNCHED(); CU(cudaGetLastError());
     sum_partials_kernel<<<1, 32, 0, c.stream>>>(c.reg_partials.f64(), grid, c.loss_acc.f64() + 1, 0);
     LAUNCHED(); CU(cudaGetLastError());
@@ -565,37 +654,110 @@ static int finish_loss(Ctx& c, const T* X, int k, long long n_src, const T* cnt_
 // ------------------------------------------------------------------------------------------------------
 // 1. stateless calls
 // ------------------------------------------------------------------------------------------------------
+// Bias arguments of the reference entry points (src/wrmf_implicit.cpp:5-31, src/wrmf_explicit.cpp:5-27).
 template <typename T>
-static int stateless_half(const b200als_csc* A, int rank, const T* X, T* Y, const T* XtX, const T* cnt_X, const HalfOpts& o,
-                          double* loss) {
+struct BiasArgs {
+  int with_biases = 0, is_x_bias_last_row = 0;
+  double global_bias = 0.0;
+  T* global_bias_base = nullptr;   // host, [rank - with_biases], in/out
+  int initialize_bias_base = 0;
+};
+
+// `rank` = rows of X and Y as the caller holds them (R's private$rank: rank + 2 with biases, model_WRMF.R:162-166).
+// With biases the reference solves a (rank-1)-sized system on row-dropped views (drop_row, wrmf_utils.hpp:3-10):
+//   is_x_bias_last_row:  X = [1, ..., x_bias]   Y = [y_bias, ..., 1]     X_nnz = X rows 0..rank-2, x_biases = last row
+//   otherwise:           X = [x_bias, ..., 1]   Y = [1, ..., y_bias]     X_nnz = X rows 1..rank-1, x_biases = first row
+// Here the views are materialised once on the device as compact matrices Xc (n_src x k), xb (n_src), Yc (n_tgt x k),
+// k = rank - 1, the generic kernels run on those, and the solved rows are scattered back into Y.
+template <typename T>
+static int stateless_half(const b200als_csc* A, int rank, const T* X, T* Y, const T* XtX, const T* cnt_X, HalfOpts o,
+                          double* loss, const BiasArgs<T>& ba = BiasArgs<T>()) {
   Ctx& c = ctx();
   TRY(c.init());
   if (!A || !X || !Y) return fail(B200ALS_EINVAL, "null argument");
   if (rank <= 0) return fail(B200ALS_EINVAL, "rank must be positive");
+  const bool implicit = (o.feedback == B200ALS_IMPLICIT);
+  const bool wb = ba.with_biases != 0, is_last = ba.is_x_bias_last_row != 0;
+  double gbias = implicit ? ba.global_bias : 0.0;
+  if (gbias < std::sqrt((double)std::numeric_limits<T>::epsilon())) gbias = 0.0;          // wrmf_implicit.hpp:108-109
+  if (wb && rank < 2) return fail(B200ALS_EINVAL, "with_biases needs at least 2 rows in X / Y");
+  if (!wb && gbias != 0.0 && !ba.global_bias_base) return fail(B200ALS_EINVAL, "global_bias needs global_bias_base");
+  const int ks = wb ? rank - 1 : rank;           // size of the solved system
+  const int xo = (wb && !is_last) ? 1 : 0;       // X_nnz = drop_row(X_nnz, is_x_bias_last_row)          (:190 / :88)
+  const int xbcol = is_last ? rank - 1 : 0;      // x_biases                                             (:115-119)
+  const int io = (wb && is_last) ? 1 : 0;        // init = drop_row(init, !is_x_bias_last_row), sic      (:191 / :90)
+  const int oo = (wb && !is_last) ? 1 : 0;       // Y.head(rank-1) / Y.tail(rank-1)                      (:240-252)
   CscDev<T> D;
   TRY(upload_csc<T>(A, D, c.stream));
   const size_t k = (size_t)rank;
-  DevBuf dX, dY, dG, dCnt;
-  CU(dX.ensure(sizeof(T) * k * (size_t)A->n_rows));
-  CU(dY.ensure(sizeof(T) * k * (size_t)A->n_cols));
-  CU(cudaMemcpyAsync(dX.p, X, sizeof(T) * k * (size_t)A->n_rows, cudaMemcpyHostToDevice, c.stream));
-  CU(cudaMemcpyAsync(dY.p, Y, sizeof(T) * k * (size_t)A->n_cols, cudaMemcpyHostToDevice, c.stream));
+  const size_t n_src = (size_t)A->n_rows, n_tgt = (size_t)A->n_cols;
+  DevBuf dX, dY, dG, dCnt, dXc, dYc, dXb, dRhs;
+  CU(dX.ensure(sizeof(T) * k * n_src));
+  CU(dY.ensure(sizeof(T) * k * n_tgt));
+  CU(cudaMemcpyAsync(dX.p, X, sizeof(T) * k * n_src, cudaMemcpyHostToDevice, c.stream));
+  CU(cudaMemcpyAsync(dY.p, Y, sizeof(T) * k * n_tgt, cudaMemcpyHostToDevice, c.stream));
+  const T* Xs = dX.template as<T>();   // what the kernels gather from
+  T* Ys = dY.template as<T>();         // what they solve in place
+  const int cp_grid = c.sm_count * 8;
+  if (wb) {
+    CU(dXc.ensure(sizeof(T) * (size_t)ks * std::max<size_t>(1, n_src)));
+    CU(dYc.ensure(sizeof(T) * (size_t)ks * std::max<size_t>(1, n_tgt)));
+    CU(dXb.ensure(sizeof(T) * std::max<size_t>(1, n_src)));
+    pack_cols_kernel<T><<<cp_grid, 256, 0, c.stream>>>(dX.template as<T>(), rank, xo, ks, (long long)n_src, dXc.template as<T>());
+    LAUNCHED(); CU(cudaGetLastError());
+    pack_cols_kernel<T><<<cp_grid, 256, 0, c.stream>>>(dX.template as<T>(), rank, xbcol, 1, (long long)n_src, dXb.template as<T>());
+    LAUNCHED(); CU(cudaGetLastError());
+    pack_cols_kernel<T><<<cp_grid, 256, 0, c.stream>>>(dY.template as<T>(), rank, io, ks, (long long)n_tgt, dYc.template as<T>());
+    LAUNCHED(); CU(cudaGetLastError());
+    Xs = dXc.template as<T>();
+    Ys = dYc.template as<T>();
+    o.with_biases = 1;
+    o.xbias = dXb.p;
+    o.reg_ld = rank;                     // every learned row of X: all but the row of ones (:286-302 / :148-172)
+    o.reg_lo = is_last ? 1 : 0;
+    o.reg_hi = is_last ? rank : rank - 1;
+  }
+  o.gbias = gbias;
   const T* G = nullptr;
-  if (o.feedback == B200ALS_IMPLICIT) {
-    CU(dG.ensure(sizeof(T) * k * k));
-    if (XtX) CU(cudaMemcpyAsync(dG.p, XtX, sizeof(T) * k * k, cudaMemcpyHostToDevice, c.stream));
-    else TRY(run_gram<T>(c, dX.template as<T>(), rank, A->n_rows, o.lambda, dG.template as<T>(), nullptr));
+  if (implicit) {
+    CU(dG.ensure(sizeof(T) * (size_t)ks * ks));
+    if (XtX) CU(cudaMemcpyAsync(dG.p, XtX, sizeof(T) * (size_t)ks * ks, cudaMemcpyHostToDevice, c.stream));
+    else TRY(run_gram<T>(c, Xs, ks, A->n_rows, o.lambda, dG.template as<T>(), nullptr));   // R/model_WRMF.R:474-486
     G = dG.template as<T>();
+    if (wb || gbias != 0.0) {
+      // rhs_init = -X_nnz-view * (x_biases + global_bias) (:143-154) ; global_bias_base = sum(X, 1) * (-global_bias) (:111-112)
+      CU(dRhs.ensure(sizeof(T) * (size_t)ks));
+      const bool compute = wb || ba.initialize_bias_base;
+      if (compute) {
+        if (ks > 256) return fail(B200ALS_EUNSUPPORTED, "bias terms: rank > 256 is not supported");
+        const int cs_grid = c.sm_count * 4;
+        CU(c.reg_partials.ensure(sizeof(double) * (size_t)cs_grid * ks));
+        weighted_colsum_kernel<T><<<cs_grid, 256, 0, c.stream>>>(Xs, ks, (long long)n_src, wb ? dXb.template as<T>() : nullptr,
+                                                               wb ? (T)gbias : T(1), c.reg_partials.f64());
+        LAUNCHED(); CU(cudaGetLastError());
+        finish_colsum_kernel<T><<<(ks + 127) / 128, 128, 0, c.stream>>>(c.reg_partials.f64(), cs_grid, ks, wb ? -1.0 : -gbias,
+                                                                       dRhs.template as<T>());
+        LAUNCHED(); CU(cudaGetLastError());
+        if (!wb) CU(cudaMemcpyAsync(ba.global_bias_base, dRhs.p, sizeof(T) * (size_t)ks, cudaMemcpyDeviceToHost, c.stream));
+      } else {
+        CU(cudaMemcpyAsync(dRhs.p, ba.global_bias_base, sizeof(T) * (size_t)ks, cudaMemcpyHostToDevice, c.stream));
+      }
+      o.rhs_init = dRhs.p;
+    }
   }
   const T* dcnt = nullptr;
   if (o.feedback == B200ALS_EXPLICIT && o.dynamic_lambda && o.lambda > 0) {
     if (!cnt_X) return fail(B200ALS_EINVAL, "explicit feedback with dynamic_lambda needs cnt_X");
-    CU(dCnt.ensure(sizeof(T) * (size_t)A->n_rows));
-    CU(cudaMemcpyAsync(dCnt.p, cnt_X, sizeof(T) * (size_t)A->n_rows, cudaMemcpyHostToDevice, c.stream));
+    CU(dCnt.ensure(sizeof(T) * n_src));
+    CU(cudaMemcpyAsync(dCnt.p, cnt_X, sizeof(T) * n_src, cudaMemcpyHostToDevice, c.stream));
     dcnt = dCnt.template as<T>();
   }
-  TRY(solve_rows<T>(c, D, dX.template as<T>(), dY.template as<T>(), G, nullptr, rank, o));
-  CU(cudaMemcpyAsync(Y, dY.p, sizeof(T) * k * (size_t)A->n_cols, cudaMemcpyDeviceToHost, c.stream));
+  TRY(solve_rows<T>(c, D, Xs, Ys, G, nullptr, ks, o));
+  if (wb) {
+    unpack_cols_kernel<T><<<cp_grid, 256, 0, c.stream>>>(dYc.template as<T>(), ks, (long long)n_tgt, dY.template as<T>(), rank, oo);
+    LAUNCHED(); CU(cudaGetLastError());
+  }
+  CU(cudaMemcpyAsync(Y, dY.p, sizeof(T) * k * n_tgt, cudaMemcpyDeviceToHost, c.stream));
   TRY(finish_loss<T>(c, dX.template as<T>(), rank, A->n_rows, dcnt, o, A->nnz, 0.0, false, loss));
   return B200ALS_OK;
 }
@@ -759,7 +921,8 @@ static int stateless_pipelined(const b200als_csc* A, const float* X, float* Y, c
     sum_partials_kernel<<<1, 32, 0, c.stream>>>(c.loss_partials.f64(), res_grid, c.loss_acc.f64(), 1);
     LAUNCHED(); CU(cudaGetLastError());
     {  // rows longer than the register tile: streaming kernel on the same (rotated) data
-      SolveParams<float> P;
+      SolveParams<float> P{};
+      P.one_minus_g = 1.f;
       P.ptr = b.ptr.i32(); P.idx = b.idx.i32(); P.val = b.val32.f32(); P.X = pc.X.f32(); P.Y = b.Y.f32();
       P.G = implicit ? Glong : nullptr; P.k = k; P.n_targets = nr; P.feedback = o.feedback; P.cg_steps = o.cg_steps;
       P.dynamic_lambda = o.dynamic_lambda; P.solver = 0; P.lambda = o.lambda; P.row_list = b.long_list.i32(); P.n_list = 0;
@@ -795,41 +958,169 @@ static bool use_pipelined(const b200als_csc* m, int rank, const float* X, const 
   return m->n_cols >= 200000;
 }
 
-static int check_bias_args(int with_biases, double global_bias) {
-  if (with_biases) return fail(B200ALS_EUNSUPPORTED, "with_user_item_bias is not implemented (SURVEY 8f-3)");
-  if (global_bias != 0.0) return fail(B200ALS_EUNSUPPORTED, "with_global_bias is not implemented (SURVEY 8f-3)");
-  return B200ALS_OK;
-}
-
+// bias terms run on the generic kernels of the plain (non-pipelined) call
 extern "C" int b200als_als_implicit_float(const b200als_csc* m, int rank, const float* X, float* Y, const float* XtX,
-                                          double lambda, int, unsigned solver, unsigned cg_steps, int with_biases, int,
-                                          double global_bias, float*, int, double* loss) {
-  TRY(check_bias_args(with_biases, global_bias));
+                                          double lambda, int, unsigned solver, unsigned cg_steps, int with_biases,
+                                          int is_x_bias_last_row, double global_bias, float* global_bias_base,
+                                          int initialize_bias_base, double* loss) {
   HalfOpts o{B200ALS_IMPLICIT, (int)solver, (int)cg_steps, 0, 0, lambda};
-  if (use_pipelined(m, rank, X, Y, o)) return stateless_pipelined(m, X, Y, XtX, nullptr, o, loss);
-  return stateless_half<float>(m, rank, X, Y, XtX, nullptr, o, loss);
+  const bool biased = with_biases || global_bias >= std::sqrt((double)std::numeric_limits<float>::epsilon());
+  if (!biased && use_pipelined(m, rank, X, Y, o)) return stateless_pipelined(m, X, Y, XtX, nullptr, o, loss);
+  BiasArgs<float> ba{with_biases, is_x_bias_last_row, global_bias, global_bias_base, initialize_bias_base};
+  return stateless_half<float>(m, rank, X, Y, XtX, nullptr, o, loss, ba);
 }
 extern "C" int b200als_als_implicit_double(const b200als_csc* m, int rank, const double* X, double* Y, const double* XtX,
-                                           double lambda, int, unsigned solver, unsigned cg_steps, int with_biases, int,
-                                           double global_bias, double*, int, double* loss) {
-  TRY(check_bias_args(with_biases, global_bias));
+                                           double lambda, int, unsigned solver, unsigned cg_steps, int with_biases,
+                                           int is_x_bias_last_row, double global_bias, double* global_bias_base,
+                                           int initialize_bias_base, double* loss) {
   HalfOpts o{B200ALS_IMPLICIT, (int)solver, (int)cg_steps, 0, 0, lambda};
-  return stateless_half<double>(m, rank, X, Y, XtX, nullptr, o, loss);
+  BiasArgs<double> ba{with_biases, is_x_bias_last_row, global_bias, global_bias_base, initialize_bias_base};
+  return stateless_half<double>(m, rank, X, Y, XtX, nullptr, o, loss, ba);
 }
 extern "C" int b200als_als_explicit_float(const b200als_csc* m, int rank, const float* X, float* Y, const float* cnt_X,
                                           double lambda, unsigned, unsigned solver, unsigned cg_steps, int dynamic_lambda,
-                                          int with_biases, int, double* loss) {
-  TRY(check_bias_args(with_biases, 0.0));
+                                          int with_biases, int is_x_bias_last_row, double* loss) {
   HalfOpts o{B200ALS_EXPLICIT, (int)solver, (int)cg_steps, dynamic_lambda != 0, 0, lambda};
-  if (use_pipelined(m, rank, X, Y, o)) return stateless_pipelined(m, X, Y, nullptr, cnt_X, o, loss);
-  return stateless_half<float>(m, rank, X, Y, nullptr, cnt_X, o, loss);
+  if (!with_biases && use_pipelined(m, rank, X, Y, o)) return stateless_pipelined(m, X, Y, nullptr, cnt_X, o, loss);
+  BiasArgs<float> ba{with_biases, is_x_bias_last_row, 0.0, nullptr, 0};
+  return stateless_half<float>(m, rank, X, Y, nullptr, cnt_X, o, loss, ba);
 }
 extern "C" int b200als_als_explicit_double(const b200als_csc* m, int rank, const double* X, double* Y, const double* cnt_X,
                                            double lambda, unsigned, unsigned solver, unsigned cg_steps, int dynamic_lambda,
-                                           int with_biases, int, double* loss) {
-  TRY(check_bias_args(with_biases, 0.0));
+                                           int with_biases, int is_x_bias_last_row, double* loss) {
   HalfOpts o{B200ALS_EXPLICIT, (int)solver, (int)cg_steps, dynamic_lambda != 0, 0, lambda};
-  return stateless_half<double>(m, rank, X, Y, nullptr, cnt_X, o, loss);
+  BiasArgs<double> ba{with_biases, is_x_bias_last_row, 0.0, nullptr, 0};
+  return stateless_half<double>(m, rank, X, Y, nullptr, cnt_X, o, loss, ba);
+}
+
+// initialize_biases<T> (wrmf_utils.hpp:170-183; src/wrmf_init.cpp:6-34) -- see bias_init.cuh
+template <typename T>
+static int initialize_biases_impl(int32_t n_user, int32_t n_item, int64_t nnz, const int32_t* csc_ptr, const int32_t* csc_idx,
+                                  double* csc_val, const int32_t* csr_ptr, const int32_t* csr_idx, double* csr_val,
+                                  T* user_bias, T* item_bias, double lambda, int dynamic_lambda, int non_negative,
+                                  int calculate_global_bias, int is_explicit, double* global_bias) {
+  Ctx& c = ctx();
+  TRY(c.init());
+  if (!csc_ptr || !csr_ptr || !user_bias || !item_bias || n_user < 0 || n_item < 0 || nnz < 0)
+    return fail(B200ALS_EINVAL, "bad argument");
+  if (nnz > 0 && (!csc_idx || !csc_val || !csr_idx || !csr_val)) return fail(B200ALS_EINVAL, "null matrix slots");
+  DevBuf cp, ci, cv, rp, ri, rv, ub, ib, part, scal, um, ua, im, ia;
+  const size_t e = (size_t)std::max<int64_t>(1, nnz);
+  CU(cp.ensure(sizeof(int32_t) * ((size_t)n_item + 1)));
+  CU(rp.ensure(sizeof(int32_t) * ((size_t)n_user + 1)));
+  CU(ci.ensure(sizeof(int32_t) * e)); CU(ri.ensure(sizeof(int32_t) * e));
+  CU(cv.ensure(sizeof(double) * e)); CU(rv.ensure(sizeof(double) * e));
+  CU(ub.ensure(sizeof(T) * (size_t)std::max(1, n_user)));
+  CU(ib.ensure(sizeof(T) * (size_t)std::max(1, n_item)));
+  const int grid = c.sm_count * 4;
+  CU(part.ensure(sizeof(double) * (size_t)grid));
+  CU(scal.ensure(sizeof(double) * 4));
+  cudaStream_t st = c.stream;
+  CU(cudaMemcpyAsync(cp.p, csc_ptr, sizeof(int32_t) * ((size_t)n_item + 1), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(rp.p, csr_ptr, sizeof(int32_t) * ((size_t)n_user + 1), cudaMemcpyHostToDevice, st));
+  if (nnz) {
+    CU(cudaMemcpyAsync(ci.p, csc_idx, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ri.p, csr_idx, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(cv.p, csc_val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(rv.p, csr_val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+  }
+  if (n_user) CU(cudaMemcpyAsync(ub.p, user_bias, sizeof(T) * (size_t)n_user, cudaMemcpyHostToDevice, st));
+  if (n_item) CU(cudaMemcpyAsync(ib.p, item_bias, sizeof(T) * (size_t)n_item, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(scal.p, 0, sizeof(double) * 4, st));
+  double* d_scal = scal.f64();   // [0] sum of values, [1] sum(user_bias), [2] sum(item_bias)
+  auto device_sum = [&](auto* v, long long n, double* out) -> int {
+    using V = std::remove_pointer_t<decltype(v)>;
+    sum_to_partials_kernel<std::remove_const_t<V>><<<grid, 256, 0, st>>>(v, n, part.f64());
+    LAUNCHED(); CU(cudaGetLastError());
+    sum_partials_kernel<<<1, 32, 0, st>>>(part.f64(), grid, out, 0);
+    LAUNCHED(); CU(cudaGetLastError());
+    return B200ALS_OK;
+  };
+  double g = 0.0;
+  const unsigned gi = (unsigned)std::max(1, (n_item + 127) / 128), gu = (unsigned)std::max(1, (n_user + 127) / 128);
+  if (calculate_global_bias && nnz > 0) {
+    TRY(device_sum((const double*)cv.f64(), (long long)nnz, d_scal));
+    double s = 0.0;
+    CU(cudaMemcpyAsync(&s, d_scal, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (is_explicit) {
+      g = s / (double)nnz;                                                     // mean rating (wrmf_utils.hpp:40-43)
+      shift_values_kernel<<<grid, 256, 0, st>>>(cv.f64(), rv.f64(), (long long)nnz, d_scal, 1.0 / (double)nnz);
+      LAUNCHED(); CU(cudaGetLastError());
+    } else {
+      g = s / (s + (double)n_item * (double)n_user - (double)nnz);             // (:91-94)
+    }
+  }
+  if (!is_explicit && non_negative) g = std::fmax(0.0, g);                       // (:95)
+  if (is_explicit) {
+    for (int iter = 0; iter < 5; iter++) {                                      // (:54-80)
+      if (n_item) {
+        bias_sweep_explicit_kernel<T><<<gi, 128, 0, st>>>(cp.i32(), ci.i32(), cv.f64(), n_item, ub.template as<T>(),
+                                                          ib.template as<T>(), (T)lambda, dynamic_lambda, non_negative);
+        LAUNCHED(); CU(cudaGetLastError());
+      }
+      if (n_user) {
+        bias_sweep_explicit_kernel<T><<<gu, 128, 0, st>>>(rp.i32(), ri.i32(), rv.f64(), n_user, ib.template as<T>(),
+                                                          ub.template as<T>(), (T)lambda, dynamic_lambda, non_negative);
+        LAUNCHED(); CU(cudaGetLastError());
+      }
+    }
+    if (calculate_global_bias && nnz > 0) {   // the reference shifts the caller's values in place (:48-51)
+      CU(cudaMemcpyAsync(csc_val, cv.p, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(csr_val, rv.p, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToHost, st));
+    }
+  } else {
+    CU(um.ensure(sizeof(double) * (size_t)std::max(1, n_user))); CU(ua.ensure(sizeof(double) * (size_t)std::max(1, n_user)));
+    CU(im.ensure(sizeof(double) * (size_t)std::max(1, n_item))); CU(ia.ensure(sizeof(double) * (size_t)std::max(1, n_item)));
+    const double lam_t = (double)(T)lambda;   // `T lambda` in the reference's signature
+    if (n_user) {
+      bias_means_implicit_kernel<<<gu, 128, 0, st>>>(rp.i32(), rv.f64(), n_user, n_item, lam_t, um.f64(), ua.f64());
+      LAUNCHED(); CU(cudaGetLastError());
+    }
+    if (n_item) {
+      bias_means_implicit_kernel<<<gi, 128, 0, st>>>(cp.i32(), cv.f64(), n_item, n_user, lam_t, im.f64(), ia.f64());
+      LAUNCHED(); CU(cudaGetLastError());
+    }
+    for (int iter = 0; iter < 5; iter++) {                                      // (:130-162)
+      if (iter > 0 && n_user) TRY(device_sum((const T*)ub.template as<T>(), (long long)n_user, d_scal + 1));
+      if (n_item) {
+        bias_sweep_implicit_kernel<T><<<gi, 128, 0, st>>>(cp.i32(), ci.i32(), cv.f64(), n_item, n_user, ub.template as<T>(),
+                                                          (iter > 0 && n_user) ? d_scal + 1 : nullptr, im.f64(), ia.f64(), g,
+                                                          non_negative, ib.template as<T>());
+        LAUNCHED(); CU(cudaGetLastError());
+        TRY(device_sum((const T*)ib.template as<T>(), (long long)n_item, d_scal + 2));
+      }
+      if (n_user) {
+        bias_sweep_implicit_kernel<T><<<gu, 128, 0, st>>>(rp.i32(), ri.i32(), rv.f64(), n_user, n_item, ib.template as<T>(),
+                                                          n_item ? d_scal + 2 : nullptr, um.f64(), ua.f64(), g, non_negative,
+                                                          ub.template as<T>());
+        LAUNCHED(); CU(cudaGetLastError());
+      }
+    }
+  }
+  if (n_user) CU(cudaMemcpyAsync(user_bias, ub.p, sizeof(T) * (size_t)n_user, cudaMemcpyDeviceToHost, st));
+  if (n_item) CU(cudaMemcpyAsync(item_bias, ib.p, sizeof(T) * (size_t)n_item, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (global_bias) *global_bias = g;
+  return B200ALS_OK;
+}
+extern "C" int b200als_initialize_biases_float(int32_t n_user, int32_t n_item, int64_t nnz, const int32_t* csc_ptr,
+                                               const int32_t* csc_idx, double* csc_val, const int32_t* csr_ptr,
+                                               const int32_t* csr_idx, double* csr_val, float* user_bias, float* item_bias,
+                                               double lambda, int dynamic_lambda, int non_negative, int calculate_global_bias,
+                                               int is_explicit_feedback, double* global_bias) {
+  return initialize_biases_impl<float>(n_user, n_item, nnz, csc_ptr, csc_idx, csc_val, csr_ptr, csr_idx, csr_val, user_bias,
+                                       item_bias, lambda, dynamic_lambda, non_negative, calculate_global_bias,
+                                       is_explicit_feedback, global_bias);
+}
+extern "C" int b200als_initialize_biases_double(int32_t n_user, int32_t n_item, int64_t nnz, const int32_t* csc_ptr,
+                                                const int32_t* csc_idx, double* csc_val, const int32_t* csr_ptr,
+                                                const int32_t* csr_idx, double* csr_val, double* user_bias, double* item_bias,
+                                                double lambda, int dynamic_lambda, int non_negative, int calculate_global_bias,
+                                                int is_explicit_feedback, double* global_bias) {
+  return initialize_biases_impl<double>(n_user, n_item, nnz, csc_ptr, csc_idx, csc_val, csr_ptr, csr_idx, csr_val, user_bias,
+                                        item_bias, lambda, dynamic_lambda, non_negative, calculate_global_bias,
+                                        is_explicit_feedback, global_bias);
 }
 
 extern "C" int b200als_gram_float(const float* X, int rank, int64_t n, double lambda, float* XtX) {

@@ -23,9 +23,12 @@ def gram(X, lambda_):
 
 
 def als_implicit(ptr, idx, val, X, Y, lambda_, solver_code, cg_steps=3, XtX=None, n_threads=1,
-                 with_user_item_bias=False, is_bias_last_row=False, global_bias=0.0):
-    """One implicit-feedback half-iteration (als_implicit_{float,double}, src/wrmf_implicit.cpp:5-31).
-    `Y` is modified in place; returns the loss."""
+                 with_user_item_bias=False, is_bias_last_row=False, global_bias=0.0, global_bias_base=None,
+                 initialize_bias_base=True):
+    """One implicit-feedback half-iteration (als_implicit_{float,double}, src/wrmf_implicit.cpp:5-31; R wrapper
+    R/model_WRMF.R:456-497).  `Y` is modified in place; returns the loss.  With `with_user_item_bias`, X and Y have
+    rank+2 columns and XtX is (rank+1) x (rank+1); `global_bias_base` (length = side of XtX, dtype of X) is rewritten
+    when `initialize_bias_base`, as in the reference."""
     dt = X.dtype.type
     if dt not in (np.float32, np.float64):
         raise ValueError("X must be float32 or float64")
@@ -34,13 +37,21 @@ def als_implicit(ptr, idx, val, X, Y, lambda_, solver_code, cg_steps=3, XtX=None
     if X.shape[1] != Y.shape[1] or Y.shape[0] != len(ptr) - 1:
         raise ValueError("shape mismatch")
     csc, keep = L.make_csc(X.shape[0], ptr, idx, val)
+    ks = X.shape[1] - int(bool(with_user_item_bias))
     if XtX is not None:
         XtX = np.ascontiguousarray(XtX, dtype=dt)
+        if XtX.shape != (ks, ks):
+            raise ValueError("XtX must be %d x %d" % (ks, ks))
+    if global_bias_base is None:
+        global_bias_base = np.zeros(ks, dt)
+    if not (isinstance(global_bias_base, np.ndarray) and global_bias_base.dtype == dt and global_bias_base.flags.c_contiguous
+            and (with_user_item_bias or len(global_bias_base) == ks)):
+        raise ValueError("global_bias_base must be a contiguous %s vector of length %d" % (np.dtype(dt).name, ks))
     loss = C.c_double(0.0)
     fn = L.lib().b200als_als_implicit_float if dt == np.float32 else L.lib().b200als_als_implicit_double
     L.check(fn(C.byref(csc), X.shape[1], L.vp(X), L.vp(Y), L.vp(XtX), float(lambda_), int(n_threads), int(solver_code),
-               int(cg_steps), int(with_user_item_bias), int(is_bias_last_row), float(global_bias), None, 0,
-               C.byref(loss)))
+               int(cg_steps), int(bool(with_user_item_bias)), int(bool(is_bias_last_row)), float(global_bias),
+               L.vp(global_bias_base), int(bool(initialize_bias_base)), C.byref(loss)))
     del keep
     return loss.value
 
@@ -63,6 +74,32 @@ def als_explicit(ptr, idx, val, X, Y, cnt_X, lambda_, solver_code, cg_steps=3, d
                C.byref(loss)))
     del keep
     return loss.value
+
+
+def initialize_biases(c_ui, c_iu, user_bias, item_bias, lambda_, dynamic_lambda, non_negative, calculate_global_bias,
+                      is_explicit_feedback):
+    """initialize_biases_{double,float} (src/wrmf_init.cpp:6-34 -> inst/include/wrmf_utils.hpp:170-183) on the GPU.
+    c_ui = (ptr[n_item+1], idx, val) the user x item matrix by item, c_iu = (ptr[n_user+1], idx, val) by user; the
+    float64 `val` arrays are shifted IN PLACE for explicit feedback with calculate_global_bias; the bias vectors are
+    filled in place.  Returns global_bias."""
+    cp, ci, cv = c_ui
+    rp, ri, rv = c_iu
+    dt = user_bias.dtype.type
+    for a in (cp, ci, rp, ri):
+        if a.dtype != np.int32 or not a.flags.c_contiguous:
+            raise ValueError("index arrays must be contiguous int32")
+    for a in (cv, rv):
+        if a.dtype != np.float64 or not a.flags.c_contiguous:
+            raise ValueError("values must be contiguous float64")
+    n_item, n_user = len(cp) - 1, len(rp) - 1
+    if item_bias.dtype != dt or len(user_bias) != n_user or len(item_bias) != n_item or dt not in (np.float32, np.float64):
+        raise ValueError("bias vectors do not match the matrix")
+    g = C.c_double(0.0)
+    fn = L.lib().b200als_initialize_biases_float if dt == np.float32 else L.lib().b200als_initialize_biases_double
+    L.check(fn(n_user, n_item, len(ci), L.vp(cp), L.vp(ci), L.vp(cv), L.vp(rp), L.vp(ri), L.vp(rv), L.vp(user_bias),
+               L.vp(item_bias), float(lambda_), int(bool(dynamic_lambda)), int(bool(non_negative)),
+               int(bool(calculate_global_bias)), int(bool(is_explicit_feedback)), C.byref(g)))
+    return g.value
 
 
 def top_product(user_emb, item_emb, k, not_recommend=None, exclude=(), glob_mean=0.0):

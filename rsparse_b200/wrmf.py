@@ -11,7 +11,7 @@ import numpy as np
 import scipy.sparse as sp
 
 from . import _lib as L
-from .ops import als_explicit, als_implicit
+from .ops import als_explicit, als_implicit, initialize_biases
 
 logger = logging.getLogger("rsparse")
 
@@ -137,8 +137,10 @@ class Session:
 class WRMF:
     """Weighted Regularized Matrix Factorization (mirror of R/model_WRMF.R:35-454).
 
-    Parameters are the reference's (`lambda` is spelled `lambda_`).  Not implemented by the engine
-    yet: with_user_item_bias / with_global_bias -- these raise."""
+    Parameters are the reference's (`lambda` is spelled `lambda_`).  With `with_user_item_bias` the factor matrices
+    carry rank + 2 rows ([1, ..., user_bias] / [item_bias, ..., 1], R/model_WRMF.R:162-166, :205-246) and every
+    half-iteration goes through the stateless C-ABI calls, as in R; without bias terms float models run on the
+    resident-factor session."""
 
     def __init__(self, rank=10, lambda_=0.0, dynamic_lambda=True, init=None, preprocess=None, feedback="implicit",
                  solver="conjugate_gradient", with_user_item_bias=False, with_global_bias=False, cg_steps=3,
@@ -153,16 +155,20 @@ class WRMF:
             raise ValueError("precision should be one of ['double', 'float']")
         if not isinstance(cg_steps, (int, np.integer)):
             raise TypeError("cg_steps must be an integer")               # stopifnot(is.integer(cg_steps))
-        if with_user_item_bias or with_global_bias:
-            raise NotImplementedError("bias terms are outside this engine's hot-path scope (SURVEY 8f-3)")
         self._solver_code = _SOLVER_CODES[solver]
         self._non_negative = solver == "nnls"
+        if self._non_negative and with_global_bias:                      # R/model_WRMF.R:90-93
+            logger.warning("setting `with_global_bias=FALSE` for 'nnls' solver")
+            with_global_bias = False
+        self._with_user_item_bias = bool(with_user_item_bias)
+        self._with_global_bias = bool(with_global_bias)
+        self.global_bias_base = None
         self._precision = precision
         self._feedback = feedback
         self._lambda = float(lambda_)
         self._dynamic_lambda = bool(dynamic_lambda)
         self._cg_steps = int(cg_steps)
-        self._rank = int(rank)
+        self._rank = int(rank) + (2 if self._with_user_item_bias else 0)   # R/model_WRMF.R:162-166
         self._preprocess = preprocess if preprocess is not None else (lambda m: m)
         self._rng = np.random.default_rng(seed)
         self._kernel = kernel
@@ -175,11 +181,15 @@ class WRMF:
         self._dt = np.float64 if precision == "double" else np.float32
 
     # ---- private$solver (R/model_WRMF.R:111-147) over the stateless C ABI -------------------------
-    def _solve(self, mat, X, Y, cnt_X=None, XtX=None, avoid_cg=False):
+    def _solve(self, mat, X, Y, is_bias_last_row, cnt_X=None, XtX=None, avoid_cg=False):
         solver_use = 0 if (avoid_cg and self._solver_code == 1) else self._solver_code
         if self._feedback == "implicit":
-            return als_implicit(*mat, X, Y, self._lambda, solver_use, self._cg_steps, XtX=XtX)
-        return als_explicit(*mat, X, Y, cnt_X, self._lambda, solver_use, self._cg_steps, self._dynamic_lambda)
+            return als_implicit(*mat, X, Y, self._lambda, solver_use, self._cg_steps, XtX=XtX,
+                                with_user_item_bias=self._with_user_item_bias, is_bias_last_row=is_bias_last_row,
+                                global_bias=self.global_bias, global_bias_base=self.global_bias_base,
+                                initialize_bias_base=not avoid_cg)
+        return als_explicit(*mat, X, Y, cnt_X, self._lambda, solver_use, self._cg_steps, self._dynamic_lambda,
+                            with_user_item_bias=self._with_user_item_bias, is_bias_last_row=is_bias_last_row)
 
     def fit_transform(self, x, n_iter=10, convergence_tol=None):
         if convergence_tol is None:
@@ -193,7 +203,10 @@ class WRMF:
         users = _targets_csc(c_ui)        # c_iu: columns = users, idx = items
         dt = self._dt
         k = self._rank
+        wuib = self._with_user_item_bias
         U = (self._rng.standard_normal((n_user, k)) / 100.0).astype(dt)   # large_rand_matrix / flrnorm(.., 0, 0.01)
+        if wuib:
+            U[:, 0] = 1.0                                                  # for item biases (R/model_WRMF.R:205-216)
         if self.components is None:
             if self._solver_code == 1:                                     # R/model_WRMF.R:219-230: zeros for CG
                 comp = np.zeros((n_item, k), dt)
@@ -203,21 +216,46 @@ class WRMF:
             if self.components.shape != (k, n_item):
                 raise ValueError("init must be rank x n_item")
             comp = np.ascontiguousarray(self.components.T, dtype=dt)
+        if wuib and self.components is None:
+            comp[:, k - 1] = 1.0                                           # for user biases (:219-243)
         if self._non_negative:                                              # R/model_WRMF.R:251-255
             comp = np.abs(comp)
             U = np.abs(U)
+        self.global_bias = 0.0
+        if wuib:                                                            # R/model_WRMF.R:260-279
+            user_bias = np.zeros(n_user, dt)
+            item_bias = np.zeros(n_item, dt)
+            global_bias = initialize_biases(items, users, user_bias, item_bias, self._lambda, self._dynamic_lambda,
+                                            self._non_negative, self._with_global_bias, self._feedback == "explicit")
+            comp[:, 0] = item_bias
+            U[:, k - 1] = user_bias
+            if self._with_global_bias:
+                self.global_bias = global_bias
+        elif self._with_global_bias:                                        # R/model_WRMF.R:280-289
+            if self._feedback == "explicit":
+                self.global_bias = float(np.mean(items[2])) if len(items[2]) else 0.0
+                items[2][:] -= self.global_bias
+                users[2][:] -= self.global_bias
+            else:
+                ssum = float(np.sum(items[2]))
+                self.global_bias = ssum / (ssum + float(n_user) * float(n_item) - len(items[2]))
+        if self._feedback == "implicit":
+            # the reference sizes this rank-1 (R/model_WRMF.R:291-297) while als_implicit<T> reads and writes `rank`
+            # entries (wrmf_implicit.hpp:111-112,155-157); the C ABI takes the length the C++ code uses
+            self.global_bias_base = np.zeros(0 if wuib else k, dt)
         cnt_u = np.diff(items[0]).astype(dt)   # diff(c_ui@p): nnz per item -> cnt_X of the user half (:311)
         cnt_i = np.diff(users[0]).astype(dt)   # diff(c_iu@p): nnz per user -> cnt_X of the item half (:312)
         self._cnt_u = cnt_u
         logger.info("starting factorization")
-        if self._precision == "float":
+        biased = wuib or (self._feedback == "implicit" and self.global_bias != 0.0)
+        if self._precision == "float" and not biased:
             res = self._fit_session(items, users, n_user, n_item, U, comp, n_iter, convergence_tol)
         else:
             loss_prev = np.inf
             for i in range(int(n_iter)):
-                loss = self._solve(items, U, comp, cnt_X=cnt_i)
+                loss = self._solve(items, U, comp, True, cnt_X=cnt_i)        # R/model_WRMF.R:319-323
                 logger.info("iter %d (items) loss = %.4f", i + 1, loss)
-                loss = self._solve(users, comp, U, cnt_X=cnt_u)
+                loss = self._solve(users, comp, U, False, cnt_X=cnt_u)       # R/model_WRMF.R:326-329
                 logger.info("iter %d (users) loss = %.4f", i + 1, loss)
                 if loss_prev / loss - 1 < convergence_tol:
                     logger.info("Converged after %d iterations", i + 1)
@@ -250,15 +288,19 @@ class WRMF:
     def _set_components(self, comp):
         self._comp_rows = np.ascontiguousarray(comp)              # n_item x rank
         self.components = self._comp_rows.T                       # rank x n_item, as in R
-        k = self._rank
         if self._feedback == "implicit":                          # private$XtX (R/model_WRMF.R:347-353)
             c64 = self._comp_rows.astype(self._dt)
+            if self._with_user_item_bias:
+                c64 = c64[:, 1:]                                  # components[-1L, ]: without the item-bias row
+            k = c64.shape[1]
             self._XtX = (c64.T @ c64 + self._lambda * np.eye(k, dtype=self._dt)).astype(self._dt)
 
     # ---- transform_ (R/model_WRMF.R:412-452) -------------------------------------------------------
     def _transform(self, users):
         res = np.zeros((len(users[0]) - 1, self._rank), self._dt)
-        self._solve(users, self._comp_rows.astype(self._dt, copy=False), res, cnt_X=self._cnt_u, XtX=self._XtX,
+        if self._with_user_item_bias:
+            res[:, 0] = 1.0                                        # R/model_WRMF.R:429-431
+        self._solve(users, self._comp_rows.astype(self._dt, copy=False), res, False, cnt_X=self._cnt_u, XtX=self._XtX,
                     avoid_cg=True)
         return res
 
@@ -268,7 +310,10 @@ class WRMF:
         x = self._preprocess(sp.csr_matrix(x))
         if x.shape[1] != self.components.shape[1]:
             raise ValueError("ncol(x) == ncol(self$components) is not TRUE")   # R/model_WRMF.R:367
-        return self._transform(_targets_csc(x))
+        users = _targets_csc(x)
+        if self.global_bias != 0.0 and self._feedback == "explicit":       # R/model_WRMF.R:381-382
+            users[2][:] -= self.global_bias
+        return self._transform(users)
 
     def predict(self, x, k, not_recommend="x", items_exclude=(), return_scores=False):
         """MatrixFactorizationRecommender$predict (R/MatrixFactorizationRecommender.R:24-78): transform(x), then the

@@ -31,3 +31,16 @@ def golden_traces():
 def cases():
     import wrmf_cases as wc
     return wc.half_iteration_cases()
+
+
+@pytest.fixture(scope="session")
+def golden_bias():
+    import numpy as np
+    import wrmf_cases as wc
+    return np.load(os.path.join(wc.GOLDEN, "bias_half_iterations.npz"))
+
+
+@pytest.fixture(scope="session")
+def bias_cases():
+    import wrmf_cases as wc
+    return wc.bias_cases()

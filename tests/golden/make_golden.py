@@ -71,6 +71,38 @@ def main():
         print("%-40s loss f64 %.8f f32 %.8f" % (name, out[name + "/loss_f64"], out[name + "/loss_f32"]))
     np.savez_compressed(os.path.join(OUT, "half_iterations.npz"), **out)
 
+    # ---- bias variants (with_user_item_bias / global_bias), also straight from the reference's headers -----------
+    out = {}
+    for name, c in wc.bias_cases().items():
+        for dt, tag in ((np.float64, "f64"), (np.float32, "f32")):
+            X = c["X"].astype(dt)
+            Y = c["Y0"].astype(dt).copy()
+            if c["feedback"] == "implicit":
+                gbb = np.zeros(X.shape[1] - int(c["with_biases"]), dt)
+                loss = oracle.als_implicit_bias(c["ptr"], c["idx"], c["val"], X, Y, wc.xtx_for(c, dt), c["lam"], c["solver"],
+                                                c["cg_steps"], c["with_biases"], c["is_last"], c["gbias"], gbb, True, 1,
+                                                impl="ref")
+                out[name + "/gbb_" + tag] = gbb
+            else:
+                loss = oracle.als_explicit_bias(c["ptr"], c["idx"], c["val"], X, Y, c["cnt_X"].astype(dt), c["lam"],
+                                                c["solver"], c["cg_steps"], c["dynamic_lambda"], c["with_biases"],
+                                                c["is_last"], 1, impl="ref")
+            out[name + "/Y_" + tag] = Y
+            out[name + "/loss_" + tag] = np.float64(loss)
+        print("%-40s loss f64 %.8f f32 %.8f" % (name, out[name + "/loss_f64"], out[name + "/loss_f32"]))
+    # initialize_biases<T> (wrmf_utils.hpp:170-183) on movielens100k
+    for is_explicit in (True, False):
+        for nn in (False, True):
+            for dt, tag in ((np.float64, "f64"), (np.float32, "f32")):
+                csc = (items[0], items[1], items[2].copy())
+                csr = (users[0], users[1], users[2].copy())
+                ub, ib = np.zeros(n_user, dt), np.zeros(n_item, dt)
+                g = oracle.initialize_biases(csc, csr, ub, ib, 0.1, True, nn, True, is_explicit, impl="ref")
+                key = "init_%s_nn%d_%s" % ("explicit" if is_explicit else "implicit", int(nn), tag)
+                out[key + "/user_bias"], out[key + "/item_bias"], out[key + "/global_bias"] = ub, ib, np.float64(g)
+                print("%-40s global_bias %.8f" % (key, g))
+    np.savez_compressed(os.path.join(OUT, "bias_half_iterations.npz"), **out)
+
     def factors(n, k, seed=[100]):
         seed[0] += 1
         return wc.det_factors(n, k, seed[0])

@@ -115,3 +115,57 @@ def half_iteration_cases():
         C[name]["X"] = np.abs(C[name]["X"])
         C[name]["Y0"] = np.abs(C[name]["Y0"])
     return C
+
+
+def xtx_for(c, dt):
+    """XtX as R builds it for als_implicit (R/model_WRMF.R:474-486): tcrossprod of X without its bias row + lambda I."""
+    X = c["X"].astype(dt)
+    if c.get("with_biases"):
+        X = X[:, :-1] if c["is_last"] else X[:, 1:]
+    return (X.T @ X + c["lam"] * np.eye(X.shape[1], dtype=dt)).astype(dt)
+
+
+def bias_cases():
+    """Half-iterations with with_user_item_bias / global_bias.  Same dict as half_iteration_cases() plus
+    with_biases, is_last (is_x_bias_last_row), gbias.  X / Y0 follow the reference's layouts (wrmf_implicit.hpp:96-101):
+    is_last: X = [1, ..., x_bias], Y = [y_bias, ..., 1]; otherwise X = [x_bias, ..., 1], Y = [1, ..., y_bias]."""
+    M = load_movielens()
+    users, items = targets_csc(M), targets_csc(M.T)
+    n_user, n_item = M.shape
+    cnt_items = np.diff(items[0]).astype(np.float32)
+    cnt_users = np.diff(users[0]).astype(np.float32)
+    rag = det_csr(400, 900, 40, 31, ragged=True, empty_every=9)
+    rag_e = det_csr(400, 900, 40, 32, ragged=True, empty_every=7, explicit=True)
+    C = {}
+
+    def add(name, mat, n_src, rank, feedback, solver, lam, seed, wb, is_last, gbias=0.0, dynamic_lambda=True, cnt_X=None,
+            cg_steps=3):
+        ptr, idx, val = mat
+        kf = rank + (2 if wb else 0)
+        X = det_factors(n_src, kf, seed, 0.1)
+        Y0 = det_factors(len(ptr) - 1, kf, seed + 1, 0.1)
+        if solver == NNLS:
+            X, Y0 = np.abs(X), np.abs(Y0)
+        if wb:
+            if is_last:
+                X[:, 0] = 1.0
+                Y0[:, -1] = 1.0
+            else:
+                X[:, -1] = 1.0
+                Y0[:, 0] = 1.0
+        C[name] = dict(ptr=ptr, idx=idx, val=val, X=X, Y0=Y0, feedback=feedback, solver=solver, lam=lam, cg_steps=cg_steps,
+                       dynamic_lambda=dynamic_lambda, cnt_X=cnt_X, with_biases=wb, is_last=is_last, gbias=gbias)
+
+    add("bias_ml100k_user_implicit_chol", users, n_item, 10, "implicit", CHOL, 0.1, 41, True, False)
+    add("bias_ml100k_item_implicit_chol", items, n_user, 6, "implicit", CHOL, 0.1, 42, True, True)
+    add("bias_rag_implicit_chol_global", rag, 900, 8, "implicit", CHOL, 0.1, 43, True, False, gbias=0.05)
+    add("bias_rag_implicit_nnls", rag, 900, 8, "implicit", NNLS, 0.1, 44, True, True)
+    add("global_rag_implicit_chol", rag, 900, 16, "implicit", CHOL, 0.1, 45, False, False, gbias=0.05)
+    add("global_ml100k_user_implicit_cg", users, n_item, 16, "implicit", CG, 0.1, 46, False, False, gbias=0.19)
+    add("global_rag_implicit_nnls", rag, 900, 12, "implicit", NNLS, 0.1, 47, False, True, gbias=0.05)
+    add("bias_ml100k_user_explicit_cg", users, n_item, 8, "explicit", CG, 0.1, 48, True, False, cnt_X=cnt_items)
+    add("bias_ml100k_item_explicit_cg_static", items, n_user, 8, "explicit", CG, 5.0, 49, True, True, dynamic_lambda=False,
+        cnt_X=cnt_users)
+    add("bias_rag_explicit_chol", rag_e, 900, 10, "explicit", CHOL, 0.1, 50, True, False, cnt_X=np.ones(900, np.float32))
+    add("bias_rag_explicit_nnls", rag_e, 900, 10, "explicit", NNLS, 0.1, 51, True, True, cnt_X=np.ones(900, np.float32))
+    return C
