@@ -1334,6 +1334,13 @@ struct b200als_session {
   std::vector<int32_t> ranges[2];   // [3*world]: every rank's [begin, end, can_chunk) per orientation (multi-GPU)
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_chunk[8] = {}, ev_comm_done = nullptr;
+  // peer-memory exchange (multi-GPU): every rank maps every other rank's factor matrices (CUDA IPC) and pushes its
+  // freshly solved rows straight into them with the copy engines over NVLink -- no SM is taken from the solve
+  static constexpr int kMaxPeers = 16;
+  int p2p_state = 0;                      // 0 not tried yet, 1 active, -1 unavailable (NCCL broadcasts instead)
+  float* peer_fac[2][kMaxPeers] = {};
+  cudaStream_t push_stream[kMaxPeers] = {};
+  cudaEvent_t ev_push[kMaxPeers] = {};
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   float t_gram = 0, t_prep = 0, t_solve = 0, t_comm = 0;
 };
@@ -1566,6 +1573,23 @@ extern "C" int b200als_destroy(b200als_session* s) {
     if (e) cudaEventDestroy(e);
   if (s->ev_comm_done) cudaEventDestroy(s->ev_comm_done);
   if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
+  if (s->p2p_state == 1) {
+    cudaDeviceSynchronize();
+    for (int w = 0; w < 2; w++)
+      for (int r = 0; r < b200als_session::kMaxPeers; r++)
+        if (s->peer_fac[w][r]) cudaIpcCloseMemHandle(s->peer_fac[w][r]);
+    for (int r = 0; r < b200als_session::kMaxPeers; r++) {
+      if (s->push_stream[r]) cudaStreamDestroy(s->push_stream[r]);
+      if (s->ev_push[r]) cudaEventDestroy(s->ev_push[r]);
+    }
+    // nobody frees a matrix a peer still has mapped: destroy is collective while the communicator lives
+    if (g_comm.comm) {
+      Ctx& c = ctx();
+      cudaMemsetAsync(c.status.p, 0, sizeof(int), c.stream);
+      g_nccl.AllReduce(c.status.p, c.status.p, 1, ncclInt32, ncclSum, g_comm.comm, c.stream);
+      cudaStreamSynchronize(c.stream);
+    }
+  }
   delete s;
   return B200ALS_OK;
 }
@@ -1708,6 +1732,91 @@ static int exchange_chunk(b200als_session* s, int which, int ch, int n_ch, cudaS
   NC(g_nccl.GroupEnd());
   return B200ALS_OK;
 }
+// Maps the peers' factor matrices.  Collective: every rank calls it at the same point.  Falls back to NCCL (state -1)
+// unless every rank could open every handle (B200ALS_EXCHANGE=nccl forces the fallback, =p2p makes failure an error).
+static int p2p_setup(b200als_session* s) {
+  if (s->p2p_state != 0) return B200ALS_OK;
+  Ctx& c = ctx();
+  const char* ev = getenv("B200ALS_EXCHANGE");
+  const bool force_nccl = ev && !strcmp(ev, "nccl"), force_p2p = ev && !strcmp(ev, "p2p");
+  const int W = g_comm.world, me = g_comm.rank;
+  int ok = (!force_nccl && W <= b200als_session::kMaxPeers) ? 1 : 0;
+  cudaIpcMemHandle_t mine[2];
+  std::memset(mine, 0, sizeof(mine));
+  if (ok)
+    for (int w = 0; w < 2; w++)
+      if (cudaIpcGetMemHandle(&mine[w], s->fac[w].p) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+  const size_t hb = sizeof(mine);
+  DevBuf d, flag;
+  CU(d.ensure(hb * (size_t)W));
+  CU(flag.ensure(sizeof(int)));
+  CU(cudaMemcpyAsync((char*)d.p + hb * me, mine, hb, cudaMemcpyHostToDevice, c.stream));
+  NC(g_nccl.AllGather((char*)d.p + hb * me, d.p, hb, ncclChar, g_comm.comm, c.stream));
+  std::vector<cudaIpcMemHandle_t> all(2 * (size_t)W);
+  CU(cudaMemcpyAsync(all.data(), d.p, hb * (size_t)W, cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaMemcpyAsync(flag.p, &ok, sizeof(int), cudaMemcpyHostToDevice, c.stream));
+  NC(g_nccl.AllReduce(flag.p, flag.p, 1, ncclInt32, ncclMin, g_comm.comm, c.stream));
+  CU(cudaMemcpyAsync(&ok, flag.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaStreamSynchronize(c.stream));
+  if (ok) {
+    for (int r = 0; r < W && ok; r++) {
+      if (r == me) continue;
+      for (int w = 0; w < 2; w++) {
+        void* q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, all[2 * (size_t)r + w], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          ok = 0;
+          cudaGetLastError();
+          break;
+        }
+        s->peer_fac[w][r] = (float*)q;
+      }
+    }
+    CU(cudaMemcpyAsync(flag.p, &ok, sizeof(int), cudaMemcpyHostToDevice, c.stream));
+    NC(g_nccl.AllReduce(flag.p, flag.p, 1, ncclInt32, ncclMin, g_comm.comm, c.stream));
+    CU(cudaMemcpyAsync(&ok, flag.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    CU(cudaStreamSynchronize(c.stream));
+  }
+  if (!ok) {
+    for (int w = 0; w < 2; w++)
+      for (int r = 0; r < b200als_session::kMaxPeers; r++)
+        if (s->peer_fac[w][r]) { cudaIpcCloseMemHandle(s->peer_fac[w][r]); s->peer_fac[w][r] = nullptr; }
+    s->p2p_state = -1;
+    if (force_p2p) return fail(B200ALS_ECUDA, "B200ALS_EXCHANGE=p2p: peer mapping of the factor matrices failed on some rank");
+    return B200ALS_OK;
+  }
+  for (int r = 0; r < W; r++) {
+    if (r == me) continue;
+    CU(cudaStreamCreateWithFlags(&s->push_stream[r], cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&s->ev_push[r], cudaEventDisableTiming));
+  }
+  s->p2p_state = 1;
+  return B200ALS_OK;
+}
+// pushes chunk `ch` of `n_ch` of this rank's block into every peer's copy of the matrix, one copy-engine stream per
+// peer, after `ready` (the chunk's solve).  Completion is collected by p2p_join().
+static int p2p_push_chunk(b200als_session* s, int which, int ch, int n_ch, cudaEvent_t ready) {
+  const std::vector<int32_t>& ranges = s->ranges[which];
+  const int me = g_comm.rank;
+  const long long rb = ranges[3 * me], len = ranges[3 * me + 1] - rb;
+  const long long cb = rb + len * ch / n_ch, ce = rb + len * (ch + 1) / n_ch;
+  if (ce <= cb) return B200ALS_OK;
+  const size_t off = (size_t)cb * s->k, bytes = sizeof(float) * (size_t)(ce - cb) * s->k;
+  const float* src = s->fac[which].f32() + off;
+  for (int i = 1; i < g_comm.world; i++) {
+    const int r = (me + i) % g_comm.world;   // staggered start: no two ranks open on the same destination
+    CU(cudaStreamWaitEvent(s->push_stream[r], ready, 0));
+    CU(cudaMemcpyAsync(s->peer_fac[which][r] + off, src, bytes, cudaMemcpyDeviceToDevice, s->push_stream[r]));
+  }
+  return B200ALS_OK;
+}
+static int p2p_join(b200als_session* s, cudaStream_t st) {
+  for (int r = 0; r < g_comm.world; r++) {
+    if (r == g_comm.rank) continue;
+    CU(cudaEventRecord(s->ev_push[r], s->push_stream[r]));
+    CU(cudaStreamWaitEvent(st, s->ev_push[r], 0));
+  }
+  return B200ALS_OK;
+}
 __global__ void finalize_gram_kernel(double* __restrict__ G64, float* __restrict__ G, int k, double lambda) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= k * k) return;
@@ -1733,6 +1842,15 @@ static int session_half(b200als_session* s, int which, int solver, float* Yout, 
   const float* G = nullptr;
   const float* diag = nullptr;
   if (g_comm.world > 1) TRY(gather_ranges(s, which));
+  if (g_comm.world > 1 && !Yout) TRY(p2p_setup(s));
+  const bool p2p = (g_comm.world > 1 && !Yout && s->p2p_state == 1);
+  if (p2p && !implicit) {
+    // one-sided pushes need every rank to have finished its earlier writes to the matrix (set_factors, randomize, the
+    // previous half-iteration) before any peer writes into it: implicit feedback gets that from the Gram all-reduce
+    // below, explicit feedback from this one-word all-reduce
+    CU(cudaMemsetAsync(c.status.p, 0, sizeof(int), c.stream));
+    NC(g_nccl.AllReduce(c.status.p, c.status.p, 1, ncclInt32, ncclSum, g_comm.comm, c.stream));
+  }
   if (implicit) {
     if (g_comm.world > 1) {
       // each rank reduces its 1/world slice of the fixed matrix; the k x k partials are summed over NVLink
@@ -1789,12 +1907,22 @@ static int session_half(b200als_session* s, int which, int solver, float* Yout, 
       oc.reset_loss = (ch == 0);
       TRY(solve_rows<float>(c, A, X, Y, G, diag, s->k, oc));
       CU(cudaEventRecord(s->ev_chunk[ch], c.stream));
-      CU(cudaStreamWaitEvent(s->comm_stream, s->ev_chunk[ch], 0));
-      TRY(exchange_chunk(s, which, ch, n_ch, s->comm_stream));
+      if (p2p) {
+        TRY(p2p_push_chunk(s, which, ch, n_ch, s->ev_chunk[ch]));
+      } else {
+        CU(cudaStreamWaitEvent(s->comm_stream, s->ev_chunk[ch], 0));
+        TRY(exchange_chunk(s, which, ch, n_ch, s->comm_stream));
+      }
     }
     CU(cudaEventRecord(s->ev[3], c.stream));
-    CU(cudaEventRecord(s->ev_comm_done, s->comm_stream));
-    CU(cudaStreamWaitEvent(c.stream, s->ev_comm_done, 0));
+    if (p2p) {
+      // own pushes done; the loss all-reduce below completes only when every rank got here, i.e. when every push
+      // into this rank's matrix has landed
+      TRY(p2p_join(s, c.stream));
+    } else {
+      CU(cudaEventRecord(s->ev_comm_done, s->comm_stream));
+      CU(cudaStreamWaitEvent(c.stream, s->ev_comm_done, 0));
+    }
   } else {
     TRY(solve_rows<float>(c, A, X, Y, G, diag, s->k, o));
     CU(cudaEventRecord(s->ev[3], c.stream));

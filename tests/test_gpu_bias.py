@@ -39,10 +39,13 @@ def run_engine_bias(c, dt, XtX="host"):
     return Y, loss, gbb
 
 
-def tols(c, dt):
+def tols(c, dt, ref32_err=0.0):
+    """(factor tolerance, loss tolerance).  fp32: 1e-5, or three times the distance of the REFERENCE's own fp32 result
+    from its fp64 result where that is larger (the systems with the column of ones are badly conditioned in fp32:
+    the reference itself is off by up to 9e-5 there)."""
     if c["solver"] == wc.NNLS:
-        return (1e-6, 1e-8) if dt == np.float64 else (5e-2, 1e-4)
-    return (1e-9, 1e-9) if dt == np.float64 else (1e-5, 1e-5)
+        return (1e-6, 1e-8) if dt == np.float64 else (max(5e-4, 3 * ref32_err), 1e-4)
+    return (1e-9, 1e-9) if dt == np.float64 else (max(1e-5, 3 * ref32_err), 1e-5)
 
 
 @pytest.mark.parametrize("name", BIAS_CASES)
@@ -53,8 +56,8 @@ def test_bias_half_iteration_vs_reference_golden(name, dt, xtx, bias_cases, gold
     if xtx == "engine" and c["feedback"] != "implicit":
         pytest.skip("XtX only exists for implicit feedback")
     Y, loss, gbb = run_engine_bias(c, dt, xtx)
-    tol_y, tol_l = tols(c, dt)
     ref = golden_bias[name + "/Y_f64"]
+    tol_y, tol_l = tols(c, dt, relF(golden_bias[name + "/Y_f32"], ref))
     assert relF(Y, ref) < tol_y, (relF(Y, ref), relF(golden_bias[name + "/Y_f32"], ref))
     assert abs(loss - float(golden_bias[name + "/loss_f64"])) <= tol_l * abs(loss)
     if c["with_biases"]:   # the row of ones of Y is not written
@@ -79,7 +82,7 @@ def test_global_bias_base_is_reused_when_not_initialised(bias_cases, golden_bias
     Y1, Y2 = c["Y0"].astype(np.float64).copy(), c["Y0"].astype(np.float64).copy()
     l1 = als_implicit(c["ptr"], c["idx"], c["val"], X, Y1, c["lam"], c["solver"], global_bias=1e-9)
     l2 = als_implicit(c["ptr"], c["idx"], c["val"], X, Y2, c["lam"], c["solver"])
-    assert np.array_equal(Y1, Y2) and l1 == l2
+    assert np.array_equal(Y1, Y2) and abs(l1 - l2) <= 1e-13 * l2   # rows are summed in ticket order
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
@@ -91,9 +94,14 @@ def test_implicit_cg_with_biases_is_solved_not_rejected(dt, is_last, bias_cases)
     c = dict(bias_cases["bias_ml100k_item_implicit_chol" if is_last else "bias_ml100k_user_implicit_chol"])
     c["solver"], c["cg_steps"] = wc.CG, 3
     Y, loss, _ = run_engine_bias(c, dt)
-    Yo, lo, _ = run_oracle_bias(c, dt, n_threads=oracle.max_threads())
-    assert relF(Y, Yo) < (1e-9 if dt == np.float64 else 1e-5)
-    assert abs(loss - lo) <= (1e-9 if dt == np.float64 else 1e-5) * abs(lo)
+    Yo, lo, _ = run_oracle_bias(c, np.float64, n_threads=oracle.max_threads())
+    if dt == np.float64:
+        tol_y = tol_l = 1e-9
+    else:   # yardstick: how far the fp32 oracle lands from the fp64 oracle on this (badly conditioned) system
+        Y32, l32, _ = run_oracle_bias(c, np.float32, n_threads=oracle.max_threads())
+        tol_y, tol_l = max(1e-5, 3 * relF(Y32, Yo)), max(1e-5, 3 * abs(l32 - lo) / abs(lo))
+    assert relF(Y, Yo) < tol_y
+    assert abs(loss - lo) <= tol_l * abs(lo)
     if dt == np.float64:
         c["cg_steps"] = 60
         Ycg, _, _ = run_engine_bias(c, dt)

@@ -52,7 +52,12 @@ def test_f64_kernels_vs_reference_golden(name, cases, golden_half):
 def test_f32_engine_vs_reference_golden(name, xtx, cases, golden_half):
     Y, loss = run_stateless(cases[name], np.float32, XtX=xtx)
     ref = golden_half[name + "/Y_f64"]
-    assert relF(Y, ref) < TOL_F32, (relF(Y, ref), relF(golden_half[name + "/Y_f32"], ref))
+    tol = TOL_F32
+    if cases[name]["solver"] == wc.NNLS:
+        # an iteration stopped at a relative coordinate step of 1e-4 (nnls.hpp:44): the reference's own fp32 run is
+        # 1.1e-5 away from its fp64 run here; allow three times that
+        tol = max(1e-4, 3 * relF(golden_half[name + "/Y_f32"], ref))
+    assert relF(Y, ref) < tol, (relF(Y, ref), relF(golden_half[name + "/Y_f32"], ref))
     assert abs(loss - float(golden_half[name + "/loss_f64"])) <= TOL_F32 * abs(loss)
     empty = np.diff(cases[name]["ptr"]) == 0
     assert np.all(Y[empty] == 0)
@@ -232,9 +237,10 @@ def test_unsupported_options_fail_loudly(cases):
     with pytest.raises(L.B200AlsError) as e:
         als_implicit(c["ptr"], c["idx"], c["val"], c["X"], c["Y0"].copy(), 0.1, 7)
     assert e.value.code == L.EINVAL
-    with pytest.raises(L.B200AlsError) as e:
-        als_implicit(c["ptr"], c["idx"], c["val"], c["X"], c["Y0"].copy(), 0.1, L.CHOLESKY, with_user_item_bias=True)
-    assert e.value.code == L.EUNSUPPORTED
+    with pytest.raises(L.B200AlsError) as e:   # bias layouts need the two extra rows
+        als_implicit(c["ptr"], c["idx"], c["val"], c["X"][:, :1].copy(), c["Y0"][:, :1].copy(), 0.1, L.CHOLESKY,
+                     with_user_item_bias=True)
+    assert e.value.code == L.EINVAL
 
 
 @pytest.mark.parametrize("name", ["synth_ragged_implicit_cg_k128", "synth_long_implicit_cg_k128", "synth_explicit_cg_k128",
