@@ -280,6 +280,7 @@ def main():
         for kk, v in s.last_timing().items():
             parts[kk] += v
     clocks = sampler.stop()
+    exchange = s.exchange_mode()
     parallel.barrier()
     launches = int(L.lib().b200als_launch_count() - launches0) - args.steps   # minus the re-initialisation launches
     ms_total = ms_sum
@@ -370,7 +371,9 @@ def main():
                "config": {"workload": "%s: %dx%d CSR, %d nnz/row, WRMF %s rank=%d %s lambda=%g, user half-iteration"
                                       % (args.workload, n_user, n_item, nnz, feedback, k,
                                          "CG(%d)" % cg if solver == 1 else "Cholesky", lam),
-                          "parallelism": "rows sharded over %d GPU(s), NCCL exchange of updated factors" % world,
+                          "parallelism": "rows sharded over %d GPU(s), exchange of updated factors: %s" % (
+                              world, {"none": "none (single GPU)", "p2p": "peer-memory pushes over NVLink (copy engines)",
+                                      "nccl": "grouped NCCL broadcasts"}[exchange]),
                           "l2": "inputs larger than L2 (CSR %.1f GB + factors %.1f GB per step vs 126 MB L2); no flush needed"
                                 % (n_local * nnz * 8 / 1e9, (n_local + n_item) * k * 4 / 1e9),
                           "kernel": args.kernel, "stage": args.stage, "ctas": args.ctas, "loss": loss},

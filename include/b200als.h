@@ -233,6 +233,10 @@ int b200als_comm_unique_id(void* id_out /* 128 bytes */);
 int b200als_comm_init(const void* id, int rank, int world_size);
 int b200als_comm_destroy(void);
 int b200als_comm_info(int* rank, int* world_size);
+/* How the last sharded half-iteration exchanged the solved rows: 0 = no exchange yet / single GPU, 1 = peer-memory
+ * pushes (CUDA IPC mappings of the peers' factor matrices, copy engines over NVLink), 2 = grouped NCCL broadcasts
+ * (the fallback when the peers cannot be mapped; B200ALS_EXCHANGE=nccl|p2p in the environment forces either). */
+int b200als_exchange_mode(b200als_session* s, int* mode);
 /* Tell a session which global column range [begin, end) of each orientation this rank owns. */
 int b200als_set_shard(b200als_session* s, int which, int32_t begin, int32_t end);
 

@@ -76,6 +76,7 @@ _PROTOS = {
     "b200als_half_iteration": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "b200als_fit": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.POINTER(C.c_int)]),
     "b200als_transform": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
+    "b200als_exchange_mode": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "b200als_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                       C.POINTER(C.c_float)]),
     "b200als_comm_unique_id": (C.c_int, [C.c_void_p]),

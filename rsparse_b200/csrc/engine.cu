@@ -1594,6 +1594,12 @@ extern "C" int b200als_destroy(b200als_session* s) {
   return B200ALS_OK;
 }
 
+extern "C" int b200als_exchange_mode(b200als_session* s, int* mode) {
+  if (!s || !mode) return fail(B200ALS_EINVAL, "bad argument");
+  *mode = (g_comm.world <= 1 || s->p2p_state == 0) ? 0 : (s->p2p_state == 1 ? 1 : 2);
+  return B200ALS_OK;
+}
+
 extern "C" int b200als_set_shard(b200als_session* s, int which, int32_t begin, int32_t end) {
   if (!s || which < 0 || which > 1) return fail(B200ALS_EINVAL, "bad argument");
   const int32_t n = (which == B200ALS_ITEMS) ? s->n_item : s->n_user;

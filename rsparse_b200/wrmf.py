@@ -128,6 +128,12 @@ class Session:
         L.check(L.lib().b200als_transform(self._h, L.vp(out), C.byref(loss)))
         return out, loss.value
 
+    def exchange_mode(self):
+        """'none' (single GPU / nothing exchanged yet), 'p2p' (peer-memory pushes) or 'nccl' (broadcast fallback)."""
+        m = C.c_int(0)
+        L.check(L.lib().b200als_exchange_mode(self._h, C.byref(m)))
+        return ("none", "p2p", "nccl")[m.value]
+
     def last_timing(self):
         t = [C.c_float(0) for _ in range(4)]
         L.check(L.lib().b200als_last_timing(self._h, *[C.byref(x) for x in t]))

@@ -35,12 +35,16 @@ def main():
         chk = float(np.abs(Yk.astype(np.float64)).sum())
         assert parallel.max_over_ranks(chk) == -parallel.max_over_ranks(-chk), "ranks disagree on the exchanged factors"
         results[kernel] = (loss1, loss2, Yk, s.last_timing())
+        mode = s.exchange_mode()
+        want = os.environ.get("B200ALS_EXCHANGE")
+        assert mode in ("p2p", "nccl") and (want is None or mode == want), (mode, want)
         s.close()
     # explicit feedback (no Gram all-reduce in front of the exchange)
     se = Session.synthetic(e - b, b, n_user, n_item, nnz, 43, k, "explicit", L.CONJUGATE_GRADIENT, 3, True, lam, 0)
     se.set_factors(L.ITEMS, X)
     se.set_factors(L.USERS, Y0)
     le = se.half_iteration(L.USERS)
+    mode = se.exchange_mode()
     Ye = se.get_factors(L.USERS)
     chk = float(np.abs(Ye.astype(np.float64)).sum())
     assert parallel.max_over_ranks(chk) == -parallel.max_over_ranks(-chk), "ranks disagree (explicit)"
@@ -63,8 +67,8 @@ def main():
         Yo = Y0.copy()
         loe = oracle.als_explicit(ptr, idx, v64, X, Yo, cnt, lam, wc.CG, 3, True, oracle.max_threads())
         rel = np.linalg.norm(Ye.astype(np.float64) - Yo) / np.linalg.norm(Yo)
-        print("explicit world %d: relF %.2e loss %.7f oracle %.7f exchange=%s" % (world, rel, le, loe,
-                                                                                 os.environ.get("B200ALS_EXCHANGE", "auto")))
+        print("explicit world %d: relF %.2e loss %.7f oracle %.7f exchange=%s (requested %s)" % (
+            world, rel, le, loe, mode, os.environ.get("B200ALS_EXCHANGE", "auto")))
         assert rel < 2e-5 and abs(le - loe) < 1e-5 * loe
         print("MULTIGPU_OK world=%d" % world)
     parallel.barrier()
