@@ -39,11 +39,12 @@ WORKLOADS = {
     "c3-tiny": (100_000, 50_000, 80, 128, 3, 0.1),         # CPU-side dry runs
     "c4": (10_000_000, 1_000_000, 80, 128, 3, 0.1),        # BASELINE configs[3]: explicit feedback (MMMF)
     "c2": (1_000_000, 100_000, 50, 64, 3, 0.1),            # BASELINE configs[1]: implicit, rank 64, Cholesky
+    "c3-chol": (1_000_000, 1_000_000, 80, 128, 3, 0.1),    # transform_-shaped: C3's row shape solved by Cholesky (a10)
 }
 # side workload "topk": MatrixFactorizationRecommender$predict's top_product
 TOPK = dict(n_user=65536, n_item=1_000_000, rank=128, k=10, nnz=80)
 # (feedback, solver) per workload; everything not listed is implicit CG
-WORKLOAD_MODE = {"c4": ("explicit", 1), "c2": ("implicit", 0)}
+WORKLOAD_MODE = {"c4": ("explicit", 1), "c2": ("implicit", 0), "c3-chol": ("implicit", 0)}
 BYTES_PER_ROW = lambda n, k: 4 * n * k + 8 * n + 4 + 4 * k + 4 * k   # 42,628 at n=80, k=128
 FLOPS_PER_ROW = lambda n, k, s: (s + 1) * (4 * n * k + 2 * k * k)
 
@@ -216,9 +217,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("B200ALS_WORKLOAD", "c3"), choices=sorted(WORKLOADS) + ["topk"])
-    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 resident full-XtX, 3 resident eigenbasis")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic; CG: 2 resident full-XtX, 3 resident eigenbasis; Cholesky: 4 row-per-thread (default), 5 tile")
     ap.add_argument("--stage", type=int, default=0, help="resident-kernel tile staging: 0 default, 1 cp.async.bulk, 2 cp.async")
-    ap.add_argument("--ctas", type=int, default=0, help="resident-kernel CTAs per SM: 0 default, 3, 4")
+    ap.add_argument("--ctas", type=int, default=0, help="CTAs per SM the kernel is built for: CG resident 0/3/4, rank-128 row-per-thread Cholesky 0/2/3")
     ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="rows in the CPU baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
@@ -293,7 +294,9 @@ def main():
     achieved = n_local * BYTES_PER_ROW(nnz, k) / (solve_ms / 1e3) / 1e9
     if solver == L.CHOLESKY:   # compute-bound path: 2nk^2 + 2nk + k^3/3 + 2k^2 flop per row
         fl = 2 * nnz * k * k + 2 * nnz * k + k ** 3 / 3 + 2 * k * k
-        roofline = {"bound": "tensor", "kernel": "als_chol_tile_kernel (fp32 FFMA2 Gram + smem Cholesky; no tensor cores yet)",
+        roofline = {"bound": "tensor", "kernel": ("als_chol_rows_kernel (row-per-thread panel Cholesky, fp32 FFMA2 Gram; no tensor cores yet)"
+                                                 if args.kernel != 5 else
+                                                 "als_chol_tile_kernel (fp32 FFMA2 Gram + register-block Cholesky; no tensor cores yet)"),
                     "achieved": n_local * fl / (solve_ms / 1e3) / 1e12, "peak": None, "unit": "TFLOP/s", "frac": None,
                     "traffic": None, "kernel_ms": solve_ms}
     else:

@@ -165,12 +165,13 @@ typedef struct b200als_options {
   int cg_steps;        /* R default 3                                                            */
   int dynamic_lambda;  /* explicit feedback only (wrmf_explicit.hpp:78)                          */
   double lambda;
-  int kernel;          /* CG kernel choice: 0 = auto; 1 = generic streaming kernel; 2 = register-resident
-                          kernel with the full XtX (rank 128 only); 3 = register-resident kernel in the
-                          eigenbasis of XtX even for small inputs (implicit, rank 128 only)       */
-  int reserved[7];     /* reserved[0]: tile staging of the register-resident kernel -- 0 default, 1 cp.async.bulk
-                          (TMA engine), 2 cp.async (LDGSTS); reserved[1]: CTAs/SM the kernel is built for
-                          (0 default, 3, 4); the rest must be 0                                       */
+  int kernel;          /* kernel choice: 0 = auto; 1 = generic streaming kernels (CG and Cholesky); CG only: 2 = register-
+                          resident kernel with the full XtX (rank 128), 3 = register-resident kernel in the eigenbasis of
+                          XtX even for small inputs (implicit, rank 128); Cholesky only (rank 64 / 128): 4 = row-per-thread
+                          panel kernel (the default), 5 = its predecessor, the 16 x 16 register-block kernel            */
+  int reserved[7];     /* reserved[0]: tile staging of the register-resident CG kernel -- 0 default, 1 cp.async.bulk
+                          (TMA engine), 2 cp.async (LDGSTS); reserved[1]: CTAs/SM the kernel is built for (CG resident
+                          kernel: 0 default, 3, 4; rank-128 row-per-thread Cholesky: 0 default, 2, 3); the rest must be 0 */
 } b200als_options;
 
 void b200als_default_options(b200als_options* o);

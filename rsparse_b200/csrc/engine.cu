@@ -21,6 +21,7 @@
 
 #include "../../include/b200als.h"
 #include "als_chol_tile.cuh"
+#include "als_chol_rows.cuh"
 #include "als_generic.cuh"
 #include "als_resident.cuh"
 #include "eig.cuh"
@@ -523,7 +524,7 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
       tiled = (o.solver == B200ALS_CHOLESKY) && (k == 64 || k == 128) && o.kernel != 1 && !sub_range && !biased;
     if (!tiled) return run_generic_chol(nullptr, 0);
     if constexpr (sizeof(T) == 4) {
-      // rows with 1..80 non-zeros: tile kernel; longer rows: generic kernel; empty rows: zero
+      // rows with 1..80 non-zeros: row-per-thread (or tile) kernel; longer rows: generic kernel; empty rows: zero
       TRY(classify_rows(c, A));
       if (A.n_empty > 0) {
         zero_empty_rows_kernel<T><<<(unsigned)(((long long)A.n_cols * k + 255) / 256), 256, 0, c.stream>>>(P.ptr, A.n_cols, k, Y);
@@ -532,19 +533,28 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
       if (A.n_short > 0) {
         P.row_list = A.all_short ? nullptr : A.short_list.i32();
         P.n_list = A.n_short;
-        const size_t smem = (k == 64) ? sizeof(CholTileSmem<64>) : sizeof(CholTileSmem<128>);
+        // default (and kernel = 4): row-per-thread panel kernel (als_chol_rows.cuh), measured 2.0x (rank 64) / 1.6x
+        // (rank 128) faster than its predecessor, the 16 x 16 register-block kernel, which stays selectable as kernel = 5
+        const bool rows_kernel = (o.kernel != 5);
         // persistent CTAs: exactly as many as are co-resident (registers AND shared memory), else a second wave
-        int per_sm = 1;
-        if (k == 64) {
-          CU(cudaFuncSetAttribute(als_chol_tile_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, als_chol_tile_kernel<64>, kCholThreads, smem));
+        int per_sm = 1, grid = 1;
+        auto launch = [&](auto kern, int threads, size_t smem) -> cudaError_t {
+          cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          if (e != cudaSuccess) return e;
+          e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+          if (e != cudaSuccess) return e;
+          grid = std::min(c.sm_count * std::max(1, per_sm), A.n_short);
+          kern<<<grid, threads, smem, c.stream>>>(P);
+          return cudaSuccess;
+        };
+        if (rows_kernel) {
+          if (k == 64) CU(launch(als_chol_rows_kernel<64, 8>, 64, sizeof(CholRowsSmem<64>)));
+          else if (o.ctas == 3) CU(launch(als_chol_rows_kernel<128, 3>, 128, sizeof(CholRowsSmem<128>)));
+          else CU(launch(als_chol_rows_kernel<128, 2>, 128, sizeof(CholRowsSmem<128>)));
         } else {
-          CU(cudaFuncSetAttribute(als_chol_tile_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, als_chol_tile_kernel<128>, kCholThreads, smem));
+          if (k == 64) CU(launch(als_chol_tile_kernel<64>, kCholThreads, sizeof(CholTileSmem<64>)));
+          else CU(launch(als_chol_tile_kernel<128>, kCholThreads, sizeof(CholTileSmem<128>)));
         }
-        const int grid = std::min(c.sm_count * std::max(1, per_sm), A.n_short);
-        if (k == 64) als_chol_tile_kernel<64><<<grid, kCholThreads, smem, c.stream>>>(P);
-        else als_chol_tile_kernel<128><<<grid, kCholThreads, smem, c.stream>>>(P);
         LAUNCHED(); CU(cudaGetLastError());
         sum_partials_kernel<<<1, 32, 0, c.stream>>>(P.loss_partials, grid, c.loss_acc.f64(), 1);
         LAUNCHED(); CU(cudaGetLastError());

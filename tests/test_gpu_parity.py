@@ -63,11 +63,11 @@ def test_f32_engine_vs_reference_golden(name, xtx, cases, golden_half):
     assert np.all(Y[empty] == 0)
 
 
-def _session_for(c, kernel, solver=None, stage=0):
+def _session_for(c, kernel, solver=None, stage=0, ctas=0):
     n_src, k = c["X"].shape
     n_tgt = c["Y0"].shape[0]
     s = Session(None, (c["ptr"], c["idx"], c["val"]), n_tgt, n_src, k, c["feedback"], c["solver"] if solver is None else solver,
-                c["cg_steps"], c["dynamic_lambda"], c["lam"], kernel, stage)
+                c["cg_steps"], c["dynamic_lambda"], c["lam"], kernel, stage, ctas)
     s.set_factors(L.ITEMS, c["X"])
     s.set_factors(L.USERS, c["Y0"])
     return s
@@ -263,12 +263,17 @@ def test_pipelined_stateless_path(name, vals, cases, golden_half, monkeypatch):
         assert np.all(Y[np.diff(c["ptr"]) == 0] == 0)
 
 
-@pytest.mark.parametrize("name,kernel", [("synth_implicit_cg_k128", 0), ("synth_ragged_implicit_cg_k128", 0),
-                                         ("synth_explicit_cg_k128", 0), ("synth_ragged_explicit_cg_k64", 0),
-                                         ("synth_long_implicit_cg_k128", 0), ("synth_implicit_chol_k64", 1)])
-def test_tiled_cholesky_vs_oracle(name, kernel, cases):
-    """The rank-64/128 tile Cholesky kernel (rows <= 80 nnz; longer and empty rows through the generic kernel)
-    against the fp64 oracle, implicit and explicit, and against the generic kernel (kernel=1)."""
+_CHOL_CASES = ["synth_implicit_cg_k128", "synth_ragged_implicit_cg_k128", "synth_explicit_cg_k128", "synth_ragged_explicit_cg_k64",
+               "synth_long_implicit_cg_k128", "synth_implicit_chol_k64"]
+
+
+@pytest.mark.parametrize("name,kernel,ctas", [(n, 0, 0) for n in _CHOL_CASES] + [(n, 5, 0) for n in _CHOL_CASES] +
+                         [("synth_implicit_cg_k128", 4, 3), ("synth_ragged_implicit_cg_k128", 4, 3), ("synth_explicit_cg_k128", 4, 3),
+                          ("synth_implicit_chol_k64", 1, 0)])
+def test_tiled_cholesky_vs_oracle(name, kernel, ctas, cases):
+    """The rank-64/128 Cholesky kernels for rows <= 80 nnz (longer and empty rows go through the generic kernel) against
+    the fp64 oracle, implicit and explicit: the row-per-thread panel kernel (default; kernel=4 with the 3-CTA/SM build of
+    rank 128), its predecessor the register-block tile kernel (kernel=5), and the generic kernel (kernel=1)."""
     c = dict(cases[name])
     X64, Y64 = c["X"].astype(np.float64), c["Y0"].astype(np.float64).copy()
     if c["feedback"] == "implicit":
@@ -278,7 +283,7 @@ def test_tiled_cholesky_vs_oracle(name, kernel, cases):
         # a session counts cnt_X itself (nnz per row of the fixed matrix, R/model_WRMF.R:305-315)
         cnt = np.bincount(c["idx"], minlength=X64.shape[0]).astype(np.float64)
         lo = oracle.als_explicit(c["ptr"], c["idx"], c["val"], X64, Y64, cnt, c["lam"], wc.CHOL, 3, c["dynamic_lambda"], 2)
-    s = _session_for(c, kernel, solver=wc.CHOL)
+    s = _session_for(c, kernel, solver=wc.CHOL, ctas=ctas)
     loss = s.half_iteration(L.USERS)
     Y = s.get_factors(L.USERS)
     s.close()
