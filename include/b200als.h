@@ -171,7 +171,7 @@ typedef struct b200als_options {
                           panel kernel (the default), 5 = its predecessor, the 16 x 16 register-block kernel            */
   int reserved[7];     /* reserved[0]: tile staging of the register-resident CG kernel -- 0 default, 1 cp.async.bulk
                           (TMA engine), 2 cp.async (LDGSTS); reserved[1]: CTAs/SM the kernel is built for (CG resident
-                          kernel: 0 default, 3, 4; rank-128 row-per-thread Cholesky: 0 default, 2, 3); the rest must be 0 */
+                          kernel: 0 default, 3, 4; rank-128 row-per-thread Cholesky: 0 default (= 3), 2, 3); the rest must be 0 */
 } b200als_options;
 
 void b200als_default_options(b200als_options* o);

@@ -44,7 +44,8 @@ struct alignas(16) CholRowsSmem {
   int fail;
 };
 
-// kCtas: resident CTAs per SM the register allocation is sized for (rank 64: 8; rank 128: 2 = 226 registers, or 3 = 168)
+// kCtas: resident CTAs per SM the register allocation is sized for (rank 64: 8; rank 128: 3 = 168 registers with 56 B of
+// cold spills, the default -- 12 instead of 8 warps per SM is worth 27 % -- or 2 = 226 registers)
 template <int K, int kCtas>
 __global__ void __launch_bounds__(K, kCtas) als_chol_rows_kernel(SolveParams<float> P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -268,11 +268,11 @@ _CHOL_CASES = ["synth_implicit_cg_k128", "synth_ragged_implicit_cg_k128", "synth
 
 
 @pytest.mark.parametrize("name,kernel,ctas", [(n, 0, 0) for n in _CHOL_CASES] + [(n, 5, 0) for n in _CHOL_CASES] +
-                         [("synth_implicit_cg_k128", 4, 3), ("synth_ragged_implicit_cg_k128", 4, 3), ("synth_explicit_cg_k128", 4, 3),
+                         [("synth_implicit_cg_k128", 4, 2), ("synth_ragged_implicit_cg_k128", 4, 2), ("synth_explicit_cg_k128", 4, 2),
                           ("synth_implicit_chol_k64", 1, 0)])
 def test_tiled_cholesky_vs_oracle(name, kernel, ctas, cases):
     """The rank-64/128 Cholesky kernels for rows <= 80 nnz (longer and empty rows go through the generic kernel) against
-    the fp64 oracle, implicit and explicit: the row-per-thread panel kernel (default; kernel=4 with the 3-CTA/SM build of
+    the fp64 oracle, implicit and explicit: the row-per-thread panel kernel (default; kernel=4 with the 2-CTA/SM build of
     rank 128), its predecessor the register-block tile kernel (kernel=5), and the generic kernel (kernel=1)."""
     c = dict(cases[name])
     X64, Y64 = c["X"].astype(np.float64), c["Y0"].astype(np.float64).copy()
