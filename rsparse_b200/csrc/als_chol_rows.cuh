@@ -24,15 +24,18 @@
 // Algorithmic work per row: 2nK^2 / 2 .. 2nK^2 (Gram, triangular per warp) + K^3/3 flop; bytes as the CG path.
 #pragma once
 #include "als_chol_tile.cuh"
+#include "gram_tc.cuh"
 
 namespace b200als {
 
 template <int K>
-struct alignas(16) CholRowsSmem {
+struct alignas(128) CholRowsSmem {
   static constexpr int LDT = K + 4;      // rows stay 16-byte aligned, consecutive rows 4 banks apart
   union {
-    float tile[kCholMaxN * K];           // gathered rows (Gram phase); 16-byte cp.async destinations
+    float tile[kCholMaxN * K];           // gathered rows (FFMA Gram); 16-byte cp.async destinations
     float Lt[K * LDT];                   // Lt[j][c] = L[c][j] for c >= j (factorisation, back substitution)
+    unsigned char op[4][(K == kTcK) ? kTcTileBytes : 16];   // tensor-core Gram (rank 128): tiles A hi/lo (= w x), B hi/lo (= x),
+                                         // 32 gathered rows each, K-major core-matrix layout of gram_tc.cuh
   };
   alignas(16) float D[4][8];             // diagonal 4 x 4 block, row i = [d_i0 .. d_i3, rhs_i, -, -, -]
   float cs[2][kCholMaxN];                // confidences / ratings of the row, double buffered (next row lands by cp.async)
@@ -41,14 +44,21 @@ struct alignas(16) CholRowsSmem {
   alignas(16) float zz[K];               // z = L^-1 rhs, then y
   float part[K / 32][32];                // back substitution: per-warp partial sums of the solved part
   alignas(8) double red[32];
+  alignas(8) uint64_t mma_done;          // tensor-core Gram: the chunk's MMAs have completed (tcgen05.commit)
+  uint32_t tmem_base;
   int fail;
 };
 
 // kCtas: resident CTAs per SM the register allocation is sized for (rank 64: 8; rank 128: 3 = 168 registers with 56 B of
 // cold spills, the default -- 12 instead of 8 warps per SM is worth 27 % -- or 2 = 226 registers)
-template <int K, int kCtas>
+// kTc (rank 128 only): the per-row Gram X_nnz diag(w) X_nnz' on tcgen05 (3xTF32, one 128 x 128 TMEM accumulator) instead of
+// the FFMA loop: the gathered rows go global -> registers -> transposed hi/lo operand tiles (the staging of gram_tc.cuh
+// with a weighted copy for the M side), one thread issues 3 MMAs per 8 gathered rows, and `tcgen05.ld.32x32b` hands
+// thread r row r of the result -- the layout the factorisation below works in.
+template <int K, int kCtas, bool kTc = false>
 __global__ void __launch_bounds__(K, kCtas) als_chol_rows_kernel(SolveParams<float> P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  static_assert(!kTc || K == kTcK, "tensor-core Gram: rank 128 only");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   using SM = CholRowsSmem<K>;
   SM& S = *reinterpret_cast<SM*>(smem_raw);
   constexpr int LDT = SM::LDT;
@@ -60,6 +70,21 @@ __global__ void __launch_bounds__(K, kCtas) als_chol_rows_kernel(SolveParams<flo
   const bool implicit = (P.feedback == 0);
   const int total = P.n_list_dev ? __ldg(P.n_list_dev) : P.n_list;
   double cta_loss = 0.0;
+  uint32_t tmem = 0, mma_phase = 0;
+  if constexpr (kTc) {
+    if (tid == 0) {
+      mbar_init(&S.mma_done, 1);
+      mbar_fence_init();
+    }
+    if (warp == 0) {   // one 128-lane x 128-column fp32 accumulator; 3 CTAs/SM x 128 <= 512 TMEM columns
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tmem = S.tmem_base;
+  }
   // Software pipeline of the CSR metadata: the row pointers of row i+2 are loaded (pinned in program order) during
   // row i, the indices / values of row i+1 travel global -> shared by 4-byte cp.async during row i, next to its tile.
   auto row_id = [&](int tt) -> int { return P.row_list ? __ldg(P.row_list + tt) : tt + P.row_begin; };
@@ -94,50 +119,171 @@ __global__ void __launch_bounds__(K, kCtas) als_chol_rows_kernel(SolveParams<flo
     __syncthreads();   // previous row fully consumed; this row's indices / values (landed last iteration) visible
     fetch_meta(buf ^ 1, pB, nB);
     if (tid == 0) S.fail = 0;
-    for (int e = tid; e < n * NB4; e += K) {
-      const int j = e / NB4, c4 = e - j * NB4;
-      cp_async_16(&S.tile[j * K + c4 * 4], P.X + (size_t)s_idx[j] * K + c4 * 4);
+    if constexpr (!kTc) {
+      for (int e = tid; e < n * NB4; e += K) {
+        const int j = e / NB4, c4 = e - j * NB4;
+        cp_async_16(&S.tile[j * K + c4 * 4], P.X + (size_t)s_idx[j] * K + c4 * 4);
+      }
     }
     // ---- while the tile is in flight: row r of XtX (implicit) or lambda_u on the diagonal (explicit) -------------
     const float lam_use = implicit ? 0.0f : (float)(P.lambda * (P.dynamic_lambda ? (double)(float)n : 1.));
     float2 a[K / 2];   // a[i] = columns (2i, 2i+1) of row r; after panel p: columns (4p + 2i, 4p + 2i + 1)
-#pragma unroll
-    for (int c4 = 0; c4 < NB4; c4++) {
-      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (implicit) {
-        // XtX is symmetric: row r is read as column r, so that the 32 lanes of a warp read 32 consecutive floats
-        if (4 * c4 <= wmax) {
-          g.x = __ldg(P.G + (size_t)(4 * c4 + 0) * K + r);
-          g.y = __ldg(P.G + (size_t)(4 * c4 + 1) * K + r);
-          g.z = __ldg(P.G + (size_t)(4 * c4 + 2) * K + r);
-          g.w = __ldg(P.G + (size_t)(4 * c4 + 3) * K + r);
+    auto init_a = [&]() {
+  #pragma unroll
+      for (int c4 = 0; c4 < NB4; c4++) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (implicit) {
+          // XtX is symmetric: row r is read as column r, so that the 32 lanes of a warp read 32 consecutive floats
+          if (4 * c4 <= wmax) {
+            g.x = __ldg(P.G + (size_t)(4 * c4 + 0) * K + r);
+            g.y = __ldg(P.G + (size_t)(4 * c4 + 1) * K + r);
+            g.z = __ldg(P.G + (size_t)(4 * c4 + 2) * K + r);
+            g.w = __ldg(P.G + (size_t)(4 * c4 + 3) * K + r);
+          }
+        } else {
+          if (4 * c4 + 0 == r) g.x = lam_use;
+          if (4 * c4 + 1 == r) g.y = lam_use;
+          if (4 * c4 + 2 == r) g.z = lam_use;
+          if (4 * c4 + 3 == r) g.w = lam_use;
         }
-      } else {
-        if (4 * c4 + 0 == r) g.x = lam_use;
-        if (4 * c4 + 1 == r) g.y = lam_use;
-        if (4 * c4 + 2 == r) g.z = lam_use;
-        if (4 * c4 + 3 == r) g.w = lam_use;
+        a[2 * c4] = make_float2(g.x, g.y);
+        a[2 * c4 + 1] = make_float2(g.z, g.w);
       }
-      a[2 * c4] = make_float2(g.x, g.y);
-      a[2 * c4 + 1] = make_float2(g.z, g.w);
-    }
+    };
+    if constexpr (!kTc) init_a();   // FFMA Gram: overlaps the tile's flight; tensor-core Gram: after the MMAs (registers)
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    // ---- Gram + rhs: a[c] += (w_j x_j[r]) x_j[c],  b_r += c_j x_j[r] ----------------------------------------------
     float br = 0.0f;
-#pragma unroll 2
-    for (int j = 0; j < n; j++) {
-      const float xr = S.tile[j * K + r];
-      const float cj = s_cs[j];
-      const float wx = implicit ? xr * (cj - 1.0f) : xr;
-      br = fmaf(cj, xr, br);
-      const float2 w2 = make_float2(wx, wx);
+    if constexpr (kTc) {
+      // ---- Gram on the tensor core, 32 gathered rows per chunk ----------------------------------------------------
+      const int n_chunks = (n + kTcRows - 1) / kTcRows;
+      constexpr int kMaxChunks = (kCholMaxN + kTcRows - 1) / kTcRows;   // 3
+      // all gathered rows of this warp's 4-row groups are requested up front: ONE memory round trip per solved row
+      float4 vv[kMaxChunks][kTcRows / 16][4];
 #pragma unroll
-      for (int c4 = 0; c4 < NB4; c4++) {
-        if (4 * c4 > wmax) break;   // warp-uniform
-        const float4 v = *reinterpret_cast<const float4*>(&S.tile[j * K + 4 * c4]);
-        a[2 * c4] = __ffma2_rn(w2, make_float2(v.x, v.y), a[2 * c4]);
-        a[2 * c4 + 1] = __ffma2_rn(w2, make_float2(v.z, v.w), a[2 * c4 + 1]);
+      for (int ch = 0; ch < kMaxChunks; ch++)
+#pragma unroll
+        for (int g = 0; g < kTcRows / 16; g++)
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) {
+            const int j = ch * kTcRows + (warp + 4 * g) * 4 + kk;
+            vv[ch][g][kk] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < n) vv[ch][g][kk] = ldg_f4(P.X + (size_t)s_idx[j] * K + lane * 4);
+          }
+#pragma unroll
+      for (int ch = 0; ch < kMaxChunks; ch++) {
+        if (ch >= n_chunks) break;   // CTA-uniform
+        const int jbase = ch * kTcRows;
+        // stage: this warp transposes the 4-row groups {warp, warp + 4} of the chunk (cf. gram_tc_kernel)
+#pragma unroll
+        for (int g = 0; g < kTcRows / 16; g++) {
+          const int kb = warp + 4 * g;
+          const float4 (&v)[4] = vv[ch][g];
+          float wv[4];
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) {
+            const int j = jbase + kb * 4 + kk;
+            wv[kk] = (j < n) ? (implicit ? (s_cs[j] - 1.0f) : 1.0f) : 0.f;
+          }
+          const float col[4][4] = {{v[0].x, v[1].x, v[2].x, v[3].x}, {v[0].y, v[1].y, v[2].y, v[3].y},
+                                   {v[0].z, v[1].z, v[2].z, v[3].z}, {v[0].w, v[1].w, v[2].w, v[3].w}};
+#pragma unroll
+          for (int jj = 0; jj < 4; jj++) {
+            const int m = 4 * lane + jj;   // feature
+            float4 bh, bl, ah, al;
+            const float x0 = col[jj][0], x1 = col[jj][1], x2 = col[jj][2], x3 = col[jj][3];
+            const float y0 = x0 * wv[0], y1 = x1 * wv[1], y2 = x2 * wv[2], y3 = x3 * wv[3];
+            bh.x = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u); bl.x = x0 - bh.x;
+            bh.y = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u); bl.y = x1 - bh.y;
+            bh.z = __uint_as_float(__float_as_uint(x2) & 0xFFFFE000u); bl.z = x2 - bh.z;
+            bh.w = __uint_as_float(__float_as_uint(x3) & 0xFFFFE000u); bl.w = x3 - bh.w;
+            ah.x = __uint_as_float(__float_as_uint(y0) & 0xFFFFE000u); al.x = y0 - ah.x;
+            ah.y = __uint_as_float(__float_as_uint(y1) & 0xFFFFE000u); al.y = y1 - ah.y;
+            ah.z = __uint_as_float(__float_as_uint(y2) & 0xFFFFE000u); al.z = y2 - ah.z;
+            ah.w = __uint_as_float(__float_as_uint(y3) & 0xFFFFE000u); al.w = y3 - ah.w;
+            const int off = (m >> 3) * kTcSBO + kb * kTcLBO + (m & 7) * 16;
+            *reinterpret_cast<float4*>(&S.op[0][off]) = ah;
+            *reinterpret_cast<float4*>(&S.op[1][off]) = al;
+            *reinterpret_cast<float4*>(&S.op[2][off]) = bh;
+            *reinterpret_cast<float4*>(&S.op[3][off]) = bl;
+          }
+        }
+        fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core's async proxy
+        __syncthreads();
+        if (tid == 0) {
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const int ksteps = min(kTcRows / 8, (n - jbase + 7) / 8);   // 8 gathered rows per MMA; the padding rows are zero
+          for (int ks = 0; ks < ksteps; ks++) {
+            const uint64_t dah = tc_smem_desc(&S.op[0][ks * 2 * kTcLBO]);
+            const uint64_t dal = tc_smem_desc(&S.op[1][ks * 2 * kTcLBO]);
+            const uint64_t dbh = tc_smem_desc(&S.op[2][ks * 2 * kTcLBO]);
+            const uint64_t dbl = tc_smem_desc(&S.op[3][ks * 2 * kTcLBO]);
+            tc_mma_tf32(tmem, dah, dbh, (ch == 0 && ks == 0) ? 0u : 1u);   // (w x)_hi' x_hi
+            tc_mma_tf32(tmem, dah, dbl, 1u);                                // (w x)_hi' x_lo
+            tc_mma_tf32(tmem, dal, dbh, 1u);                                // (w x)_lo' x_hi
+          }
+          tc_commit(&S.mma_done);
+        }
+        // rhs while the MMAs run: b_r += c_j x_j[r], x = hi + lo exactly, from the B tiles (row r of the tile = feature r)
+        {
+          const int roff = (r >> 3) * kTcSBO + (r & 7) * 16;
+#pragma unroll
+          for (int kb = 0; kb < kTcRows / 4; kb++) {
+            if (jbase + 4 * kb >= n) break;   // CTA-uniform
+            const float4 h4 = *reinterpret_cast<const float4*>(&S.op[2][roff + kb * kTcLBO]);
+            const float4 l4 = *reinterpret_cast<const float4*>(&S.op[3][roff + kb * kTcLBO]);
+            const int j = jbase + 4 * kb;
+            const float c0 = s_cs[j], c1 = (j + 1 < n) ? s_cs[j + 1] : 0.f, c2 = (j + 2 < n) ? s_cs[j + 2] : 0.f,
+                        c3 = (j + 3 < n) ? s_cs[j + 3] : 0.f;
+            br = fmaf(c0, h4.x + l4.x, fmaf(c1, h4.y + l4.y, fmaf(c2, h4.z + l4.z, fmaf(c3, h4.w + l4.w, br))));
+          }
+        }
+        mbar_wait(&S.mma_done, mma_phase);
+        mma_phase ^= 1;
+        __syncthreads();   // every thread has read its rhs entries before the tiles are overwritten (next chunk / Lt)
+      }
+      // accumulator -> registers: thread r receives row r (lanes 32 warp .. 32 warp + 31 of TMEM)
+      init_a();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int c0 = 0; c0 < K; c0 += 32) {
+        if (c0 > wmax) break;   // warp-uniform: columns beyond the warp's last row are never needed
+        uint32_t d[32];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]),
+              "=r"(d[9]), "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15]), "=r"(d[16]),
+              "=r"(d[17]), "=r"(d[18]), "=r"(d[19]), "=r"(d[20]), "=r"(d[21]), "=r"(d[22]), "=r"(d[23]), "=r"(d[24]),
+              "=r"(d[25]), "=r"(d[26]), "=r"(d[27]), "=r"(d[28]), "=r"(d[29]), "=r"(d[30]), "=r"(d[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          a[(c0 + c) >> 1].x += __uint_as_float(d[c]);
+          a[(c0 + c) >> 1].y += __uint_as_float(d[c + 1]);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // ordered before the next row's MMAs by its barriers
+    } else {
+      // ---- Gram + rhs: a[c] += (w_j x_j[r]) x_j[c],  b_r += c_j x_j[r] ----------------------------------------------
+  #pragma unroll 2
+      for (int j = 0; j < n; j++) {
+        const float xr = S.tile[j * K + r];
+        const float cj = s_cs[j];
+        const float wx = implicit ? xr * (cj - 1.0f) : xr;
+        br = fmaf(cj, xr, br);
+        const float2 w2 = make_float2(wx, wx);
+  #pragma unroll
+        for (int c4 = 0; c4 < NB4; c4++) {
+          if (4 * c4 > wmax) break;   // warp-uniform
+          const float4 v = *reinterpret_cast<const float4*>(&S.tile[j * K + 4 * c4]);
+          a[2 * c4] = __ffma2_rn(w2, make_float2(v.x, v.y), a[2 * c4]);
+          a[2 * c4 + 1] = __ffma2_rn(w2, make_float2(v.z, v.w), a[2 * c4 + 1]);
+        }
       }
     }
     // ---- right-looking Cholesky, 4 columns per pair of barriers ----------------------------------------------------
@@ -301,6 +447,11 @@ __global__ void __launch_bounds__(K, kCtas) als_chol_rows_kernel(SolveParams<flo
     advance();
   }
   if (tid == 0) P.loss_partials[blockIdx.x] = cta_loss;
+  if constexpr (kTc) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+  }
 }
 
 }  // namespace b200als
