@@ -549,7 +549,8 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
         };
         if (rows_kernel) {
           if (k == 64) CU(launch(als_chol_rows_kernel<64, 8>, 64, sizeof(CholRowsSmem<64>)));
-          else if (o.kernel == 6) CU(launch(als_chol_rows_kernel<128, 3, true>, 128, sizeof(CholRowsSmem<128>)));   // tcgen05 Gram (experimental)
+          else if (o.kernel == 6) CU(launch(als_chol_rows_kernel<128, 3, 1>, 128, sizeof(CholRowsSmem<128>)));   // tcgen05 Gram, single-buffered (experimental)
+          else if (o.kernel == 7) CU(launch(als_chol_rows_kernel<128, 3, 2>, 128, sizeof(CholRowsSmem<128>)));   // tcgen05 Gram, pipelined (experimental, not yet run on a GPU)
           else if (o.ctas == 2) CU(launch(als_chol_rows_kernel<128, 2>, 128, sizeof(CholRowsSmem<128>)));
           else CU(launch(als_chol_rows_kernel<128, 3>, 128, sizeof(CholRowsSmem<128>)));   // measured: 134.5 vs 171.2 ms / 1 M rows
         } else {
