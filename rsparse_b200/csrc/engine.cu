@@ -22,6 +22,7 @@
 #include "../../include/b200als.h"
 #include "als_chol_tile.cuh"
 #include "als_chol_rows.cuh"
+#include "als_chol_rows_split.cuh"
 #include "als_generic.cuh"
 #include "als_resident.cuh"
 #include "eig.cuh"
@@ -550,6 +551,7 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
         if (rows_kernel) {
           if (k == 64) CU(launch(als_chol_rows_kernel<64, 8>, 64, sizeof(CholRowsSmem<64>)));
           else if (o.kernel == 6) CU(launch(als_chol_rows_kernel<128, 3, 1>, 128, sizeof(CholRowsSmem<128>)));   // tcgen05 Gram, single-buffered (experimental)
+          else if (o.kernel == 8) CU(launch(als_chol_rows_split_kernel, kSplitThreads, sizeof(CholRowsSmem<128>)));   // split rows (experimental, not yet run on a GPU)
           else if (o.kernel == 7) CU(launch(als_chol_rows_kernel<128, 3, 2>, 128, sizeof(CholRowsSmem<128>)));   // tcgen05 Gram, pipelined (experimental, not yet run on a GPU)
           else if (o.ctas == 2) CU(launch(als_chol_rows_kernel<128, 2>, 128, sizeof(CholRowsSmem<128>)));
           else CU(launch(als_chol_rows_kernel<128, 3>, 128, sizeof(CholRowsSmem<128>)));   // measured: 134.5 vs 171.2 ms / 1 M rows

@@ -1,11 +1,11 @@
 #!/bin/bash
 # usage: gpurun --timeout 200 -- 'bash scripts/gpu_chol_tc.sh <tag>'  -- the tcgen05 per-row Gram variants of the row-per-thread
-# Cholesky kernel (kernel = 6 single-buffered, 7 pipelined): parity vs the fp64 oracle, then the rank-128 bench line of each
+# Cholesky kernel (kernel = 6 single-buffered, 7 pipelined) and the split-row variant (kernel = 8): parity vs the fp64 oracle, then the rank-128 bench line of each
 TAG=${1:-choltc}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 export PYTHONUNBUFFERED=1
-for KN in ${KERNELS:-6 7}; do
+for KN in ${KERNELS:-6 7 8}; do
   echo "== kernel $KN"
   CHOL_KERNEL=$KN timeout 50 python scripts/check_chol_rows.py 2>&1 | tail -8 | tee $OUT/check_chol_tc_k$KN.txt
   timeout 50 python bench.py --workload c3-chol --kernel $KN --steps 3 2>&1 | tail -1 | tee $OUT/bench_c3-chol_k$KN.json | cut -c1-300
