@@ -40,7 +40,7 @@ struct SolveParams {
   double* loss_partials;  // [gridDim.x]
   int* status;            // != 0: some system was not positive definite
   // ---- bias terms (with_user_item_bias / with_global_bias).  The engine hands these kernels *compact* matrices:
-  // X without its bias row, Y = the rows being solved, both k wide (see engine.cu, BiasPlan) ----
+  // X without its bias row, Y = the rows being solved, both k wide (see stateless_half, engine_stateless.inl) ----
   const T* xbias;         // [n_src] x_biases (wrmf_implicit.hpp:115-119, wrmf_explicit.hpp:58-63) or nullptr
   const T* rhs_init;      // [k] implicit only: rhs_init (wrmf_implicit.hpp:143-157) or nullptr
   T gbias;                // global_bias (implicit), 0 when unused

@@ -1,0 +1,122 @@
+// engine_context.inl -- part of engine.cu (included there; not a standalone translation unit).
+// ------------------------------------------------------------------------------------------------------
+// device context shared by the stateless calls and sessions
+// ------------------------------------------------------------------------------------------------------
+struct Ctx {
+  int device = -1;
+  int sm_count = 148;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  DevBuf ticket, loss_partials, loss_acc, status, gram_partials, reg_partials, rot_rt;
+  bool attrs_set = false;
+  int init() {
+    if (stream) return B200ALS_OK;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+      return fail(B200ALS_ECUDA, "no CUDA device visible (this engine has no CPU fallback)");
+    CU(cudaGetDevice(&device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    sm_count = prop.multiProcessorCount;
+    smem_optin = prop.sharedMemPerBlockOptin;
+    CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CU(ticket.ensure(sizeof(unsigned long long)));
+    CU(loss_acc.ensure(4 * sizeof(double)));
+    CU(status.ensure(sizeof(int)));
+    return B200ALS_OK;
+  }
+};
+static Ctx& ctx() {
+  static thread_local Ctx c;
+  return c;
+}
+
+template <typename T>
+struct CscDev {
+  int32_t n_rows = 0, n_cols = 0;
+  int64_t nnz = 0;
+  DevBuf ptr, idx, val;
+  // row classes for the resident kernel (built lazily)
+  DevBuf short_list, long_list;
+  int n_short = -1, n_long = 0, n_empty = 0;
+  bool all_short = false;
+};
+
+template <typename T>
+static int upload_csc(const b200als_csc* A, CscDev<T>& D, cudaStream_t st) {
+  if (!A || !A->ptr || (A->nnz > 0 && (!A->idx || (!A->val_f64 && !A->val_f32))))
+    return fail(B200ALS_EINVAL, "b200als_csc: null ptr/idx/val");
+  if (A->n_cols < 0 || A->n_rows < 0 || A->nnz < 0) return fail(B200ALS_EINVAL, "b200als_csc: negative size");
+  D.n_rows = A->n_rows;
+  D.n_cols = A->n_cols;
+  D.nnz = A->nnz;
+  CU(D.ptr.ensure(sizeof(int32_t) * ((size_t)A->n_cols + 1)));
+  CU(D.idx.ensure(sizeof(int32_t) * (size_t)A->nnz));
+  CU(D.val.ensure(sizeof(T) * (size_t)A->nnz));
+  CU(cudaMemcpyAsync(D.ptr.p, A->ptr, sizeof(int32_t) * ((size_t)A->n_cols + 1), cudaMemcpyHostToDevice, st));
+  if (A->nnz) {
+    CU(cudaMemcpyAsync(D.idx.p, A->idx, sizeof(int32_t) * (size_t)A->nnz, cudaMemcpyHostToDevice, st));
+    const bool same_f64 = A->val_f64 && sizeof(T) == 8, same_f32 = !A->val_f64 && sizeof(T) == 4;
+    if (same_f64 || same_f32) {
+      CU(cudaMemcpyAsync(D.val.p, A->val_f64 ? (const void*)A->val_f64 : (const void*)A->val_f32,
+                         sizeof(T) * (size_t)A->nnz, cudaMemcpyHostToDevice, st));
+    } else {
+      // double -> float (or float -> double) once at upload; the reference converts per visit
+      // (wrmf_implicit.hpp:182-183), same rounding
+      DevBuf tmp;
+      const size_t eb = A->val_f64 ? 8 : 4;
+      CU(tmp.ensure(eb * (size_t)A->nnz));
+      CU(cudaMemcpyAsync(tmp.p, A->val_f64 ? (const void*)A->val_f64 : (const void*)A->val_f32, eb * (size_t)A->nnz,
+                         cudaMemcpyHostToDevice, st));
+      const int bs = 256;
+      const unsigned gs = (unsigned)((A->nnz + bs - 1) / bs);
+      if (A->val_f64) convert_kernel<double, T><<<gs, bs, 0, st>>>(tmp.f64(), D.val.template as<T>(), A->nnz);
+      else convert_kernel<float, T><<<gs, bs, 0, st>>>(tmp.f32(), D.val.template as<T>(), A->nnz);
+      LAUNCHED(); CU(cudaGetLastError());
+      CU(cudaStreamSynchronize(st));
+    }
+  }
+  D.n_short = -1;
+  return B200ALS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Gram
+// ------------------------------------------------------------------------------------------------------
+// B200ALS_GRAM=ffma forces the fp32 FMA kernel; default at rank 128 / fp32 is the tcgen05 3xTF32 kernel
+static bool gram_use_tensor_cores() {
+  const char* e = getenv("B200ALS_GRAM");
+  return !(e && (e[0] == 'f' || e[0] == 'F'));
+}
+template <typename T>
+static int run_gram(Ctx& c, const T* X, int k, long long n, double lambda, T* G, double* G64) {
+  if constexpr (sizeof(T) == 4) {
+    if (k == kTcK && n >= 8192 && gram_use_tensor_cores()) {   // small inputs: the exact fp32 FMA kernel
+      long long rows_per = std::max<long long>(1024, (n + 887) / 888);
+      rows_per = ((rows_per + 255) / 256) * 256;   // whole drain windows
+      const long long n_cta = (n + rows_per - 1) / rows_per;
+      CU(c.gram_partials.ensure(sizeof(double) * (size_t)n_cta * kTcK * kTcK));
+      const size_t smem = sizeof(GramTcSmem);
+      CU(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      gram_tc_kernel<<<(unsigned)n_cta, 128, smem, c.stream>>>((const float*)X, n, rows_per, c.gram_partials.f64());
+      LAUNCHED(); CU(cudaGetLastError());
+      gram_reduce_kernel<T><<<(k * k + 255) / 256, 256, 0, c.stream>>>(c.gram_partials.f64(), (int)n_cta, 1, k, lambda, G, G64);
+      LAUNCHED(); CU(cudaGetLastError());
+      return B200ALS_OK;
+    }
+  }
+  const int nt1 = (k + kGramTile - 1) / kGramTile, n_tiles = nt1 * (nt1 + 1) / 2;
+  long long n_cta = std::min<long long>((long long)c.sm_count * 2 / std::max(1, n_tiles) + 1, (n + 255) / 256);
+  n_cta = std::max<long long>(1, n_cta);
+  long long rows_per = (n + n_cta - 1) / n_cta;
+  rows_per = ((rows_per + kGramRows - 1) / kGramRows) * kGramRows;
+  n_cta = std::max<long long>(1, (n + rows_per - 1) / rows_per);
+  CU(c.gram_partials.ensure(sizeof(double) * (size_t)n_cta * n_tiles * kGramTile * kGramTile));
+  gram_partial_kernel<T><<<dim3((unsigned)n_cta, (unsigned)n_tiles), 256, 0, c.stream>>>(X, k, n, rows_per,
+                                                                                         c.gram_partials.f64(), nt1);
+  LAUNCHED(); CU(cudaGetLastError());
+  gram_reduce_kernel<T><<<(k * k + 255) / 256, 256, 0, c.stream>>>(c.gram_partials.f64(), (int)n_cta, n_tiles, k,
+                                                                   lambda, G, G64);
+  LAUNCHED(); CU(cudaGetLastError());
+  return B200ALS_OK;
+}
