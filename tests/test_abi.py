@@ -80,3 +80,14 @@ def test_synth_csr_host_generator():
 def test_bad_arguments_are_rejected():
     assert L.lib().b200als_synth_csr_host(10, 5, 6, 1, 0, 0, None, None, None, None) == L.EINVAL
     assert b"synthetic" in L.lib().b200als_last_error()
+
+
+def test_r_shim_type_checks_against_the_abi():
+    """r-package/src/b200als_shim.c (the `.Call` layer for an R build) is type-checked against include/b200als.h with
+    stand-in R headers carrying R's real signatures: every ABI call in the shim matches the header, -Werror."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    p = subprocess.run(["sh", os.path.join(ROOT, "r-package", "tests", "check_shim.sh")], capture_output=True, text=True)
+    assert p.returncode == 0 and "type-check ok" in p.stdout, p.stdout + p.stderr
