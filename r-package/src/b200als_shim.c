@@ -207,6 +207,35 @@ SEXP _rsparse_initialize_biases_float(SEXP m_csc_r, SEXP m_csr_r, SEXP user_bias
   return Rf_ScalarReal(g);
 }
 
+/* top_product (src/matrix_top_product.cpp:20-102; Rcpp export src/RcppExports.cpp:188-203, 7 arguments; R caller
+ * find_top_product, R/utils.R:31-59).  R hands over doubles (float models are widened at R/utils.R:35-36, so narrowing
+ * them back is exact; a precision = "double" model is rounded to float here -- the engine's scores are still accumulated
+ * in double like the reference's, but the ranking of near-ties may then differ).  x is n_user x rank, y is rank x n_item;
+ * the result is the reference's: an n_user x k IntegerMatrix of 1-based item ids (NA padded) with attribute "scores". */
+SEXP _rsparse_top_product(SEXP x, SEXP y, SEXP k, SEXP n_threads, SEXP not_recommend_r, SEXP exclude, SEXP glob_mean) {
+  const int n_user = Rf_nrows(x), rank = Rf_ncols(x), n_item = Rf_ncols(y), top_k = Rf_asInteger(k);
+  if (Rf_nrows(y) != rank) Rf_error("b200als: ncol(x) == nrow(y) is not TRUE");
+  (void)n_threads;
+  float* xe = (float*)R_alloc((size_t)rank * (size_t)(n_user > 0 ? n_user : 1), sizeof(float));   /* rank x n_user */
+  float* ye = (float*)R_alloc((size_t)rank * (size_t)(n_item > 0 ? n_item : 1), sizeof(float));   /* rank x n_item */
+  const double* xd = REAL(x);
+  const double* yd = REAL(y);
+  for (int u = 0; u < n_user; u++)
+    for (int f = 0; f < rank; f++) xe[(size_t)u * rank + f] = (float)xd[(size_t)f * n_user + u];
+  for (size_t e = 0; e < (size_t)rank * (size_t)n_item; e++) ye[e] = (float)yd[e];
+  SEXP nj = R_do_slot(not_recommend_r, Rf_install("j"));   /* dgRMatrix: @p row pointers, @j column indices */
+  SEXP np = R_do_slot(not_recommend_r, Rf_install("p"));
+  const int have_filter = XLENGTH(nj) > 0;
+  SEXP res = PROTECT(Rf_allocMatrix(INTSXP, n_user, top_k));
+  SEXP scores = PROTECT(Rf_allocMatrix(REALSXP, n_user, top_k));
+  check(b200als_top_product(xe, n_user, ye, n_item, rank, top_k, have_filter ? INTEGER(np) : NULL,
+                            have_filter ? INTEGER(nj) : NULL, INTEGER(exclude), (int)XLENGTH(exclude), Rf_asReal(glob_mean),
+                            INTEGER(res), REAL(scores)));
+  Rf_setAttrib(res, Rf_install("scores"), scores);
+  UNPROTECT(2);
+  return res;
+}
+
 static const R_CallMethodDef CallEntries[] = {
     {"_rsparse_als_implicit_float", (DL_FUNC)&_rsparse_als_implicit_float, 13},
     {"_rsparse_als_implicit_double", (DL_FUNC)&_rsparse_als_implicit_double, 13},
@@ -214,6 +243,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"_rsparse_als_explicit_double", (DL_FUNC)&_rsparse_als_explicit_double, 11},
     {"_rsparse_initialize_biases_double", (DL_FUNC)&_rsparse_initialize_biases_double, 9},
     {"_rsparse_initialize_biases_float", (DL_FUNC)&_rsparse_initialize_biases_float, 9},
+    {"_rsparse_top_product", (DL_FUNC)&_rsparse_top_product, 7},
     {"b200als_R_create", (DL_FUNC)&b200als_R_create, 8},
     {"b200als_R_set_factors", (DL_FUNC)&b200als_R_set_factors, 3},
     {"b200als_R_get_factors", (DL_FUNC)&b200als_R_get_factors, 3},

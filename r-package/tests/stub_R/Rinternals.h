@@ -22,6 +22,9 @@ int Rf_asInteger(SEXP);
 int Rf_asLogical(SEXP);
 double Rf_asReal(SEXP);
 int Rf_nrows(SEXP);
+int Rf_ncols(SEXP);
+SEXP Rf_allocMatrix(SEXPTYPE, int, int);
+SEXP Rf_setAttrib(SEXP, SEXP, SEXP);
 SEXP Rf_ScalarReal(double);
 SEXP Rf_allocVector(SEXPTYPE, R_xlen_t);
 SEXP Rf_lengthgets(SEXP, R_xlen_t);
