@@ -142,8 +142,8 @@ struct RotSmem {
   float R[kRotK][kRotK];           // 64 KB
   float Xt[kRotK][kRotRows + 4];   // the row block TRANSPOSED: Xt[f][r]; one 128-bit read = 4 rows of feature f
 };
-__global__ void __launch_bounds__(256) rotate_rows_kernel(const float* __restrict__ X, float* __restrict__ Z,
-                                                          const float* __restrict__ R, long long n) {
+// X and Z may be the SAME buffer (in-place rotation): neither is __restrict__; a block reads its rows before writing them.
+__global__ void __launch_bounds__(256) rotate_rows_kernel(const float* X, float* Z, const float* __restrict__ R, long long n) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RotSmem& S = *reinterpret_cast<RotSmem*>(smem_raw);
   const int tid = threadIdx.x;

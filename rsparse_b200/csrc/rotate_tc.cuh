@@ -39,8 +39,9 @@ __global__ void transpose_128_kernel(const float* __restrict__ R, float* __restr
   if (e < kTcK * kTcK) Rt[(e % kTcK) * kTcK + (e / kTcK)] = R[e];
 }
 
-__global__ void __launch_bounds__(128) rotate_tc_kernel(const float* __restrict__ X, float* __restrict__ Z,
-                                                        const float* __restrict__ Rt, long long n) {
+// X and Z may be the SAME buffer (in-place rotation, how the engine calls it): neither is __restrict__; every row is read
+// (one stage ahead) before it is written, by the CTA that writes it.
+__global__ void __launch_bounds__(128) rotate_tc_kernel(const float* X, float* Z, const float* __restrict__ Rt, long long n) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   RotTcSmem& S = *reinterpret_cast<RotTcSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
