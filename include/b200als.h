@@ -171,7 +171,8 @@ typedef struct b200als_options {
                           panel kernel (the default), 5 = its predecessor, the 16 x 16 register-block kernel, 6 / 7 = the
                           default kernel with the per-row Gram on tcgen05 (rank 128; experimental: 6 single-buffered,
                           parity-checked but slower today; 7 pipelined, not yet run on hardware), 8 = rank-128 rows
-                          split over two threads for occupancy (experimental, not yet run on hardware)              */
+                          split over two threads for occupancy, 9 = rank-64 warp per system (both experimental, not
+                          yet run on hardware)                                                                        */
   int reserved[7];     /* reserved[0]: tile staging of the register-resident CG kernel -- 0 default, 1 cp.async.bulk
                           (TMA engine), 2 cp.async (LDGSTS); reserved[1]: CTAs/SM the kernel is built for (CG resident
                           kernel: 0 default, 3, 4; rank-128 row-per-thread Cholesky: 0 default (= 3), 2, 3); the rest must be 0 */

@@ -15,7 +15,7 @@ from rsparse_b200 import _lib as L  # noqa: E402
 
 TOL = 1e-5
 CTAS = int(os.environ.get("CHOL_CTAS", "0"))
-KUT = int(os.environ.get("CHOL_KERNEL", "4"))   # kernel under test: 4 row-per-thread, 6 / 7 with the tcgen05 Gram, 8 split rows (rank 128)
+KUT = int(os.environ.get("CHOL_KERNEL", "4"))   # kernel under test: 4 row-per-thread, 6 / 7 with the tcgen05 Gram, 8 split rows (rank 128), 9 warp per system (rank 64)
 cases = wc.half_iteration_cases()
 bad = 0
 for name in ("synth_implicit_chol_k64", "synth_implicit_cg_k128", "synth_ragged_implicit_cg_k128", "synth_explicit_cg_k128",
