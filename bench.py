@@ -68,6 +68,16 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
+def traffic_per_launch(workload, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the ncu capture
+    recorded in profiles/traffic.json for this workload and GPU count; None when no capture exists."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return int(t[workload][str(world)]["bytes"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -121,18 +131,16 @@ def host_csr(L, n_rows, n_item, nnz, seed, pinned=True, offset=0):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path on this box's host cores."""
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores.  Nothing of the
+    product is imported or loaded here: inputs come from the oracle library's own generator."""
     if rank != 0:
         return
     import oracle
-    from rsparse_b200 import _lib as L
     n_user, n_item, nnz, k, cg, lam = WORKLOADS[args.workload]
-    threads = oracle.max_threads()
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the baseline uses every host core it may run on
+    threads = oracle.host_threads()
     sample = min(n_user, args.cpu_rows)
-    ptr = np.empty(sample + 1, np.int32)
-    idx = np.empty(sample * nnz, np.int32)
-    val = np.empty(sample * nnz, np.float64)
-    L.check(L.lib().b200als_synth_csr_host(sample, n_item, nnz, 42, 0, 0, L.vp(ptr), L.vp(idx), None, L.vp(val)))
+    ptr, idx, val = oracle.synth_csr(sample, n_item, nnz, 42, False, 0, True, threads)
     rng = np.random.default_rng(0)
     # same input distribution as the GPU arm (see main()): trained-like item factors, R-initialised user factors
     X = rng.standard_normal((n_item, k), dtype=np.float32) * (ITEM_SCALE * (1.0 + np.arange(k, dtype=np.float32)) ** -ITEM_DECAY)
@@ -154,23 +162,29 @@ def run_reference(args, rank, world):
             best_t = min(best_t, time.perf_counter() - t)
         speeds[impl] = n_probe / best_t
     best = max(speeds, key=speeds.get)
+    # bounded: the whole arm stays under ~90 s whatever --steps / --warmup the driver passes
+    budget_s = 60.0
+    est = sample / speeds[best]
+    warmup = max(1, min(args.warmup, 1 if est > 2.0 else args.warmup))
+    steps = max(1, min(args.steps, int(budget_s / max(est, 1e-3))))
     Y0 = Y.copy()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         oracle.als_implicit(ptr, idx, val, X, Y, G, lam, 1, cg, threads, impl=best)
     dt = 0.0
-    for _ in range(args.steps):
+    for _ in range(steps):
         Y[:] = Y0                      # like the GPU arm: every step starts from the initialisation (not timed)
         t0 = time.perf_counter()
         oracle.als_implicit(ptr, idx, val, X, Y, G, lam, 1, cg, threads, impl=best)
         dt += time.perf_counter() - t0
-    value = sample * args.steps / dt
+    value = sample * steps / dt
     kind = "reference" if best == "ref" else "port"
-    sample_desc = ("first %d rows of the %dx%d/%d-nnz CSR against the full item matrix, XtX precomputed (not timed); "
-                   "probe on 100k rows: %s" % (sample, n_user, n_item, nnz,
-                                                ", ".join("%s %.0f rows/s" % (("oracle/_ref (reference source + mini_arma)" if i == "ref" else "oracle port (AVX2 loops)"), v) for i, v in speeds.items())))
+    sample_desc = ("first %d rows of the %dx%d/%d-nnz CSR against the full item matrix, XtX precomputed (not timed), %d host threads "
+                   "(OMP_NUM_THREADS in the environment was %s and is overridden by num_threads()); probe on 100k rows: %s"
+                   % (sample, n_user, n_item, nnz, threads, os.environ.get("OMP_NUM_THREADS", "unset"),
+                      ", ".join("%s %.0f rows/s" % (("oracle/_ref (reference source + mini_arma)" if i == "ref" else "oracle port (AVX2 loops)"), v) for i, v in speeds.items())))
     out = {"impl": "reference", "metric": METRIC, "value": value,
-           "unit": "user-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "unit": "user-updates/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+           "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
            "config": {"workload": "%s: %dx%d CSR, %d nnz/row, WRMF implicit rank=%d CG(%d), lambda=%g; CPU sample of %d rows"
                       % (args.workload, n_user, n_item, nnz, k, cg, lam, sample)},
@@ -238,10 +252,11 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
-    from rsparse_b200 import parallel
-    rank, world, local_rank = parallel.env_rank_world()
+    rank, world, local_rank = (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+                               int(os.environ.get("LOCAL_RANK", "0")))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    from rsparse_b200 import parallel
 
     if args.workload == "topk":
         return run_topk(args)
@@ -312,8 +327,7 @@ def main():
                     "traffic": None, "kernel_ms": solve_ms}
     else:
       roofline = {"bound": "hbm", "kernel": "als_cg_resident_kernel", "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": (TRAFFIC_BYTES_PER_LAUNCH[args.workload] * n_local // n_user
-                            if args.workload in TRAFFIC_BYTES_PER_LAUNCH else None),
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic_per_launch(args.workload, world),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": n_local * BYTES_PER_ROW(nnz, k),
                 "kernel_ms": solve_ms, "fp32_tflops": n_local * FLOPS_PER_ROW(nnz, k, cg) / (solve_ms / 1e3) / 1e12}
     if solver == L.CHOLESKY:
@@ -353,7 +367,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         import oracle
-        threads = oracle.max_threads()
+        threads = oracle.host_threads()
         sample = min(n_local, args.cpu_rows)
         if args.no_e2e:
             ptr, idx, val = host_csr(L, sample, n_item, nnz, 42, False, 0)
@@ -397,10 +411,6 @@ def main():
         print(json.dumps(out), flush=True)
     s.close()
 
-
-# dram__bytes_read.sum + dram__bytes_write.sum of one als_cg_resident_kernel launch, from the committed
-# `ncu --set full` capture (profiles/); None until a capture for that workload exists.
-TRAFFIC_BYTES_PER_LAUNCH = {"c3": 353241793792 + 5129585152}   # profiles/r1/resident_dram_c3.csv (N = 1)
 
 if __name__ == "__main__":
     main()

@@ -68,7 +68,32 @@ def ref():
 
 
 def max_threads():
+    """The reference's omp_thread_count() (src/utils.cpp:84-91): honours OMP_NUM_THREADS / OMP_THREAD_LIMIT."""
     return int(lib().oracle_max_threads())
+
+
+def host_threads():
+    """Threads the CPU arms of bench.py use: every core this process may run on, NOT omp_get_max_threads() --
+    torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which would silently make the baseline
+    single-threaded.  The half-iteration entry points take n_threads explicitly (`num_threads(n)` clause)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def synth_csr(n_rows, n_cols, nnz_per_row, seed=42, explicit_values=False, row_offset=0, with_values=True, n_threads=None):
+    """bench.py's synthetic CSR, generated on the host by the oracle library (same entries as the product's
+    b200als_synth_csr_host; see tests/test_abi.py)."""
+    ptr = np.empty(n_rows + 1, np.int32)
+    idx = np.empty(n_rows * nnz_per_row, np.int32)
+    val = np.empty(n_rows * nnz_per_row, np.float64) if with_values else None
+    rc = lib().oracle_synth_csr(C.c_int(n_rows), C.c_int(n_cols), C.c_int(nnz_per_row), C.c_ulonglong(seed),
+                                C.c_int(int(explicit_values)), C.c_longlong(row_offset), _p(ptr), _p(idx),
+                                _p(val) if with_values else None, C.c_int(n_threads or host_threads()))
+    if rc != 0:
+        raise ValueError("oracle_synth_csr: bad shape (rc %d)" % rc)
+    return ptr, idx, val
 
 
 def _p(a):

@@ -747,6 +747,37 @@ int oracle_max_threads(void) {
 #endif
 }
 
+
+// Synthetic CSR of bench.py / BASELINE.md section 2 (row r draws one ascending column id per equal-width stratum of
+// [0, n_cols) from a counter-based splitmix64 hash; values 1 + floor(10 u^2) or ratings 1..5).  Restated here so that
+// bench.py's CPU arms (`--impl reference`, `cpu_baseline`) generate their inputs WITHOUT loading the product library;
+// tests/test_abi.py checks that it equals the product's generator entry for entry.
+static inline uint64_t synth_mix(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+int oracle_synth_csr(int n_rows, int n_cols, int nnz_per_row, unsigned long long seed, int explicit_values,
+                     long long row_offset, int* ptr, int* idx, double* val, int n_threads) {
+  if (n_rows < 0 || n_cols <= 0 || nnz_per_row <= 0 || nnz_per_row > n_cols) return 1;
+  if ((long long)n_rows * nnz_per_row > 2147483647LL) return 2;
+#pragma omp parallel for schedule(static) num_threads(n_threads > 0 ? n_threads : 1)
+  for (long long r = 0; r < (long long)n_rows; r++) {
+    ptr[r] = (int)(r * nnz_per_row);
+    for (int j = 0; j < nnz_per_row; j++) {
+      const uint64_t h = synth_mix((uint64_t)seed * 0x100000001B3ull + (uint64_t)(r + row_offset) * (uint64_t)nnz_per_row + (uint64_t)j);
+      const long long lo = ((long long)j * n_cols) / nnz_per_row, hi = ((long long)(j + 1) * n_cols) / nnz_per_row;
+      const long long e = r * nnz_per_row + j;
+      idx[e] = (int)(lo + (long long)(h % (uint64_t)(hi - lo)));
+      const float u = (float)((h >> 40) & 0xFFFFFF) / 16777216.0f;
+      if (val) val[e] = (double)(explicit_values ? (1.0f + floorf(u * 5.0f)) : (1.0f + floorf(10.0f * u * u)));
+    }
+  }
+  ptr[n_rows] = (int)((long long)n_rows * nnz_per_row);
+  return 0;
+}
+
 double oracle_als_implicit_f32(int nc, size_t nnz, const int* p, const int* idx, const double* v,
                                const float* X, int k, int n_src, float* Y, const float* XtX,
                                double lambda, int n_threads, int solver, int cg_steps) {

@@ -77,6 +77,20 @@ def test_synth_csr_host_generator():
     assert set(np.unique(v32)) <= {1.0, 2.0, 3.0, 4.0, 5.0}
 
 
+def test_oracle_generator_equals_the_products():
+    """bench.py's CPU arms build their CSR with oracle.synth_csr so that the reference arm never loads the product
+    library; both generators must yield the same matrix, entry for entry (implicit, explicit, row offsets)."""
+    import oracle
+    n_rows, n_cols, nnz = 777, 4001, 23
+    for explicit, off in ((0, 0), (1, 0), (0, 12345)):
+        ptr = np.zeros(n_rows + 1, np.int32)
+        idx = np.zeros(n_rows * nnz, np.int32)
+        v64 = np.zeros(n_rows * nnz, np.float64)
+        L.check(L.lib().b200als_synth_csr_host(n_rows, n_cols, nnz, 42, explicit, off, L.vp(ptr), L.vp(idx), None, L.vp(v64)))
+        p2, i2, v2 = oracle.synth_csr(n_rows, n_cols, nnz, 42, bool(explicit), off)
+        assert np.array_equal(ptr, p2) and np.array_equal(idx, i2) and np.array_equal(v64, v2)
+
+
 def test_bad_arguments_are_rejected():
     assert L.lib().b200als_synth_csr_host(10, 5, 6, 1, 0, 0, None, None, None, None) == L.EINVAL
     assert b"synthetic" in L.lib().b200als_last_error()
