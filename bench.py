@@ -51,6 +51,10 @@ WORKLOADS = {
     "c4": (10_000_000, 1_000_000, 80, 128, 3, 0.1),        # BASELINE configs[3]: explicit feedback (MMMF)
     "c2": (1_000_000, 100_000, 50, 64, 3, 0.1),            # BASELINE configs[1]: implicit, rank 64, Cholesky
     "c3-chol": (1_000_000, 1_000_000, 80, 128, 3, 0.1),    # transform_-shaped: C3's row shape solved by Cholesky (a10)
+    "c5": (50_000_000, 5_000_000, 100, 256, 3, 0.1),       # BASELINE configs[4]: rank 256, 8 GPUs (5e9 nnz: >= 4 ranks)
+    "c5-slice": (6_250_000, 5_000_000, 100, 256, 3, 0.1),  # one rank's share of C5 at 8 GPUs, as a single-GPU run
+    "c5-small": (500_000, 5_000_000, 100, 256, 3, 0.1),    # ncu captures
+    "c3-k64": (10_000_000, 1_000_000, 80, 64, 3, 0.1),     # C3's shape at rank 64 (tile kernel, half-warp per gathered row)
 }
 # side workload "topk": MatrixFactorizationRecommender$predict's top_product
 TOPK = dict(n_user=65536, n_item=1_000_000, rank=128, k=10, nnz=80)
@@ -271,8 +275,10 @@ def main():
     n_local = end - begin
 
     feedback, solver = WORKLOAD_MODE.get(args.workload, ("implicit", L.CONJUGATE_GRADIENT))
-    if (feedback, solver) != ("implicit", L.CONJUGATE_GRADIENT):
+    if (feedback, solver) != ("implicit", L.CONJUGATE_GRADIENT) or k != 128:
         args.no_e2e = args.no_cpu = True     # side workloads: device-resident number only
+    if n_user // world * nnz > 2**31 - 1:
+        raise SystemExit("workload %s needs more GPUs: %d nnz per rank exceed the 32-bit row pointers of a shard" % (args.workload, n_user // world * nnz))
     s = Session.synthetic(n_local, begin, n_user, n_item, nnz, 42, k, feedback, solver, cg, True, lam,
                           args.kernel, args.stage, args.ctas)
     # Inputs: users at R's initialisation scale N(0,1)/100 (R/model_WRMF.R:203-215); items "trained-like":
@@ -326,7 +332,9 @@ def main():
                     "achieved": n_local * fl / (solve_ms / 1e3) / 1e12, "peak": None, "unit": "TFLOP/s", "frac": None,
                     "traffic": None, "kernel_ms": solve_ms}
     else:
-      roofline = {"bound": "hbm", "kernel": "als_cg_resident_kernel", "achieved": achieved, "peak": hbm_peak,
+      roofline = {"bound": "hbm", "kernel": ("als_cg_resident_kernel" if (k == 128 and nnz <= 80 and args.kernel not in (1, 10)) else
+                                             "als_cg_generic_kernel" if args.kernel == 1 else "als_cg_tile_kernel"),
+                "achieved": achieved, "peak": hbm_peak,
                 "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic_per_launch(args.workload, world),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": n_local * BYTES_PER_ROW(nnz, k),
                 "kernel_ms": solve_ms, "fp32_tflops": n_local * FLOPS_PER_ROW(nnz, k, cg) / (solve_ms / 1e3) / 1e12}

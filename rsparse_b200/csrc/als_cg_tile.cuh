@@ -1,0 +1,357 @@
+// als_cg_tile.cuh -- fixed-step CG half-iteration with the row's gathered factor tile RESIDENT IN SHARED MEMORY:
+// the general fast path -- any rank k <= 256 with k % 4 == 0, any row length that fits the tile buffer (the host bins
+// rows by length, engine_solve.inl), fp32, eigenbasis / full XtX / explicit feedback.  als_cg_resident_kernel
+// (als_resident.cuh) stays the specialised kernel for rank 128 with rows of <= 80 entries; everything it cannot take
+// lands here instead of on the streaming kernel (als_generic.cuh), which re-gathers the tile from L2 on every sweep.
+//
+// Reference semantics: cg_solver_implicit (inst/include/wrmf_implicit.hpp:8-32), cg_solver_explicit
+// (inst/include/wrmf_explicit.hpp:8-31) and the column loops around them (wrmf_implicit.hpp:175-282,
+// wrmf_explicit.hpp:71-146); same iterates, same `rsnew < CG_TOL` exit.
+//
+// Shape of the kernel:
+//   * one CTA solves one row at a time (static interleave over a persistent grid => fixed loss summation order);
+//     the row's tile X_nnz (n x k floats) is gathered from HBM ONCE by 16-byte cp.async into one of two tile
+//     buffers -- the tile of the CTA's next row lands while this row computes; CSR indices / values travel
+//     global -> shared two rows ahead, row pointers three rows ahead (registers): no dependent HBM chain per row;
+//   * a gathered row of k floats is held by LPR = KPAD/4 (<= 32) lanes as one float4 each (two float4 per lane at
+//     rank 256), so a warp works on 32/LPR gathered rows at a time and small ranks do not idle lanes;
+//   * a CG step is one sweep over the tile: per batch of 4 row steps  u_j = x_j . v  (packed FFMA2 + a transposing
+//     halving reduction: 3 + log2(LPR/4) shuffles for 4 x 32/LPR rows),  w_j = f(c_j, u_j)  by the owner lanes,
+//     4 broadcast shuffles,  acc += w_j x_j  from the same registers; then one cross-warp sum through shared memory;
+//   * XtX p: d (.) p in the eigenbasis of XtX (eig.cuh), or (kFullG) every (warp, lane group) multiplies its slab
+//     of XtX rows from L1/L2 and the slabs ride the same reduction; lambda_use p for explicit feedback;
+//   * the loss term X_nnz' y comes from the u vectors already computed (X_nnz'y = X_nnz'x0 + sum_k alpha_k X_nnz'p_k).
+// Algorithmic HBM bytes per row: 4nk + 8n + 4 + 4k + 4k.
+#pragma once
+#include "als_resident.cuh"   // packed-fp32 helpers (dot4, axpy4, fma4, ...)
+
+namespace b200als {
+
+struct TileCgParams {
+  const int32_t* ptr;
+  const int32_t* idx;
+  const float* val;
+  const float* X;      // k x n_src
+  float* Y;            // k x n_targets
+  const float* diag;   // [k] eigenvalues of XtX (+lambda): implicit, eigenbasis
+  const float* G;      // k x k XtX + lambda I: implicit, kFullG
+  int k;               // rank, k % 4 == 0, k <= KPAD of the instantiation
+  int feedback;
+  int cg_steps;
+  int dynamic_lambda;
+  float lambda;
+  const int32_t* row_list;  // rows of this launch's length class (nullptr: rows row_begin .. row_begin + n_list - 1)
+  int n_list;
+  int ptr_base;
+  int row_begin;
+  int cap;                  // tile-buffer capacity in gathered rows (every listed row has 1 <= nnz <= cap)
+  double* loss_partials;    // [gridDim.x]
+};
+
+constexpr int kTileBatch = 4;   // row steps per reduction batch
+
+// shared-memory carve-up (bytes), shared by host and device
+struct TileCgLayout {
+  int kpad, cap, warps, full_g;
+  __host__ __device__ size_t tile_off(int b) const { return (size_t)b * cap * kpad * 4; }
+  __host__ __device__ size_t ybuf_off(int b) const { return tile_off(2) + (size_t)b * kpad * 4; }
+  __host__ __device__ size_t vbuf_off(int b) const { return ybuf_off(2) + (size_t)b * warps * kpad * 4; }
+  __host__ __device__ size_t vec_off() const { return vbuf_off(2); }                                    // [warps][kpad], kFullG only
+  __host__ __device__ size_t idx_off(int s) const { return vec_off() + (full_g ? (size_t)warps * kpad * 4 : 0) + (size_t)s * cap * 4; }
+  __host__ __device__ size_t val_off(int s) const { return idx_off(3) + (size_t)s * cap * 4; }
+  __host__ __device__ size_t ubuf_off(int b) const { return val_off(3) + (size_t)b * cap * 4; }
+  __host__ __device__ size_t uy_off() const { return ubuf_off(2); }
+  __host__ __device__ size_t red_off() const { return (uy_off() + (size_t)cap * 4 + 15) & ~(size_t)15; }
+  __host__ __device__ size_t bytes() const { return red_off() + 32 * 8; }
+};
+
+template <int LPR, int C, bool kFullG>
+__global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
+  static_assert(LPR == 4 || LPR == 8 || LPR == 16 || LPR == 32, "lanes per gathered row");
+  static_assert(C == 1 || (C == 2 && LPR == 32), "two chunks per lane only at rank 256");
+  constexpr int KPAD = LPR * 4 * C;
+  constexpr int RPW = 32 / LPR;                  // gathered rows per warp per row step
+  constexpr int LOG_LPR = (LPR == 4) ? 2 : (LPR == 8) ? 3 : (LPR == 16) ? 4 : 5;
+  constexpr int SLOT_SHIFT = LOG_LPR - 2;        // slot of a lane = top two bits of its index within the group
+  constexpr int B = kTileBatch;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int W = blockDim.x >> 5, T = blockDim.x;
+  const int gi = lane / LPR, gl = lane % LPR;    // lane group within the warp, lane within the group
+  const int k = P.k;
+  const TileCgLayout L{KPAD, P.cap, W, kFullG ? 1 : 0};
+  auto tile_of = [&](int b) { return reinterpret_cast<float*>(smem_raw + L.tile_off(b)); };
+  auto ybuf_of = [&](int b) { return reinterpret_cast<float*>(smem_raw + L.ybuf_off(b)); };
+  auto vbuf_of = [&](int b) { return reinterpret_cast<float*>(smem_raw + L.vbuf_off(b)); };
+  auto idx_of = [&](int s) { return reinterpret_cast<int*>(smem_raw + L.idx_off(s)); };
+  auto val_of = [&](int s) { return reinterpret_cast<float*>(smem_raw + L.val_off(s)); };
+  auto ubuf_of = [&](int b) { return reinterpret_cast<float*>(smem_raw + L.ubuf_off(b)); };
+  float* uy = reinterpret_cast<float*>(smem_raw + L.uy_off());
+  double* red = reinterpret_cast<double*>(smem_raw + L.red_off());
+  float* vecw = reinterpret_cast<float*>(smem_raw + L.vec_off()) + (size_t)w * KPAD;   // kFullG: this warp's copy of v
+
+  const bool implicit = (P.feedback == 0);
+  const int stride = gridDim.x;
+  const long long n_list = P.n_list;
+  auto valid = [&](int i) -> bool { return (long long)blockIdx.x + (long long)i * stride < n_list; };
+  auto row_of = [&](int i) -> int {
+    const long long t = (long long)blockIdx.x + (long long)i * stride;
+    return P.row_list ? __ldg(P.row_list + t) : (int)t + P.row_begin;
+  };
+  // which features this lane holds: chunk c covers [128 c + 4 gl, +4); valid while below k (k % 4 == 0)
+  bool fvalid[C];
+  int foff[C];
+#pragma unroll
+  for (int c = 0; c < C; c++) { foff[c] = c * 128 + 4 * gl; fvalid[c] = foff[c] < k; }
+
+  // ---- staging helpers ------------------------------------------------------------------------------------
+  auto issue_meta = [&](int slot, int p, int n) {          // CSR indices / values of a row -> shared (4-byte cp.async)
+    int* si = idx_of(slot);
+    float* sv = val_of(slot);
+    for (int j = tid; j < n; j += T) {
+      cp_async_4(si + j, P.idx + p + j);
+      cp_async_4(sv + j, P.val + p + j);
+    }
+  };
+  auto issue_tile = [&](int buf, int slot, int row, int n) {   // gathered rows + warm-start y -> shared (16-byte cp.async)
+    const int* si = idx_of(slot);
+    float* tl = tile_of(buf);
+    constexpr int CPR = KPAD / 4;                            // 16-byte chunks per padded row (power of two)
+    const int total = n * CPR;
+    for (int q = tid; q < total; q += T) {
+      const int j = q / CPR, c4 = q % CPR;
+      if (4 * c4 < k) cp_async_16(tl + (size_t)j * KPAD + 4 * c4, P.X + (size_t)si[j] * k + 4 * c4);
+    }
+    if (tid < CPR && 4 * tid < k) cp_async_16(ybuf_of(buf) + 4 * tid, P.Y + (size_t)row * k + 4 * tid);
+  };
+
+  // ---- pipeline prologue ----------------------------------------------------------------------------------
+  //   row i   : rid0, n0            tile landing / landed in buffer i & 1, metadata in slot i % 3
+  //   row i+1 : rid1, n1            metadata landed (slot (i+1) % 3); tile issued at the start of row i
+  //   row i+2 : rid2, p2, n2        metadata issued at the start of row i
+  //   row i+3 : rid3                row pointers loaded during row i
+  int rid0 = -1, rid1 = -1, rid2 = -1, rid3 = -1;
+  int n0 = 0, n1 = 0, n2 = 0, p2 = 0;
+  if (valid(0)) {
+    rid0 = row_of(0);
+    const int p = __ldg(P.ptr + rid0) - P.ptr_base;
+    n0 = __ldg(P.ptr + rid0 + 1) - P.ptr_base - p;
+    issue_meta(0, p, n0);
+  }
+  if (valid(1)) {
+    rid1 = row_of(1);
+    const int p = __ldg(P.ptr + rid1) - P.ptr_base;
+    n1 = __ldg(P.ptr + rid1 + 1) - P.ptr_base - p;
+    issue_meta(1, p, n1);
+  }
+  if (valid(2)) { rid2 = row_of(2); p2 = __ldg(P.ptr + rid2) - P.ptr_base; n2 = __ldg(P.ptr + rid2 + 1) - P.ptr_base - p2; }
+  if (valid(3)) rid3 = row_of(3);
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  if (valid(0)) issue_tile(0, 0, rid0, n0);
+
+  float4 dg[C];
+#pragma unroll
+  for (int c = 0; c < C; c++)
+    dg[c] = (!kFullG && implicit && fvalid[c]) ? ldg_f4(P.diag + foff[c]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  double warp_loss = 0.0;
+  int sweep = 0;
+
+  // dot over the k features of two replicated vectors (every lane of the CTA ends with the same value)
+  auto vdot = [&](const float4 (&a)[C], const float4 (&b)[C]) -> float {
+    float s = dot4(a[0], b[0]);
+    if constexpr (C == 2) s += dot4(a[1], b[1]);
+#pragma unroll
+    for (int m = LPR / 2; m > 0; m >>= 1) s += __shfl_xor_sync(kFull, s, m);
+    return s;
+  };
+
+  for (int i = 0; valid(i); i++) {
+    const int n = n0;
+    const int buf = i & 1, slot = i % 3;
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();   // tile i and the metadata of row i+1 have landed; every warp is done with row i-1
+    // ---- prefetch (nothing here waits on memory) ----
+    if (valid(i + 1)) issue_tile(buf ^ 1, (i + 1) % 3, rid1, n1);
+    if (valid(i + 2)) issue_meta((i + 2) % 3, p2, n2);
+    int p3 = 0, p3e = 0, rid4 = -1;
+    if (valid(i + 3)) { p3 = ld_pinned_i32(P.ptr + rid3); p3e = ld_pinned_i32(P.ptr + rid3 + 1); }
+    if (valid(i + 4)) rid4 = P.row_list ? ld_pinned_i32(P.row_list + ((long long)blockIdx.x + (long long)(i + 4) * stride))
+                                        : row_of(i + 4);
+
+    const float* tl = tile_of(buf);
+    const float* sv = val_of(slot);
+    const float lam_use = implicit ? P.lambda : (P.lambda * (P.dynamic_lambda ? (float)n : 1.0f));
+    // row steps of this warp: step rs covers gathered rows (rs * W + w) * RPW + gi
+    const int n_steps_total = (n + RPW - 1) / RPW;                     // row steps over the whole CTA
+    const int my_steps = (n_steps_total > w) ? (n_steps_total - w + W - 1) / W : 0;
+
+    // One sweep: acc = sum_j f(c_j, x_j . v) x_j  (+ / - XtX v when kFullG), summed over the CTA; u_j -> ubuf.
+    //   mode 0: w = c - (c - 1) u   (implicit r0)      mode 1: w = (c - 1) u   (implicit Ap)
+    //   mode 2: w = c - u           (explicit r0)      mode 3: w = u           (explicit Ap)
+    auto run_sweep = [&](const float4 (&v)[C], int mode, int gmode, float4 (&out)[C]) {
+      float* ub = ubuf_of(sweep & 1);
+      float4 acc[C];
+#pragma unroll
+      for (int c = 0; c < C; c++) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int b0 = 0; b0 < my_steps; b0 += B) {
+        float4 x[B][C];
+        float t[B];
+#pragma unroll
+        for (int s = 0; s < B; s++) {
+          const int j = ((b0 + s) * W + w) * RPW + gi;
+          const bool ok = (b0 + s < my_steps) && (j < n);
+#pragma unroll
+          for (int c = 0; c < C; c++)
+            x[s][c] = (ok && fvalid[c]) ? *reinterpret_cast<const float4*>(tl + (size_t)j * KPAD + foff[c])
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+          t[s] = dot4(x[s][0], v[0]);
+          if constexpr (C == 2) t[s] += dot4(x[s][1], v[1]);
+        }
+        // transposing halving reduction over the LPR lanes of the group: 4 -> 2 -> 1 values, then plain butterflies
+        const bool up1 = (gl & (LPR / 2)) != 0, up2 = (gl & (LPR / 4)) != 0;
+        float o0 = (up1 ? t[2] : t[0]) + __shfl_xor_sync(kFull, up1 ? t[0] : t[2], LPR / 2);
+        float o1 = (up1 ? t[3] : t[1]) + __shfl_xor_sync(kFull, up1 ? t[1] : t[3], LPR / 2);
+        float u = (up2 ? o1 : o0) + __shfl_xor_sync(kFull, up2 ? o0 : o1, LPR / 4);
+#pragma unroll
+        for (int m = LPR / 8; m > 0; m >>= 1) u += __shfl_xor_sync(kFull, u, m);
+        // this lane's slot: row step b0 + (gl >> SLOT_SHIFT) of its group
+        const int ms = gl >> SLOT_SHIFT;
+        const int mj = ((b0 + ms) * W + w) * RPW + gi;
+        float wq = 0.0f;
+        if ((b0 + ms < my_steps) && (mj < n)) {
+          const float cj = sv[mj];
+          wq = (mode == 0) ? (cj - (cj - 1.0f) * u) : (mode == 1) ? ((cj - 1.0f) * u) : (mode == 2) ? (cj - u) : u;
+          if ((gl & ((1 << SLOT_SHIFT) - 1)) == 0) ub[mj] = u;
+        }
+#pragma unroll
+        for (int s = 0; s < B; s++) {
+          const float ws = __shfl_sync(kFull, wq, gi * LPR + (s << SLOT_SHIFT));
+#pragma unroll
+          for (int c = 0; c < C; c++) acc[c] = axpy4(ws, x[s][c], acc[c]);
+        }
+      }
+      if constexpr (kFullG) {
+        if (gmode != 0) {
+          // this (warp, group)'s slab of XtX rows: j = unit, unit + U, ...; v_j from this warp's shared copy of v
+#pragma unroll
+          for (int c = 0; c < C; c++)
+            if (gi == 0 && fvalid[c]) *reinterpret_cast<float4*>(vecw + foff[c]) = v[c];
+          __syncwarp();
+          float4 g[C];
+#pragma unroll
+          for (int c = 0; c < C; c++) g[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int U = W * RPW;
+          for (int j = w * RPW + gi; j < k; j += U) {
+            const float vj = vecw[j];
+#pragma unroll
+            for (int c = 0; c < C; c++)
+              if (fvalid[c]) g[c] = axpy4(vj, ldg_f4(P.G + (size_t)j * k + foff[c]), g[c]);
+          }
+          const float sg = (gmode == 1) ? -1.0f : 1.0f;
+#pragma unroll
+          for (int c = 0; c < C; c++) acc[c] = axpy4(sg, g[c], acc[c]);
+          __syncwarp();
+        }
+      }
+      // sum over the lane groups of the warp, then over the warps (fixed order)
+#pragma unroll
+      for (int m = LPR; m < 32; m <<= 1) {
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          acc[c].x += __shfl_xor_sync(kFull, acc[c].x, m);
+          acc[c].y += __shfl_xor_sync(kFull, acc[c].y, m);
+          acc[c].z += __shfl_xor_sync(kFull, acc[c].z, m);
+          acc[c].w += __shfl_xor_sync(kFull, acc[c].w, m);
+        }
+      }
+      float* vb = vbuf_of(sweep & 1);
+      if (gi == 0) {
+#pragma unroll
+        for (int c = 0; c < C; c++) *reinterpret_cast<float4*>(vb + (size_t)w * KPAD + foff[c]) = acc[c];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        float4 s4 = *reinterpret_cast<const float4*>(vb + foff[c]);
+        for (int ww = 1; ww < W; ww++) s4 = add4(s4, *reinterpret_cast<const float4*>(vb + (size_t)ww * KPAD + foff[c]));
+        out[c] = fvalid[c] ? s4 : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      sweep++;
+    };
+
+    // ---- CG (cg_solver_implicit / cg_solver_explicit) ---------------------------------------------------------
+    float4 x[C], r[C], p[C], v[C], Ap[C];
+#pragma unroll
+    for (int c = 0; c < C; c++)
+      x[c] = fvalid[c] ? *reinterpret_cast<const float4*>(ybuf_of(buf) + foff[c]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    run_sweep(x, implicit ? 0 : 2, (kFullG && implicit) ? 1 : 0, v);
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      if (implicit) r[c] = kFullG ? v[c] : fma4(neg4(dg[c]), x[c], v[c]);     // v - d (.) x   (wrmf_implicit.hpp:16)
+      else r[c] = axpy4(-lam_use, x[c], v[c]);                                // v - lambda_use x (wrmf_explicit.hpp:15)
+      p[c] = r[c];
+    }
+    // X_nnz' y for the loss starts as X_nnz' x0 (the u of the first sweep)
+    {
+      const float* ub = ubuf_of((sweep - 1) & 1);
+      for (int j = tid; j < n; j += T) uy[j] = ub[j];
+    }
+    float rsold = vdot(r, r);
+    // guard the reference lacks (rsold / p'Ap = 0/0 once a row has converged exactly): a zero residual skips the loop
+    const int n_cg = (rsold > 0.0f) ? P.cg_steps : 0;
+    for (int it = 0; it < n_cg; it++) {
+      run_sweep(p, implicit ? 1 : 3, (kFullG && implicit) ? 2 : 0, v);
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        if (implicit) Ap[c] = kFullG ? v[c] : fma4(dg[c], p[c], v[c]);        // XtX p + X_nnz((c-1) . X_nnz'p)  (:22)
+        else Ap[c] = axpy4(lam_use, p[c], v[c]);                              // X_nnz X_nnz' p + lambda p       (:21)
+      }
+      const float pAp = vdot(p, Ap);
+      const float a = (pAp != 0.0f) ? __fdiv_rn(rsold, pAp) : 0.0f;
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        x[c] = axpy4(a, p[c], x[c]);
+        r[c] = axpy4(-a, Ap[c], r[c]);
+      }
+      {
+        const float* ub = ubuf_of((sweep - 1) & 1);
+        for (int j = tid; j < n; j += T) uy[j] = fmaf(a, ub[j], uy[j]);   // own entries only: no barrier needed
+      }
+      if (it + 1 == n_cg) break;
+      const float rsnew = vdot(r, r);
+      if (rsnew < (float)B200ALS_CG_TOL) break;                          // identical in every warp
+      const float bt = __fdiv_rn(rsnew, rsold);
+#pragma unroll
+      for (int c = 0; c < C; c++) p[c] = axpy4(bt, p[c], r[c]);
+      rsold = rsnew;
+    }
+    if (w == 0 && gi == 0) {
+#pragma unroll
+      for (int c = 0; c < C; c++)
+        if (fvalid[c]) *reinterpret_cast<float4*>(P.Y + (size_t)rid0 * k + foff[c]) = x[c];
+    }
+    // ---- loss (wrmf_implicit.hpp:259-261 / wrmf_explicit.hpp:131-132); every thread reads back its own uy entries ----
+    {
+      float l = 0.0f;
+      for (int j = tid; j < n; j += T) {
+        const float cj = sv[j];
+        const float d = implicit ? (1.0f - uy[j]) : (cj - uy[j]);
+        l += implicit ? d * d * cj : d * d;
+      }
+      l = warp_sum(l);
+      if (w == 0) l = fmaf(lam_use, vdot(x, x), l);
+      if (lane == 0) warp_loss += (double)l;
+    }
+    // ---- advance the pipeline ----
+    n0 = n1; rid0 = rid1;
+    n1 = n2; rid1 = rid2;
+    p2 = p3 - P.ptr_base; n2 = p3e - p3; rid2 = rid3;
+    rid3 = rid4;
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  const double tot = block_sum_double((lane == 0) ? warp_loss : 0.0, red);
+  if (tid == 0) P.loss_partials[blockIdx.x] = tot;
+}
+
+}  // namespace b200als

@@ -24,6 +24,7 @@ struct SolveParams {
   const T* X;          // rank x n_src   (fixed factor matrix)
   T* Y;                // rank x n_targets (solved in place)
   const T* G;          // rank x rank, XtX + lambda*I (implicit) ; nullptr for explicit
+  const T* diag;       // [rank] CG only: X and Y are stored in the eigenbasis of XtX (eig.cuh), XtX v = diag (.) v; G unused
   int k;
   int n_targets;
   int feedback;        // 0 implicit, 1 explicit
@@ -178,8 +179,19 @@ __global__ void __launch_bounds__(256) als_cg_generic_kernel(SolveParams<T> P) {
     // r = X_nnz (c - (c-1) % X_nnz' x) - XtX x      (wrmf_implicit.hpp:16)
     // r = X_nnz (c - X_nnz' x) - lambda x            (wrmf_explicit.hpp:15)
     fused_pass<T, KPL>(P, p1, n, x, acc, implicit ? kR0Implicit : kR0Explicit);
+    T dgv[KPL];
+#pragma unroll
+    for (int e = 0; e < KPL; e++) {
+      const int f = e * 32 + lane;
+      dgv[e] = (P.diag && f < k) ? __ldg(P.diag + f) : T(0);
+    }
     if (implicit) {
-      gemv_sym<T, KPL>(P.G, k, x, Ap);
+      if (P.diag) {
+#pragma unroll
+        for (int e = 0; e < KPL; e++) Ap[e] = dgv[e] * x[e];
+      } else {
+        gemv_sym<T, KPL>(P.G, k, x, Ap);
+      }
 #pragma unroll
       for (int e = 0; e < KPL; e++) {
         r[e] = acc[e] - Ap[e];
@@ -200,7 +212,12 @@ __global__ void __launch_bounds__(256) als_cg_generic_kernel(SolveParams<T> P) {
       // Ap = X_nnz (X_nnz' p) + lambda p             (wrmf_explicit.hpp:21)
       fused_pass<T, KPL>(P, p1, n, p, acc, implicit ? kApImplicit : kApExplicit);
       if (implicit) {
-        gemv_sym<T, KPL>(P.G, k, p, Ap);
+        if (P.diag) {
+#pragma unroll
+          for (int e = 0; e < KPL; e++) Ap[e] = dgv[e] * p[e];
+        } else {
+          gemv_sym<T, KPL>(P.G, k, p, Ap);
+        }
 #pragma unroll
         for (int e = 0; e < KPL; e++) Ap[e] += acc[e];
       } else {

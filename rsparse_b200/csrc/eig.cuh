@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256) rotate_rows_kernel(const float* X, float*
     for (int t = tid; t < kRotRows * (kRotK / 4); t += 256) {
       const int c4 = t / kRotRows, rr = t % kRotRows;   // consecutive threads -> consecutive rows: conflict-free stores
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r0 + rr < n) v = __ldg(reinterpret_cast<const float4*>(X + (size_t)(r0 + rr) * kRotK) + c4);
+      if (r0 + rr < n) v = *(reinterpret_cast<const float4*>(X + (size_t)(r0 + rr) * kRotK) + c4);   // plain load: Z may alias X
       S.Xt[c4 * 4 + 0][rr] = v.x;
       S.Xt[c4 * 4 + 1][rr] = v.y;
       S.Xt[c4 * 4 + 2][rr] = v.z;
@@ -189,6 +189,84 @@ __global__ void __launch_bounds__(256) rotate_rows_kernel(const float* X, float*
       if (r < n) {
         *reinterpret_cast<float4*>(Z + (size_t)r * kRotK + tx * 4) = make_float4(acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y);
         *reinterpret_cast<float4*>(Z + (size_t)r * kRotK + 64 + tx * 4) = make_float4(acc[i][2].x, acc[i][2].y, acc[i][3].x, acc[i][3].y);
+      }
+    }
+  }
+}
+
+// Z = X * R for any rank k <= KPAD with k % 4 == 0 (fp32 FFMA2; the rank-128 kernels above / rotate_tc.cuh are the
+// fast paths).  One CTA of 256 threads per 64-row block: the block is staged transposed (Xt[f][r]) once, R streams
+// through shared memory in chunks of 32 input features (from L2: k * k * 4 bytes per block), thread tile = 4 rows x
+// (4 columns per 64-column block).  In place allowed (Z == X): a block reads all of its rows before it writes them.
+template <int KPAD>
+struct RotAnySmem {
+  float Xt[KPAD][kRotRows + 4];
+  float Rc[32][KPAD];
+};
+template <int KPAD>
+__global__ void __launch_bounds__(256) rotate_any_kernel(const float* X, float* Z, const float* __restrict__ R, long long n, int k) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RotAnySmem<KPAD>& S = *reinterpret_cast<RotAnySmem<KPAD>*>(smem_raw);
+  constexpr int NB = (KPAD + 63) / 64;           // 64-column blocks per thread
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int k4 = k / 4;
+  const long long n_blocks = (n + kRotRows - 1) / kRotRows;
+  for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+    const long long r0 = blk * kRotRows;
+    __syncthreads();
+    for (int t = tid; t < kRotRows * k4; t += 256) {
+      const int c4 = t / kRotRows, rr = t % kRotRows;   // consecutive threads -> consecutive rows: conflict-free stores
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + rr < n) v = *(reinterpret_cast<const float4*>(X + (size_t)(r0 + rr) * k) + c4);
+      S.Xt[c4 * 4 + 0][rr] = v.x;
+      S.Xt[c4 * 4 + 1][rr] = v.y;
+      S.Xt[c4 * 4 + 2][rr] = v.z;
+      S.Xt[c4 * 4 + 3][rr] = v.w;
+    }
+    float2 acc[4][NB][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int m = 0; m < NB; m++) acc[i][m][0] = acc[i][m][1] = make_float2(0.f, 0.f);
+    for (int f0 = 0; f0 < k; f0 += 32) {
+      const int fc = min(32, k - f0);
+      __syncthreads();   // Xt staged (first chunk) / previous chunk of R consumed
+      for (int t = tid; t < 32 * (KPAD / 4); t += 256) {
+        const int ff = t / (KPAD / 4), c4 = t % (KPAD / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ff < fc && c4 < k4) v = __ldg(reinterpret_cast<const float4*>(R + (size_t)(f0 + ff) * k) + c4);
+        *reinterpret_cast<float4*>(&S.Rc[ff][c4 * 4]) = v;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int ff = 0; ff < fc; ff++) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&S.Xt[f0 + ff][ty * 4]);
+        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+        for (int m = 0; m < NB; m++) {
+          if (m * 64 + tx * 4 < KPAD) {
+            const float4 b = *reinterpret_cast<const float4*>(&S.Rc[ff][m * 64 + tx * 4]);
+            const float2 b0 = make_float2(b.x, b.y), b1 = make_float2(b.z, b.w);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              const float2 a2 = make_float2(av[i], av[i]);
+              acc[i][m][0] = __ffma2_rn(a2, b0, acc[i][m][0]);
+              acc[i][m][1] = __ffma2_rn(a2, b1, acc[i][m][1]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const long long r = r0 + ty * 4 + i;
+      if (r < n) {
+#pragma unroll
+        for (int m = 0; m < NB; m++) {
+          const int col = m * 64 + tx * 4;
+          if (col < k)
+            *reinterpret_cast<float4*>(Z + (size_t)r * k + col) = make_float4(acc[i][m][0].x, acc[i][m][0].y, acc[i][m][1].x, acc[i][m][1].y);
+        }
       }
     }
   }

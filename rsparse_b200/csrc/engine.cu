@@ -26,6 +26,7 @@
 #include "als_chol_warp64.cuh"
 #include "als_generic.cuh"
 #include "als_resident.cuh"
+#include "als_cg_tile.cuh"
 #include "eig.cuh"
 #include "gram.cuh"
 #include "gram_tc.cuh"

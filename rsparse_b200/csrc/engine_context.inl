@@ -40,6 +40,18 @@ struct CscDev {
   DevBuf short_list, long_list;
   int n_short = -1, n_long = 0, n_empty = 0;
   bool all_short = false;
+  // row-length classes of the CG path (built lazily per rank by plan_rows, engine_solve.inl)
+  struct RowClass {
+    int lo = 0, hi = 0;       // rows with lo <= nnz <= hi
+    int cap = 0, warps = 0;   // tile kernel launch shape (0: not a tile class)
+    int count = 0;
+    DevBuf list;              // ascending row ids (stable compaction => deterministic launch order)
+  };
+  static constexpr int kClsResident = 0, kClsTile0 = 1, kClsLong = 4, kNumCls = 5;
+  RowClass cls[kNumCls];
+  int plan_key = -1;          // rank * 2 + resident_eligible the plan was built for
+  int plan_empty = 0;
+  int plan_single = -1;       // >= 0: every row of the block lies in this one class (chunked solves allowed)
 };
 
 template <typename T>
@@ -77,6 +89,7 @@ static int upload_csc(const b200als_csc* A, CscDev<T>& D, cudaStream_t st) {
     }
   }
   D.n_short = -1;
+  D.plan_key = -1;
   return B200ALS_OK;
 }
 
@@ -90,6 +103,12 @@ static bool gram_use_tensor_cores() {
 }
 template <typename T>
 static int run_gram(Ctx& c, const T* X, int k, long long n, double lambda, T* G, double* G64) {
+  if (n <= 0) {   // empty matrix (e.g. an empty Gram slice of a multi-GPU run): G = lambda I, no launch geometry to derive
+    CU(c.gram_partials.ensure(sizeof(double)));
+    gram_reduce_kernel<T><<<(k * k + 255) / 256, 256, 0, c.stream>>>(c.gram_partials.f64(), 0, 1, k, lambda, G, G64);
+    LAUNCHED(); CU(cudaGetLastError());
+    return B200ALS_OK;
+  }
   if constexpr (sizeof(T) == 4) {
     if (k == kTcK && n >= 8192 && gram_use_tensor_cores()) {   // small inputs: the exact fp32 FMA kernel
       long long rows_per = std::max<long long>(1024, (n + 887) / 888);

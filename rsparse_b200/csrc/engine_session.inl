@@ -295,8 +295,28 @@ extern "C" int b200als_set_shard(b200als_session* s, int which, int32_t begin, i
   return B200ALS_OK;
 }
 
-static int rotate_matrix(Ctx& c, float* M, long long n, const float* R) {
+static int rotate_matrix(Ctx& c, float* M, long long n, const float* R, int k) {
   if (n <= 0) return B200ALS_OK;
+  if (k != kTcK) {
+    // other ranks (k % 4 == 0, k <= 256): fp32 FFMA kernel, R streamed through shared memory
+    if (k % 4 != 0 || k > 256) return fail(B200ALS_EUNSUPPORTED, "change of basis needs rank % 4 == 0 and rank <= 256");
+    const long long blocks = (n + kRotRows - 1) / kRotRows;
+    auto launch = [&](auto kern, size_t smem) -> cudaError_t {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      int per_sm = 1;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
+      if (e != cudaSuccess) return e;
+      const int grid = (int)std::min<long long>(blocks, (long long)c.sm_count * std::max(1, per_sm));
+      kern<<<grid, 256, smem, c.stream>>>(M, M, R, n, k);
+      return cudaSuccess;
+    };
+    if (k <= 64) CU(launch(rotate_any_kernel<64>, sizeof(RotAnySmem<64>)));
+    else if (k <= 128) CU(launch(rotate_any_kernel<128>, sizeof(RotAnySmem<128>)));
+    else CU(launch(rotate_any_kernel<256>, sizeof(RotAnySmem<256>)));
+    LAUNCHED(); CU(cudaGetLastError());
+    return B200ALS_OK;
+  }
   // large matrices: tcgen05 3xTF32 kernel (B200ALS_ROTATE=ffma forces the fp32 FMA kernel)
   const char* env = getenv("B200ALS_ROTATE");
   const bool force_tc = env && (env[0] == 't' || env[0] == 'T');   // tests
@@ -331,7 +351,7 @@ extern "C" int b200als_set_factors(b200als_session* s, int which, const float* h
   if (!s->basis_identity) {
     convert_kk_kernel<<<(s->k * s->k + 255) / 256, 256, 0, c.stream>>>(s->B64.f64(), s->Bf.f32(), s->k, 0);
     LAUNCHED(); CU(cudaGetLastError());
-    TRY(rotate_matrix(c, s->fac[which].f32(), n, s->Bf.f32()));
+    TRY(rotate_matrix(c, s->fac[which].f32(), n, s->Bf.f32(), s->k));
   }
   CU(cudaStreamSynchronize(c.stream));
   return B200ALS_OK;
@@ -346,7 +366,7 @@ static int export_rotated(b200als_session* s, const float* dev, long long n, flo
     CU(cudaMemcpyAsync(s->scratch.p, dev, bytes, cudaMemcpyDeviceToDevice, c.stream));
     convert_kk_kernel<<<(s->k * s->k + 255) / 256, 256, 0, c.stream>>>(s->B64.f64(), s->Bf.f32(), s->k, 1);
     LAUNCHED(); CU(cudaGetLastError());
-    TRY(rotate_matrix(c, s->scratch.f32(), n, s->Bf.f32()));
+    TRY(rotate_matrix(c, s->scratch.f32(), n, s->Bf.f32(), s->k));
     CU(cudaMemcpyAsync(host, s->scratch.p, bytes, cudaMemcpyDeviceToHost, c.stream));
   }
   CU(cudaStreamSynchronize(c.stream));
@@ -392,12 +412,15 @@ extern "C" int b200als_randomize_factors(b200als_session* s, int which, uint64_t
 static int gather_ranges(b200als_session* s, int which) {
   if (!s->ranges[which].empty()) return B200ALS_OK;
   Ctx& c = ctx();
-  TRY(classify_rows(c, s->csc[which]));
+  // chunked solves (exchange overlapped with the solve) need every row of the block in ONE length class of the CG path
+  const bool cg_fast = (s->k % 4 == 0) && (s->k <= 256);
+  if (cg_fast) TRY(plan_rows(c, s->csc[which], s->k, s->k == kResK && s->opt.kernel != 10));
+  const bool one_class = cg_fast && s->csc[which].plan_single >= 0 && s->csc[which].plan_single != CscDev<float>::kClsLong;
   std::vector<int32_t> ranges(3 * g_comm.world);
   DevBuf d;
   CU(d.ensure(sizeof(int32_t) * 3 * g_comm.world));
   int32_t mine[3] = {s->shard_begin[which], s->shard_end[which],
-                     (s->csc[which].all_short && s->csc[which].n_cols >= 8 * 4096) ? 1 : 0};
+                     (one_class && s->csc[which].n_cols >= 8 * 4096) ? 1 : 0};
   CU(cudaMemcpyAsync(d.i32() + 3 * g_comm.rank, mine, sizeof(mine), cudaMemcpyHostToDevice, c.stream));
   NC(g_nccl.AllGather(d.i32() + 3 * g_comm.rank, d.p, 3, ncclInt32, g_comm.comm, c.stream));
   CU(cudaMemcpyAsync(ranges.data(), d.p, sizeof(int32_t) * 3 * g_comm.world, cudaMemcpyDeviceToHost, c.stream));
@@ -556,11 +579,13 @@ static int session_half(b200als_session* s, int which, int solver, float* Yout, 
   }
   CU(cudaEventRecord(s->ev[1], c.stream));
   // eigenbasis path: implicit CG, rank 128, resident kernel, enough rows to amortise the rotation
-  bool use_diag = implicit && solver == B200ALS_CONJUGATE_GRADIENT && s->k == kResK && o.kernel != 1 && o.kernel != 2 && !Yout;
-  if (use_diag) {
-    TRY(classify_rows(c, A));
-    if (o.kernel != 3 && (A.n_long > 0 || (long long)A.n_cols * g_comm.world < 50000)) use_diag = false;
-  }
+  // The decision uses GLOBAL quantities only (rank, options, the global number of solved rows), so every rank of a
+  // multi-GPU run takes the same branch: rows of any length are solved in the eigenbasis (resident / tile / streaming
+  // kernels all take `diag`), a shard with long rows no longer opts out on its own.
+  const long long n_solved_global = (which == B200ALS_ITEMS) ? s->n_item : s->n_user;
+  bool use_diag = implicit && solver == B200ALS_CONJUGATE_GRADIENT && (s->k % 4 == 0) && s->k <= 256 && o.kernel != 1 &&
+                  o.kernel != 2 && !Yout;
+  if (use_diag && o.kernel != 3 && o.kernel != 10 && n_solved_global < 50000) use_diag = false;
   if (use_diag) {
     const size_t jsm = sizeof(double) * (size_t)s->k * (s->k + 1);
     const int a_in_smem = (jsm + 8192 <= c.smem_optin) ? 1 : 0;
@@ -569,8 +594,8 @@ static int session_half(b200als_session* s, int which, int solver, float* Yout, 
                                                                           s->diag.f32(), s->Btmp.f64(), 30, a_in_smem);
     LAUNCHED(); CU(cudaGetLastError());
     // fixed <- fixed Q (whole matrix), solved slice <- slice Q, B <- B Q
-    TRY(rotate_matrix(c, X, n_fixed, s->Q.f32()));
-    TRY(rotate_matrix(c, Y, A.n_cols, s->Q.f32()));
+    TRY(rotate_matrix(c, X, n_fixed, s->Q.f32(), s->k));
+    TRY(rotate_matrix(c, Y, A.n_cols, s->Q.f32(), s->k));
     matmul_kk_kernel<<<(s->k * s->k + 255) / 256, 256, 0, c.stream>>>(s->B64.f64(), s->Btmp.f64(),
                                                                      s->Vt.f64(), s->k);
     LAUNCHED(); CU(cudaGetLastError());

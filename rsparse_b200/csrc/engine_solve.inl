@@ -52,6 +52,117 @@ static int launch_cg_generic(Ctx& c, const SolveParams<T>& P, int n_work, int* g
   return B200ALS_OK;
 }
 
+// ---- row-length classes of the CG path ---------------------------------------------------------------------
+// Rows are binned by their number of entries: [resident kernel: 1..80 at rank 128] / three tile-kernel classes sized so
+// that 4, 2 or 1 CTAs of als_cg_tile_kernel share an SM / longer rows (streaming kernel) / empty rows (zeroed).
+// Lists come from stable compactions (cub::DeviceSelect::If over a counting iterator): ascending row ids, so the
+// launch order, hence the loss summation order, is the same on every run.
+struct LenInRange {
+  const int32_t* ptr;
+  int lo, hi;
+  __host__ __device__ bool operator()(const int& r) const {
+    const int n = ptr[r + 1] - ptr[r];
+    return n >= lo && n <= hi;
+  }
+};
+static int tile_kpad(int k) { return k <= 16 ? 16 : k <= 32 ? 32 : k <= 64 ? 64 : k <= 128 ? 128 : 256; }
+static int tile_cap_for(int kpad, int warps, size_t budget) {
+  int cap = 0;
+  for (int cnd = 4; cnd <= 8192; cnd += 4) {
+    const TileCgLayout L{kpad, cnd, warps, 1};
+    if (L.bytes() > budget) break;
+    cap = cnd;
+  }
+  return cap;
+}
+template <typename T>
+static int plan_rows(Ctx& c, CscDev<T>& A, int k, bool resident_ok) {
+  const int key = k * 2 + (resident_ok ? 1 : 0);
+  if (A.plan_key == key) return B200ALS_OK;
+  using RC = typename CscDev<T>::RowClass;
+  const int kpad = tile_kpad(k);
+  int warpsL = 8;
+  if (const char* e = getenv("B200ALS_TILE_WARPS_L")) warpsL = std::max(1, std::min(16, atoi(e)));
+  const size_t sm_bytes = c.smem_optin + 1024;   // per-SM shared memory (the opt-in per-block limit + the 1 KB reserve)
+  const int shape[3][2] = {{4, 4}, {8, 2}, {warpsL, 1}};   // {warps per CTA, CTAs per SM} of the three tile classes
+  int lo = 1;
+  RC& R = A.cls[CscDev<T>::kClsResident];
+  R.lo = 1; R.hi = resident_ok ? kResMaxN : 0; R.cap = 0; R.warps = 0;
+  if (resident_ok) lo = kResMaxN + 1;
+  for (int t = 0; t < 3; t++) {
+    RC& C = A.cls[CscDev<T>::kClsTile0 + t];
+    C.warps = shape[t][0];
+    C.cap = tile_cap_for(kpad, C.warps, sm_bytes / shape[t][1] - 1024);
+    C.lo = lo;
+    C.hi = std::max(lo - 1, C.cap);
+    lo = C.hi + 1;
+  }
+  RC& Lg = A.cls[CscDev<T>::kClsLong];
+  Lg.lo = lo; Lg.hi = std::numeric_limits<int>::max(); Lg.cap = 0; Lg.warps = 0;
+  DevBuf counts, temp;
+  CU(counts.ensure(sizeof(int) * CscDev<T>::kNumCls));
+  CU(cudaMemsetAsync(counts.p, 0, sizeof(int) * CscDev<T>::kNumCls, c.stream));
+  if (A.n_cols > 0) {
+    cub::CountingInputIterator<int> rows(0);
+    size_t temp_bytes = 0;
+    CU(cub::DeviceSelect::If(nullptr, temp_bytes, rows, (int32_t*)nullptr, (int*)nullptr, A.n_cols, LenInRange{nullptr, 0, 0}, c.stream));
+    CU(temp.ensure(temp_bytes));
+    for (int q = 0; q < CscDev<T>::kNumCls; q++) {
+      RC& C = A.cls[q];
+      if (C.hi < C.lo) continue;
+      CU(C.list.ensure(sizeof(int32_t) * (size_t)A.n_cols));
+      CU(cub::DeviceSelect::If(temp.p, temp_bytes, rows, C.list.i32(), counts.i32() + q, A.n_cols,
+                               LenInRange{A.ptr.i32(), C.lo, C.hi}, c.stream));
+      LAUNCHED();
+    }
+  }
+  int h[CscDev<T>::kNumCls];
+  CU(cudaMemcpyAsync(h, counts.p, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaStreamSynchronize(c.stream));
+  int total = 0;
+  A.plan_single = -1;
+  for (int q = 0; q < CscDev<T>::kNumCls; q++) {
+    A.cls[q].count = (A.cls[q].hi < A.cls[q].lo) ? 0 : h[q];
+    total += A.cls[q].count;
+    if (A.cls[q].count == A.n_cols && A.n_cols > 0) A.plan_single = q;
+  }
+  A.plan_empty = A.n_cols - total;
+  A.plan_key = key;
+  return B200ALS_OK;
+}
+
+// launches als_cg_tile_kernel for one length class; *grid_out = CTAs launched (loss partials to sum)
+static int launch_cg_tile(Ctx& c, TileCgParams P, int warps, bool full_g, int* grid_out) {
+  const int kpad = tile_kpad(P.k);
+  const TileCgLayout L{kpad, P.cap, warps, full_g ? 1 : 0};
+  const size_t smem = L.bytes();
+  if (smem > c.smem_optin) return fail(B200ALS_EUNSUPPORTED, "tile kernel: row class does not fit shared memory");
+  int per_sm = 1, grid = 1;
+  const int threads = warps * 32;
+  auto launch = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+    if (e != cudaSuccess) return e;
+    grid = std::min(c.sm_count * std::max(1, per_sm), P.n_list);
+    kern<<<grid, threads, smem, c.stream>>>(P);
+    return cudaSuccess;
+  };
+#define B200ALS_TILE_CASE(LPR, CC)                                                             \
+  CU(full_g ? launch(als_cg_tile_kernel<LPR, CC, true>) : launch(als_cg_tile_kernel<LPR, CC, false>))
+  switch (kpad) {
+    case 16: B200ALS_TILE_CASE(4, 1); break;
+    case 32: B200ALS_TILE_CASE(8, 1); break;
+    case 64: B200ALS_TILE_CASE(16, 1); break;
+    case 128: B200ALS_TILE_CASE(32, 1); break;
+    default: B200ALS_TILE_CASE(32, 2); break;
+  }
+#undef B200ALS_TILE_CASE
+  LAUNCHED(); CU(cudaGetLastError());
+  *grid_out = grid;
+  return B200ALS_OK;
+}
+
 // Runs one half-iteration on device data.  `diag`/`rotated`: the caller has put X and Y in the eigenbasis of
 // G (implicit CG, rank 128, resident kernel) and passes the eigenvalues.  Accumulates the loss numerator
 // (sum over solved rows) into c.loss_acc[0].
@@ -81,6 +192,7 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
   P.X = X;
   P.Y = Y;
   P.G = (o.feedback == B200ALS_IMPLICIT) ? G : nullptr;
+  P.diag = nullptr;
   P.k = k;
   P.n_targets = n_rows_here;
   P.row_begin = sub_range ? o.row_begin : 0;
@@ -95,7 +207,7 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
   P.ptr_base = 0;
   P.ticket = c.ticket.u64();
   P.status = c.status.i32();
-  const int max_grid = c.sm_count * 8;
+  const int max_grid = c.sm_count * 32;
   CU(c.loss_partials.ensure(sizeof(double) * (size_t)max_grid));
   P.loss_partials = c.loss_partials.f64();
 
@@ -155,11 +267,16 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
         const bool rows_kernel = (o.kernel != 5);
         // persistent CTAs: exactly as many as are co-resident (registers AND shared memory), else a second wave
         int per_sm = 1, grid = 1;
+        const int min_per_sm = (k == 128 && (o.kernel == 6 || o.kernel == 7)) ? 3 : 1;
         auto launch = [&](auto kern, int threads, size_t smem) -> cudaError_t {
           cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
           if (e != cudaSuccess) return e;
           e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
           if (e != cudaSuccess) return e;
+          // kernels that allocate tensor memory report 1 CTA/SM here although 3 are co-resident (registers, shared
+          // memory and 3 x 128 TMEM columns all fit): measured round 2 (profiles/r2/chol_tc_occupancy.txt)
+          per_sm = std::max(per_sm, min_per_sm);
+          if (const char* e = getenv("B200ALS_CHOL_PER_SM")) per_sm = std::max(1, atoi(e));
           grid = std::min(c.sm_count * std::max(1, per_sm), A.n_short);
           kern<<<grid, threads, smem, c.stream>>>(P);
           return cudaSuccess;
@@ -186,23 +303,35 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
   }
 
   // ---- conjugate gradient ----
-  bool resident = false;
+  // fp32, rank % 4 == 0, rank <= 256, no bias terms: rows are binned by length (plan_rows) -- the register-resident kernel
+  // takes rows of <= 80 entries at rank 128, the shared-memory tile kernel every other row that fits its buffers, the
+  // streaming kernel the rest.  kernel = 1 forces the streaming kernel (the reference's arithmetic, full XtX),
+  // kernel = 10 keeps the resident kernel out (tests / A-B runs of the tile kernel).
+  bool tile_ok = false;
   if constexpr (sizeof(T) == 4) {
-    resident = (k == kResK) && (o.kernel != 1) && (o.feedback == B200ALS_EXPLICIT || G || diag) && !biased;
-    if (o.kernel == 2 && !resident) return fail(B200ALS_EUNSUPPORTED, "resident kernel requires rank 128 fp32");
+    tile_ok = (k % 4 == 0) && (k <= 256) && (o.kernel != 1) && (o.feedback == B200ALS_EXPLICIT || G || diag) && !biased;
+    if (o.kernel == 2 && !(tile_ok && k == kResK)) return fail(B200ALS_EUNSUPPORTED, "resident kernel requires rank 128 fp32");
   }
-  if (!resident) {
-    if (diag && !G) return fail(B200ALS_EINVAL, "generic CG needs the full XtX");
+  if (!tile_ok) {
+    if (diag && !G) {
+      if constexpr (sizeof(T) == 4) P.diag = (const T*)diag;
+      else return fail(B200ALS_EINVAL, "the eigenbasis path is fp32 only");
+    }
     return run_generic_cg(nullptr, 0);
   }
   if constexpr (sizeof(T) == 4) {
-    TRY(classify_rows(c, A));
-    if (sub_range && !A.all_short) return fail(B200ALS_EINVAL, "row sub-ranges need a block without empty or long rows");
-    if (A.n_empty > 0) {
+    using CD = CscDev<T>;
+    const bool resident_ok = (k == kResK) && (o.kernel != 10);
+    TRY(plan_rows(c, A, k, resident_ok));
+    if (sub_range && (A.plan_single < 0 || A.plan_single == CD::kClsLong))
+      return fail(B200ALS_EINVAL, "row sub-ranges need a block whose rows all fall into one length class");
+    if (A.plan_empty > 0) {
       zero_empty_rows_kernel<T><<<(unsigned)(((long long)A.n_cols * k + 255) / 256), 256, 0, c.stream>>>(P.ptr, A.n_cols, k, Y);
       LAUNCHED(); CU(cudaGetLastError());
     }
-    if (A.n_short > 0) {
+    const bool full_g = (o.feedback == B200ALS_IMPLICIT) && !diag;
+    const typename CD::RowClass& RC = A.cls[CD::kClsResident];
+    if (RC.count > 0) {
       ResidentParams R;
       R.ptr = P.ptr;
       R.idx = P.idx;
@@ -215,8 +344,8 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
       R.cg_steps = o.cg_steps;
       R.dynamic_lambda = o.dynamic_lambda;
       R.lambda = (float)o.lambda;
-      R.row_list = A.all_short ? nullptr : A.short_list.i32();
-      R.n_list = sub_range ? n_rows_here : A.n_short;
+      R.row_list = (A.plan_single == CD::kClsResident) ? nullptr : RC.list.i32();
+      R.n_list = sub_range ? n_rows_here : RC.count;
       R.n_list_dev = nullptr;
       R.ptr_base = 0;
       R.row_begin = sub_range ? o.row_begin : 0;
@@ -224,7 +353,6 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
       const int ctas = (o.ctas == 3 || o.ctas == 4) ? o.ctas : kDefaultCtas;
       const int grid = std::min(c.sm_count * ctas, R.n_list);
       const size_t smem = sizeof(ResidentSmem);
-      const bool full_g = (o.feedback == B200ALS_IMPLICIT) && !diag;
       auto launch = [&](auto kern) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -243,9 +371,38 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
       sum_partials_kernel<<<1, 32, 0, c.stream>>>(P.loss_partials, grid, c.loss_acc.f64(), 1);
       LAUNCHED(); CU(cudaGetLastError());
     }
-    if (A.n_long > 0) {
-      if (diag && !G) return fail(B200ALS_EINVAL, "rows longer than 80 need the full XtX for the streaming kernel");
-      TRY(run_generic_cg(A.long_list.i32(), A.n_long));
+    for (int t = 0; t < 3; t++) {
+      const int q = CD::kClsTile0 + t;
+      const typename CD::RowClass& TC = A.cls[q];
+      if (TC.count == 0) continue;
+      TileCgParams TP;
+      TP.ptr = P.ptr;
+      TP.idx = P.idx;
+      TP.val = (const float*)P.val;
+      TP.X = (const float*)X;
+      TP.Y = (float*)Y;
+      TP.diag = diag;
+      TP.G = (const float*)G;
+      TP.k = k;
+      TP.feedback = o.feedback;
+      TP.cg_steps = o.cg_steps;
+      TP.dynamic_lambda = o.dynamic_lambda;
+      TP.lambda = (float)o.lambda;
+      TP.row_list = (A.plan_single == q) ? nullptr : TC.list.i32();
+      TP.n_list = sub_range ? n_rows_here : TC.count;
+      TP.ptr_base = 0;
+      TP.row_begin = sub_range ? o.row_begin : 0;
+      TP.cap = TC.cap;
+      TP.loss_partials = P.loss_partials;
+      int grid = 0;
+      TRY(launch_cg_tile(c, TP, TC.warps, full_g, &grid));
+      sum_partials_kernel<<<1, 32, 0, c.stream>>>(P.loss_partials, grid, c.loss_acc.f64(), 1);
+      LAUNCHED(); CU(cudaGetLastError());
+    }
+    const typename CD::RowClass& LC = A.cls[CD::kClsLong];
+    if (LC.count > 0) {
+      if (diag && !G) P.diag = (const T*)diag;
+      TRY(run_generic_cg(LC.list.i32(), LC.count));
     }
   }
   return B200ALS_OK;

@@ -146,7 +146,7 @@ static PipeCtx& pipe_ctx() {
   static thread_local PipeCtx p;
   return p;
 }
-static int rotate_matrix(Ctx& c, float* M, long long n, const float* R);
+static int rotate_matrix(Ctx& c, float* M, long long n, const float* R, int k);
 
 static int stateless_pipelined(const b200als_csc* A, const float* X, float* Y, const float* XtX, const float* cnt_X,
                                const HalfOpts& o, double* loss) {
@@ -213,7 +213,7 @@ static int stateless_pipelined(const b200als_csc* A, const float* X, float* Y, c
     LAUNCHED(); CU(cudaGetLastError());
     diag_matrix_kernel<<<(k * k + 255) / 256, 256, 0, c.stream>>>(pc.diag.f32(), pc.Gdiag.f32(), k);
     LAUNCHED(); CU(cudaGetLastError());
-    TRY(rotate_matrix(c, pc.X.f32(), A->n_rows, pc.Q.f32()));
+    TRY(rotate_matrix(c, pc.X.f32(), A->n_rows, pc.Q.f32(), k));
     diag = pc.diag.f32();
     Glong = pc.Gdiag.f32();
   }
@@ -257,7 +257,7 @@ static int stateless_pipelined(const b200als_csc* A, const float* X, float* Y, c
     LAUNCHED(); CU(cudaGetLastError());
     zero_empty_rows_kernel<float><<<(unsigned)(((long long)nr * k + 255) / 256), 256, 0, c.stream>>>(b.ptr.i32(), nr, k, b.Y.f32());
     LAUNCHED(); CU(cudaGetLastError());
-    if (implicit) TRY(rotate_matrix(c, b.Y.f32(), nr, pc.Q.f32()));
+    if (implicit) TRY(rotate_matrix(c, b.Y.f32(), nr, pc.Q.f32(), k));
     ResidentParams R;
     R.ptr = b.ptr.i32(); R.idx = b.idx.i32(); R.val = b.val32.f32();
     R.X = pc.X.f32(); R.Y = b.Y.f32(); R.diag = diag; R.G = nullptr;
@@ -282,7 +282,7 @@ static int stateless_pipelined(const b200als_csc* A, const float* X, float* Y, c
       sum_partials_kernel<<<1, 32, 0, c.stream>>>(c.loss_partials.f64(), gen_grid, c.loss_acc.f64(), 1);
       LAUNCHED(); CU(cudaGetLastError());
     }
-    if (implicit) TRY(rotate_matrix(c, b.Y.f32(), nr, pc.Qt.f32()));
+    if (implicit) TRY(rotate_matrix(c, b.Y.f32(), nr, pc.Qt.f32(), k));
     CU(cudaEventRecord(b.compute_done, c.stream));
     // device -> host
     CU(cudaStreamWaitEvent(pc.d2h, b.compute_done, 0));

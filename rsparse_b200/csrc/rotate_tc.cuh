@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(128) rotate_tc_kernel(const float* X, float* Z
     for (int i = 0; i < 8; i++) {
       const int rr = warp * 32 + i * 4 + (lane >> 3), c4 = lane & 7;
       const long long row = tile * 128 + rr;
-      v[i] = (tile < n_tiles && row < n) ? __ldg(reinterpret_cast<const float4*>(X + (size_t)row * kTcK + q * 32) + c4)
+      v[i] = (tile < n_tiles && row < n) ? *(reinterpret_cast<const float4*>(X + (size_t)row * kTcK + q * 32) + c4)   /* plain load: Z may alias X */
                                          : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };

@@ -79,8 +79,8 @@ def test_cg_kernel_variants_agree_with_reference(name, kernel, stage, cases, gol
     """generic streaming (1), register-resident with full XtX (2), register-resident in the eigenbasis (3);
     tile staging by cp.async.bulk (stage 1) or cp.async (stage 2)."""
     c = cases[name]
-    if kernel == 3 and (c["feedback"] != "implicit" or np.diff(c["ptr"]).max() > 80):
-        pytest.skip("eigenbasis path: implicit feedback, rows <= 80 nnz")
+    if kernel == 3 and c["feedback"] != "implicit":
+        pytest.skip("eigenbasis path: implicit feedback")
     s = _session_for(c, kernel, stage=stage)
     loss = s.half_iteration(L.USERS)
     Y = s.get_factors(L.USERS)
@@ -90,6 +90,26 @@ def test_cg_kernel_variants_agree_with_reference(name, kernel, stage, cases, gol
     assert relF(Y, ref) < TOL_F32
     assert abs(loss - float(golden_half[name + "/loss_f64"])) <= TOL_F32 * abs(loss)
     assert relF(X, c["X"]) < 2e-6   # the fixed matrix comes back unchanged (rotated out of the eigenbasis for kernel 3)
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if "_cg" in n and wc.half_iteration_cases()[n]["X"].shape[1] % 4 == 0])
+@pytest.mark.parametrize("kernel", [10, 0])
+def test_tile_cg_kernel_in_session(name, kernel, cases, golden_half):
+    """als_cg_tile_kernel (shared-memory tile, any rank % 4 == 0 up to 256, rows binned by length) through the
+    device-resident session: kernel = 10 keeps the register-resident kernel out and forces the eigenbasis for implicit
+    feedback (tile kernel with `diag`; rows beyond the largest tile class take the streaming kernel with `diag`),
+    kernel = 0 is the automatic choice.  Ranks 8 ... 256, ragged / empty / long rows, implicit and explicit."""
+    c = cases[name]
+    s = _session_for(c, kernel)
+    loss = s.half_iteration(L.USERS)
+    Y = s.get_factors(L.USERS)
+    X = s.get_factors(L.ITEMS)
+    s.close()
+    ref = golden_half[name + "/Y_f64"]
+    assert relF(Y, ref) < TOL_F32, relF(Y, ref)
+    assert abs(loss - float(golden_half[name + "/loss_f64"])) <= TOL_F32 * abs(loss)
+    assert relF(X, c["X"]) < 2e-6
+    assert np.all(Y[np.diff(c["ptr"]) == 0] == 0)
 
 
 def test_row_results_depend_only_on_their_own_indices(cases):
