@@ -28,7 +28,8 @@ def build(force=False):
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
         subprocess.check_call(["make", "-C", _HERE, os.path.join(_HERE, "liboracle_wrmf.so")])
     ref = os.path.join(_HERE, "_ref", "libref_wrmf.so")
-    if os.path.isdir("/root/reference/inst/include") and (force or not os.path.exists(ref)):
+    ref2 = os.path.join(_HERE, "_ref", "libref_topk.so")
+    if os.path.isdir("/root/reference/inst/include") and (force or not os.path.exists(ref) or not os.path.exists(ref2)):
         subprocess.check_call(["sh", os.path.join(_HERE, "build_ref.sh")])
 
 
@@ -65,6 +66,39 @@ def ref():
                      "ref_initialize_biases_f32", "ref_initialize_biases_f64"):
             getattr(_ref, name).restype = C.c_double
     return _ref
+
+
+_ref_topk = None
+
+
+def ref_topk_available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libref_topk.so"))
+
+
+def ref_top_product(x, y, k, nr_ptr=None, nr_idx=None, exclude_1based=(), glob_mean=0.0, n_threads=1):
+    """The reference's own `top_product` (src/matrix_top_product.cpp:20-102, compiled in place by build_ref.sh).
+    x: (n_user, rank), y: (n_item, rank), rows = embeddings; same return convention as oracle.topk.top_product:
+    (idx 1-based int32 (n_user, k) with NA_integer_, scores float64 (n_user, k) with NaN)."""
+    global _ref_topk
+    if _ref_topk is None:
+        build()
+        _ref_topk = C.CDLL(os.path.join(_HERE, "_ref", "libref_topk.so"))
+    x64 = np.asfortranarray(np.asarray(x, np.float64))                   # n_user x rank, column-major
+    y64 = np.ascontiguousarray(np.asarray(y, np.float64))                # (n_item, rank) C-order == rank x n_item column-major
+    n_user, rank = x64.shape
+    n_item = y64.shape[0]
+    if nr_ptr is None:
+        nr_ptr, nr_idx = np.zeros(n_user + 1, np.int32), np.zeros(0, np.int32)
+    nr_ptr = np.ascontiguousarray(nr_ptr, np.int32)
+    nr_idx = np.ascontiguousarray(nr_idx, np.int32)
+    nr_x = np.ones(len(nr_idx), np.float64)
+    ex = np.ascontiguousarray(np.asarray(list(exclude_1based), dtype=np.int32))
+    out_idx = np.empty((k, n_user), np.int32)        # column-major n_user x k
+    out_sc = np.empty((k, n_user), np.float64)
+    _ref_topk.ref_top_product(_p(x64), C.c_int(n_user), C.c_int(rank), _p(y64), C.c_int(n_item), C.c_uint(k),
+                              C.c_uint(n_threads), _p(nr_ptr), _p(nr_idx), _p(nr_x), C.c_size_t(len(nr_idx)), _p(ex),
+                              C.c_int(len(ex)), C.c_double(glob_mean), _p(out_idx), _p(out_sc))
+    return np.ascontiguousarray(out_idx.T), np.ascontiguousarray(out_sc.T)
 
 
 def max_threads():

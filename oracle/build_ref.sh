@@ -14,3 +14,8 @@ g++ $CXXFLAGS $INC -DREF_IMPLICIT -c "$HERE/ref_shim.cpp" -o "$HERE/_ref/ref_imp
 g++ $CXXFLAGS $INC -DREF_EXPLICIT -c "$HERE/ref_shim.cpp" -o "$HERE/_ref/ref_explicit.o"
 g++ -shared -fopenmp "$HERE/_ref/ref_implicit.o" "$HERE/_ref/ref_explicit.o" -o "$HERE/_ref/libref_wrmf.so"
 echo "built $HERE/_ref/libref_wrmf.so"
+# top_product (src/matrix_top_product.cpp:20-102), compiled in place against oracle/mini_rcpp + oracle/mini_arma
+g++ $CXXFLAGS -I "$HERE/mini_rcpp" $INC -I "$REF/src" -c "$REF/src/matrix_top_product.cpp" -o "$HERE/_ref/ref_topk_src.o"
+g++ $CXXFLAGS -I "$HERE/mini_rcpp" $INC -I "$REF/src" -c "$HERE/ref_topk_shim.cpp" -o "$HERE/_ref/ref_topk_shim.o"
+g++ -shared -fopenmp "$HERE/_ref/ref_topk_src.o" "$HERE/_ref/ref_topk_shim.o" -o "$HERE/_ref/libref_topk.so"
+echo "built $HERE/_ref/libref_topk.so"

@@ -2,7 +2,10 @@
 (/root/reference/src/matrix_top_product.cpp:20-102), for SMALL cases only: the score row in double
 (`arma::rowvec yvec = x.row(j) * y`, :54), the walk over items in increasing index with the two exclusion
 rules (:63-78), the size-k min-heap of (score, index) pairs with the strict replacement test
-`q.top().first < val` (:80-86) and the fill-from-the-end output order (:88-95)."""
+`q.top().first < val` (:80-86) and the fill-from-the-end output order (:88-95).
+PINNED: tests/test_oracle.py::test_topk_restatement_is_pinned_to_the_reference checks it against the reference's own
+source compiled in place (oracle/ref_topk_shim.cpp -> oracle/_ref/libref_topk.so) and the committed outputs of that
+binary (tests/golden/topk.npz)."""
 import heapq
 
 import numpy as np

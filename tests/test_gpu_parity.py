@@ -420,6 +420,23 @@ def test_top_product_matches_reference_semantics(n_user, n_item, rank, k):
     assert np.array_equal(idx[0], np.argsort(-full[0], kind="stable")[:min(k, n_item)])
 
 
+@pytest.mark.parametrize("name", sorted(wc.topk_cases()))
+def test_top_product_vs_reference_golden(name):
+    """b200als_top_product against the outputs of the reference's own top_product (tests/golden/topk.npz, generated
+    from src/matrix_top_product.cpp compiled in place): indices bit-exact -- exact ties, NA padding, per-user and
+    global exclusions included -- scores to rounding."""
+    import os
+    from rsparse_b200 import top_product
+    c = wc.topk_cases()[name]
+    g = np.load(os.path.join(wc.GOLDEN, "topk.npz"))
+    idx, sc = top_product(c["x"], c["y"], c["k"], c["nr"], c["exclude"], glob_mean=c["glob_mean"])
+    gi = g[name + "/idx"]
+    ref0 = np.where(gi == -2147483648, -1, gi - 1)
+    assert np.array_equal(idx, ref0)
+    ok = ref0 >= 0
+    assert np.allclose(sc[ok], g[name + "/scores"][ok], rtol=1e-12, atol=0) and np.all(np.isnan(sc[~ok]))
+
+
 def test_top_product_ties_follow_the_heap_rule():
     """All-zero user embeddings give equal scores everywhere: the heap keeps the FIRST k items and emits them by
     decreasing index (src/matrix_top_product.cpp:80-95)."""

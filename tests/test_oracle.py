@@ -95,3 +95,24 @@ def test_als_trace_oracle_vs_reference_golden(golden_traces):
     G = I.T @ I + lam * np.eye(k)
     oracle.als_implicit(*users, I, res, G, lam, wc.CHOL, 3, 2)
     assert relF(res, golden_traces[name + "/user_emb_f64"]) < 1e-10
+
+
+@pytest.mark.parametrize("name", sorted(wc.topk_cases()))
+def test_topk_restatement_is_pinned_to_the_reference(name):
+    """oracle/topk.py against (1) the committed outputs of the reference's own top_product
+    (tests/golden/topk.npz, made by tests/golden/make_golden_topk.py from src/matrix_top_product.cpp compiled in
+    place) and (2) that binary itself when it is present: indices identical (ties and NA padding included),
+    scores equal to rounding (the score row is a BLAS-free dot product in both, summed in a different order)."""
+    import os
+    from oracle.topk import top_product as py_top
+    c = wc.topk_cases()[name]
+    nr = c["nr"]
+    args = (c["x"], c["y"], c["k"], None if nr is None else nr.indptr, None if nr is None else nr.indices,
+            [e + 1 for e in c["exclude"]], c["glob_mean"])
+    idx, sc = py_top(*args)
+    g = np.load(os.path.join(wc.GOLDEN, "topk.npz"))
+    assert np.array_equal(idx, g[name + "/idx"])
+    assert np.allclose(sc, g[name + "/scores"], rtol=1e-12, atol=0, equal_nan=True)
+    if oracle.ref_topk_available():
+        ridx, rsc = oracle.ref_top_product(*args)
+        assert np.array_equal(ridx, g[name + "/idx"]) and np.array_equal(rsc, g[name + "/scores"], equal_nan=True)

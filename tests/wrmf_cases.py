@@ -169,3 +169,33 @@ def bias_cases():
     add("bias_rag_explicit_chol", rag_e, 900, 10, "explicit", CHOL, 0.1, 50, True, False, cnt_X=np.ones(900, np.float32))
     add("bias_rag_explicit_nnls", rag_e, 900, 10, "explicit", NNLS, 0.1, 51, True, True, cnt_X=np.ones(900, np.float32))
     return C
+
+
+def topk_cases():
+    """name -> dict(x, y, k, nr (scipy CSR or None), exclude (0-based), glob_mean): inputs of `top_product`
+    (src/matrix_top_product.cpp:20-102).  Includes exact ties (duplicated item rows, all-zero users), NA padding
+    (k > number of admissible items), per-user and global exclusions."""
+    import scipy.sparse as sp
+    C = {}
+
+    def add(name, n_user, n_item, rank, k, seed, density=0.1, exclude=(), glob_mean=0.0, with_nr=True, dup=False, zero_users=0):
+        x = det_factors(n_user, rank, seed, 1.0)
+        y = det_factors(n_item, rank, seed + 1, 1.0)
+        if dup:                                     # exact score ties: every third item repeats its predecessor
+            y[2::3] = y[1::3][: len(y[2::3])]
+        if zero_users:
+            x[:zero_users] = 0.0
+        nr = None
+        if with_nr:
+            u = det_uniform(n_user * n_item, seed + 2).reshape(n_user, n_item)
+            nr = sp.csr_matrix((u < density).astype(np.float64))
+            nr.sort_indices()
+        C[name] = dict(x=x, y=y, k=k, nr=nr, exclude=list(exclude), glob_mean=glob_mean)
+
+    add("plain_100x50_r10_k10", 100, 50, 10, 10, 150, with_nr=False)
+    add("filter_70x333_r16_k7", 70, 333, 16, 7, 433)
+    add("filter_excl_33x1000_r128_k40", 33, 1000, 128, 40, 1100, exclude=(1, 3, 999), glob_mean=0.25)
+    add("na_padding_5x20_r4_k20", 5, 20, 4, 20, 120, density=0.3, exclude=(0, 7))
+    add("ties_40x90_r8_k12", 40, 90, 8, 12, 77, dup=True, zero_users=3, exclude=(0,))
+    add("ties_nofilter_9x30_r4_k30", 9, 30, 4, 30, 78, with_nr=False, dup=True, zero_users=2)
+    return C
