@@ -246,7 +246,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("B200ALS_WORKLOAD", "c3"), choices=sorted(WORKLOADS) + ["topk"])
-    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic; CG: 2 resident full-XtX, 3 resident eigenbasis; Cholesky: 4 row-per-thread (default), 5 tile")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic; CG: 2 resident full-XtX, 3 resident eigenbasis, 10 shared-memory tile kernel only; Cholesky: 0 = tcgen05-Gram rows kernel (rank 128) / warp per system (rank 64), 4 FFMA2-Gram rows kernel")
     ap.add_argument("--stage", type=int, default=0, help="resident-kernel tile staging: 0 default, 1 cp.async.bulk, 2 cp.async")
     ap.add_argument("--ctas", type=int, default=0, help="CTAs per SM the kernel is built for: CG resident 0/3/4, rank-128 row-per-thread Cholesky 0/2/3")
     ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="rows in the CPU baseline sample")
@@ -326,9 +326,9 @@ def main():
     achieved = n_local * BYTES_PER_ROW(nnz, k) / (solve_ms / 1e3) / 1e9
     if solver == L.CHOLESKY:   # compute-bound path: 2nk^2 + 2nk + k^3/3 + 2k^2 flop per row
         fl = 2 * nnz * k * k + 2 * nnz * k + k ** 3 / 3 + 2 * k * k
-        roofline = {"bound": "tensor", "kernel": ("als_chol_rows_kernel (row-per-thread panel Cholesky, fp32 FFMA2 Gram; no tensor cores yet)"
-                                                 if args.kernel != 5 else
-                                                 "als_chol_tile_kernel (fp32 FFMA2 Gram + register-block Cholesky; no tensor cores yet)"),
+        roofline = {"bound": "tensor", "kernel": ("als_chol_rows_kernel<128,3,1> (row-per-thread panel Cholesky, per-row Gram on tcgen05 3xTF32)" if (k == 128 and args.kernel != 4)
+                                                 else "als_chol_warp64_kernel (warp per system, fp32 FFMA2)" if (k == 64 and args.kernel != 4)
+                                                 else "als_chol_rows_kernel (row-per-thread panel Cholesky, fp32 FFMA2 Gram)"),
                     "achieved": n_local * fl / (solve_ms / 1e3) / 1e12, "peak": None, "unit": "TFLOP/s", "frac": None,
                     "traffic": None, "kernel_ms": solve_ms}
     else:
@@ -339,11 +339,19 @@ def main():
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": n_local * BYTES_PER_ROW(nnz, k),
                 "kernel_ms": solve_ms, "fp32_tflops": n_local * FLOPS_PER_ROW(nnz, k, cg) / (solve_ms / 1e3) / 1e12}
     if solver == L.CHOLESKY:
+        # rank 128: the per-row Gram (2nk^2 of the flops) runs on tcgen05 as 3xTF32 => effective tensor peak = TF32 dense / 3
+        # = measured bf16 sustained / 2 / 3; rank 64: fp32 FFMA2 kernel => nominal fp32 peak (148 SMs x 128 lanes x 2 x clock)
         try:
-            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
-            roofline["peak"], roofline["frac"] = pk, roofline["achieved"] / pk
+            pk16 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
         except Exception:
-            pass
+            pk16 = 1364.4
+        if k == 128 and args.kernel != 4:
+            pk, src = pk16 / 6.0, "3xTF32 effective = measured bf16 sustained / 2 (TF32 rate) / 3 (split passes)"
+        else:
+            roofline["bound"] = "fp32"
+            pk, src = 148 * 128 * 2 * 1.965e9 / 1e12, "nominal fp32 FMA peak (148 SMs x 128 lanes x 2 flop x 1.965 GHz)"
+        roofline["peak"], roofline["frac"], roofline["peak_source"] = pk, roofline["achieved"] / pk, src
+        roofline["gram_share_of_flops"] = 2 * nnz * k * k / fl
 
     # ---- e2e: stateless C-ABI call, host buffers, copies inside the timed region -----------------------
     e2e = None

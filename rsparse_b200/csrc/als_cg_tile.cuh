@@ -16,8 +16,11 @@
 //   * a gathered row of k floats is held by LPR = KPAD/4 (<= 32) lanes as one float4 each (two float4 per lane at
 //     rank 256), so a warp works on 32/LPR gathered rows at a time and small ranks do not idle lanes;
 //   * a CG step is one sweep over the tile: per batch of 4 row steps  u_j = x_j . v  (packed FFMA2 + a transposing
-//     halving reduction: 3 + log2(LPR/4) shuffles for 4 x 32/LPR rows),  w_j = f(c_j, u_j)  by the owner lanes,
-//     4 broadcast shuffles,  acc += w_j x_j  from the same registers; then one cross-warp sum through shared memory;
+//     halving reduction: 3 + log2(LPR/4) shuffles for 4 x 32/LPR rows, select-free because every lane loads its
+//     batch permuted by the slot it will own),  w_j = k0 c_j + (k1 c_j + k2) u_j  by the owner lanes, 4 broadcast
+//     shuffles,  acc += w_j x_j  from the same registers; whole batches run without bounds checks (the padding
+//     columns of the shared-memory tile are zero for the whole kernel); then one cross-warp sum through shared
+//     memory (two-stage when the CTA has more than 4 warps);
 //   * XtX p: d (.) p in the eigenbasis of XtX (eig.cuh), or (kFullG) every (warp, lane group) multiplies its slab
 //     of XtX rows from L1/L2 and the slabs ride the same reduction; lambda_use p for explicit feedback;
 //   * the loss term X_nnz' y comes from the u vectors already computed (X_nnz'y = X_nnz'x0 + sum_k alpha_k X_nnz'p_k).
@@ -56,7 +59,8 @@ struct TileCgLayout {
   __host__ __device__ size_t tile_off(int b) const { return (size_t)b * cap * kpad * 4; }
   __host__ __device__ size_t ybuf_off(int b) const { return tile_off(2) + (size_t)b * kpad * 4; }
   __host__ __device__ size_t vbuf_off(int b) const { return ybuf_off(2) + (size_t)b * warps * kpad * 4; }
-  __host__ __device__ size_t vec_off() const { return vbuf_off(2); }                                    // [warps][kpad], kFullG only
+  __host__ __device__ size_t sum_off() const { return vbuf_off(2); }                                    // [2][kpad] two-stage cross-warp sum
+  __host__ __device__ size_t vec_off() const { return sum_off() + (size_t)2 * kpad * 4; }               // [warps][kpad], kFullG only
   __host__ __device__ size_t idx_off(int s) const { return vec_off() + (full_g ? (size_t)warps * kpad * 4 : 0) + (size_t)s * cap * 4; }
   __host__ __device__ size_t val_off(int s) const { return idx_off(3) + (size_t)s * cap * 4; }
   __host__ __device__ size_t ubuf_off(int b) const { return val_off(3) + (size_t)b * cap * 4; }
@@ -74,10 +78,12 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
   constexpr int LOG_LPR = (LPR == 4) ? 2 : (LPR == 8) ? 3 : (LPR == 16) ? 4 : 5;
   constexpr int SLOT_SHIFT = LOG_LPR - 2;        // slot of a lane = top two bits of its index within the group
   constexpr int B = kTileBatch;
+  static_assert(B == 4, "the halving reduction below is written for batches of 4 row steps");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int W = blockDim.x >> 5, T = blockDim.x;
   const int gi = lane / LPR, gl = lane % LPR;    // lane group within the warp, lane within the group
+  const int slot = gl >> SLOT_SHIFT;             // which of a batch's 4 row steps this lane owns after the reduction
   const int k = P.k;
   const TileCgLayout L{KPAD, P.cap, W, kFullG ? 1 : 0};
   auto tile_of = [&](int b) { return reinterpret_cast<float*>(smem_raw + L.tile_off(b)); };
@@ -88,6 +94,7 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
   auto ubuf_of = [&](int b) { return reinterpret_cast<float*>(smem_raw + L.ubuf_off(b)); };
   float* uy = reinterpret_cast<float*>(smem_raw + L.uy_off());
   double* red = reinterpret_cast<double*>(smem_raw + L.red_off());
+  float* sumv = reinterpret_cast<float*>(smem_raw + L.sum_off());                       // [2][KPAD] two-stage cross-warp sum
   float* vecw = reinterpret_cast<float*>(smem_raw + L.vec_off()) + (size_t)w * KPAD;   // kFullG: this warp's copy of v
 
   const bool implicit = (P.feedback == 0);
@@ -98,23 +105,27 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
     const long long t = (long long)blockIdx.x + (long long)i * stride;
     return P.row_list ? __ldg(P.row_list + t) : (int)t + P.row_begin;
   };
-  // which features this lane holds: chunk c covers [128 c + 4 gl, +4); valid while below k (k % 4 == 0)
+  // which features this lane holds: chunk c covers [128 c + 4 gl, +4); beyond k (k % 4 == 0) the shared-memory copies
+  // stay zero for the whole kernel (zero-filled below, never written by a copy), so only global accesses are guarded
   bool fvalid[C];
   int foff[C];
 #pragma unroll
   for (int c = 0; c < C; c++) { foff[c] = c * 128 + 4 * gl; fvalid[c] = foff[c] < k; }
+  for (size_t e = (size_t)tid * 16; e < L.vec_off(); e += (size_t)T * 16)   // tiles, y buffers, exchange buffers
+    *reinterpret_cast<float4*>(smem_raw + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
 
   // ---- staging helpers ------------------------------------------------------------------------------------
-  auto issue_meta = [&](int slot, int p, int n) {          // CSR indices / values of a row -> shared (4-byte cp.async)
-    int* si = idx_of(slot);
-    float* sv = val_of(slot);
+  auto issue_meta = [&](int sl, int p, int n) {          // CSR indices / values of a row -> shared (4-byte cp.async)
+    int* si = idx_of(sl);
+    float* sv = val_of(sl);
     for (int j = tid; j < n; j += T) {
       cp_async_4(si + j, P.idx + p + j);
       cp_async_4(sv + j, P.val + p + j);
     }
   };
-  auto issue_tile = [&](int buf, int slot, int row, int n) {   // gathered rows + warm-start y -> shared (16-byte cp.async)
-    const int* si = idx_of(slot);
+  auto issue_tile = [&](int buf, int sl, int row, int n) {   // gathered rows + warm-start y -> shared (16-byte cp.async)
+    const int* si = idx_of(sl);
     float* tl = tile_of(buf);
     constexpr int CPR = KPAD / 4;                            // 16-byte chunks per padded row (power of two)
     const int total = n * CPR;
@@ -168,7 +179,7 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
 
   for (int i = 0; valid(i); i++) {
     const int n = n0;
-    const int buf = i & 1, slot = i % 3;
+    const int buf = i & 1, sl = i % 3;
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();   // tile i and the metadata of row i+1 have landed; every warp is done with row i-1
     // ---- prefetch (nothing here waits on memory) ----
@@ -179,64 +190,74 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
     if (valid(i + 4)) rid4 = P.row_list ? ld_pinned_i32(P.row_list + ((long long)blockIdx.x + (long long)(i + 4) * stride))
                                         : row_of(i + 4);
 
-    const float* tl = tile_of(buf);
-    const float* sv = val_of(slot);
+    const float* sv = val_of(sl);
     const float lam_use = implicit ? P.lambda : (P.lambda * (P.dynamic_lambda ? (float)n : 1.0f));
-    // row steps of this warp: step rs covers gathered rows (rs * W + w) * RPW + gi
-    const int n_steps_total = (n + RPW - 1) / RPW;                     // row steps over the whole CTA
+    // Row steps: step rs of warp w covers gathered rows (rs * W + w) * RPW + gi.  Register s of a batch holds row step
+    // b0 + (s ^ slot): lanes of different slots keep their batch permuted, which makes both halving levels of the
+    // reduction the same instruction stream for every lane (keep registers 0/1, send 2/3; keep 0, send 1) -- no selects.
+    const int n_steps_total = (n + RPW - 1) / RPW;                        // over the whole CTA
     const int my_steps = (n_steps_total > w) ? (n_steps_total - w + W - 1) / W : 0;
+    const int full_steps_total = n / RPW;                                 // row steps whose RPW rows all exist
+    const int my_full = (full_steps_total > w) ? (full_steps_total - w + W - 1) / W : 0;
+    const int nb_full = my_full / B;                                      // batches that need no bounds checks
+    const int step_stride = W * RPW * KPAD;                               // floats between consecutive row steps of a warp
+    const float* lane_tile = tile_of(buf) + (size_t)(w * RPW + gi) * KPAD + foff[0];
 
-    // One sweep: acc = sum_j f(c_j, x_j . v) x_j  (+ / - XtX v when kFullG), summed over the CTA; u_j -> ubuf.
-    //   mode 0: w = c - (c - 1) u   (implicit r0)      mode 1: w = (c - 1) u   (implicit Ap)
-    //   mode 2: w = c - u           (explicit r0)      mode 3: w = u           (explicit Ap)
-    auto run_sweep = [&](const float4 (&v)[C], int mode, int gmode, float4 (&out)[C]) {
+    // One sweep: acc = sum_j w_j x_j with w_j = k0 c_j + (k1 c_j + k2) (x_j . v)  (+ / - XtX v when kFullG), summed
+    // over the CTA; u_j = x_j . v -> ubuf.
+    //   implicit r0: c - (c-1) u  (1,-1, 1)     implicit Ap: (c-1) u  (0, 1,-1)
+    //   explicit r0: c - u        (1, 0,-1)     explicit Ap: u        (0, 0, 1)
+    auto run_sweep = [&](const float4 (&v)[C], float k0, float k1, float k2, int gmode, float4 (&out)[C]) {
       float* ub = ubuf_of(sweep & 1);
       float4 acc[C];
 #pragma unroll
       for (int c = 0; c < C; c++) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int b0 = 0; b0 < my_steps; b0 += B) {
+      auto batch = [&](int b0, bool checked) {
         float4 x[B][C];
         float t[B];
 #pragma unroll
         for (int s = 0; s < B; s++) {
-          const int j = ((b0 + s) * W + w) * RPW + gi;
-          const bool ok = (b0 + s < my_steps) && (j < n);
+          const int rs = b0 + (s ^ slot);
+          const float* src = lane_tile + (size_t)rs * step_stride;
+          bool ok = true;
+          if (checked) ok = (rs < my_steps) && ((rs * W + w) * RPW + gi < n);
 #pragma unroll
           for (int c = 0; c < C; c++)
-            x[s][c] = (ok && fvalid[c]) ? *reinterpret_cast<const float4*>(tl + (size_t)j * KPAD + foff[c])
-                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+            x[s][c] = ok ? *reinterpret_cast<const float4*>(src + c * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
           t[s] = dot4(x[s][0], v[0]);
           if constexpr (C == 2) t[s] += dot4(x[s][1], v[1]);
         }
-        // transposing halving reduction over the LPR lanes of the group: 4 -> 2 -> 1 values, then plain butterflies
-        const bool up1 = (gl & (LPR / 2)) != 0, up2 = (gl & (LPR / 4)) != 0;
-        float o0 = (up1 ? t[2] : t[0]) + __shfl_xor_sync(kFull, up1 ? t[0] : t[2], LPR / 2);
-        float o1 = (up1 ? t[3] : t[1]) + __shfl_xor_sync(kFull, up1 ? t[1] : t[3], LPR / 2);
-        float u = (up2 ? o1 : o0) + __shfl_xor_sync(kFull, up2 ? o0 : o1, LPR / 4);
+        // transposing halving reduction over the LPR lanes of the group, then plain butterflies
+        const float o0 = t[0] + __shfl_xor_sync(kFull, t[2], LPR / 2);
+        const float o1 = t[1] + __shfl_xor_sync(kFull, t[3], LPR / 2);
+        float u = o0 + __shfl_xor_sync(kFull, o1, LPR / 4);
 #pragma unroll
         for (int m = LPR / 8; m > 0; m >>= 1) u += __shfl_xor_sync(kFull, u, m);
-        // this lane's slot: row step b0 + (gl >> SLOT_SHIFT) of its group
-        const int ms = gl >> SLOT_SHIFT;
-        const int mj = ((b0 + ms) * W + w) * RPW + gi;
+        // u = x_j . v of this lane's own row step (register 0 = step b0 + slot)
+        const int mrs = b0 + slot;
+        const int mj = (mrs * W + w) * RPW + gi;
         float wq = 0.0f;
-        if ((b0 + ms < my_steps) && (mj < n)) {
+        if (!checked || ((mrs < my_steps) && (mj < n))) {
           const float cj = sv[mj];
-          wq = (mode == 0) ? (cj - (cj - 1.0f) * u) : (mode == 1) ? ((cj - 1.0f) * u) : (mode == 2) ? (cj - u) : u;
+          wq = fmaf(fmaf(k1, cj, k2), u, k0 * cj);
           if ((gl & ((1 << SLOT_SHIFT) - 1)) == 0) ub[mj] = u;
         }
 #pragma unroll
         for (int s = 0; s < B; s++) {
-          const float ws = __shfl_sync(kFull, wq, gi * LPR + (s << SLOT_SHIFT));
+          const float ws = __shfl_sync(kFull, wq, gi * LPR + ((s ^ slot) << SLOT_SHIFT));
 #pragma unroll
           for (int c = 0; c < C; c++) acc[c] = axpy4(ws, x[s][c], acc[c]);
         }
-      }
+      };
+      int b0 = 0;
+      for (int nb = 0; nb < nb_full; nb++, b0 += B) batch(b0, false);
+      for (; b0 < my_steps; b0 += B) batch(b0, true);
       if constexpr (kFullG) {
         if (gmode != 0) {
           // this (warp, group)'s slab of XtX rows: j = unit, unit + U, ...; v_j from this warp's shared copy of v
 #pragma unroll
           for (int c = 0; c < C; c++)
-            if (gi == 0 && fvalid[c]) *reinterpret_cast<float4*>(vecw + foff[c]) = v[c];
+            if (gi == 0) *reinterpret_cast<float4*>(vecw + foff[c]) = v[c];
           __syncwarp();
           float4 g[C];
 #pragma unroll
@@ -271,11 +292,26 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
         for (int c = 0; c < C; c++) *reinterpret_cast<float4*>(vb + (size_t)w * KPAD + foff[c]) = acc[c];
       }
       __syncthreads();
+      if (W <= 4) {
+        // few warps: every lane adds the W partials of its own features
 #pragma unroll
-      for (int c = 0; c < C; c++) {
-        float4 s4 = *reinterpret_cast<const float4*>(vb + foff[c]);
-        for (int ww = 1; ww < W; ww++) s4 = add4(s4, *reinterpret_cast<const float4*>(vb + (size_t)ww * KPAD + foff[c]));
-        out[c] = fvalid[c] ? s4 : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < C; c++) {
+          float4 s4 = *reinterpret_cast<const float4*>(vb + foff[c]);
+          for (int ww = 1; ww < W; ww++) s4 = add4(s4, *reinterpret_cast<const float4*>(vb + (size_t)ww * KPAD + foff[c]));
+          out[c] = s4;
+        }
+      } else {
+        // many warps: thread f < KPAD adds the W partials of feature f (conflict-free 4-byte reads), the sums are
+        // published once and read back by everyone -- W + 1 reads per thread instead of W 16-byte reads per lane
+        float* sb = sumv + (sweep & 1) * KPAD;
+        if (tid < KPAD) {
+          float s1 = vb[tid];
+          for (int ww = 1; ww < W; ww++) s1 += vb[(size_t)ww * KPAD + tid];
+          sb[tid] = s1;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < C; c++) out[c] = *reinterpret_cast<const float4*>(sb + foff[c]);
       }
       sweep++;
     };
@@ -283,9 +319,8 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
     // ---- CG (cg_solver_implicit / cg_solver_explicit) ---------------------------------------------------------
     float4 x[C], r[C], p[C], v[C], Ap[C];
 #pragma unroll
-    for (int c = 0; c < C; c++)
-      x[c] = fvalid[c] ? *reinterpret_cast<const float4*>(ybuf_of(buf) + foff[c]) : make_float4(0.f, 0.f, 0.f, 0.f);
-    run_sweep(x, implicit ? 0 : 2, (kFullG && implicit) ? 1 : 0, v);
+    for (int c = 0; c < C; c++) x[c] = *reinterpret_cast<const float4*>(ybuf_of(buf) + foff[c]);
+    run_sweep(x, 1.0f, implicit ? -1.0f : 0.0f, implicit ? 1.0f : -1.0f, (kFullG && implicit) ? 1 : 0, v);
 #pragma unroll
     for (int c = 0; c < C; c++) {
       if (implicit) r[c] = kFullG ? v[c] : fma4(neg4(dg[c]), x[c], v[c]);     // v - d (.) x   (wrmf_implicit.hpp:16)
@@ -301,7 +336,7 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
     // guard the reference lacks (rsold / p'Ap = 0/0 once a row has converged exactly): a zero residual skips the loop
     const int n_cg = (rsold > 0.0f) ? P.cg_steps : 0;
     for (int it = 0; it < n_cg; it++) {
-      run_sweep(p, implicit ? 1 : 3, (kFullG && implicit) ? 2 : 0, v);
+      run_sweep(p, 0.0f, implicit ? 1.0f : 0.0f, implicit ? -1.0f : 1.0f, (kFullG && implicit) ? 2 : 0, v);
 #pragma unroll
       for (int c = 0; c < C; c++) {
         if (implicit) Ap[c] = kFullG ? v[c] : fma4(dg[c], p[c], v[c]);        // XtX p + X_nnz((c-1) . X_nnz'p)  (:22)

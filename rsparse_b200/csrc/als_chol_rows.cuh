@@ -3,9 +3,9 @@
 // Reference: lhs = XtX + X_nnz diag(c-1) X_nnz', rhs = X_nnz c, solve(lhs, rhs)   (wrmf_implicit.hpp:207-236)
 //            lhs = X_nnz X_nnz' + lambda_u I, rhs = X_nnz r, solve(lhs, rhs)      (wrmf_explicit.hpp:103-108)
 //
-// Why a second kernel: als_chol_tile_kernel keeps 16 x 16 register blocks and pays one CTA barrier (160 threads) per
-// COLUMN, with every block updated at every column under masks (ncu: 35.7 k warp-instructions per row at rank 64,
-// barrier-bound).  Here a CTA of K threads owns one system, thread r holds row r of the lower triangle (K registers)
+// (The first-generation kernel kept 16 x 16 register blocks and paid one CTA barrier per COLUMN -- 35.7 k
+// warp-instructions per row at rank 64, barrier-bound, 2x slower; it was removed in round 2, profiles/r1 keeps its
+// numbers.)  Here a CTA of K threads owns one system, thread r holds row r of the lower triangle (K registers)
 // and the right-looking factorisation advances FOUR columns per pair of barriers:
 //   P1  the four threads of the diagonal block publish their 4 x 4 block (+ their rhs entries)      -> barrier
 //   P2  every thread factors that 4 x 4 block redundantly (4 MUFU.RSQ + ~30 flop, no serial owner), solves its own
@@ -23,10 +23,12 @@
 // warps subtract the solved part, warp 0 solves each 32 x 32 triangle with one shuffle per step.
 // Algorithmic work per row: 2nK^2 / 2 .. 2nK^2 (Gram, triangular per warp) + K^3/3 flop; bytes as the CG path.
 #pragma once
-#include "als_chol_tile.cuh"
+#include "als_generic.cuh"  // SolveParams
 #include "rotate_tc.cuh"   // gram_tc.cuh + rt_desc / tf32_hi
 
 namespace b200als {
+
+constexpr int kCholMaxN = 80;   // longest row (gathered rows) the register / shared-memory layout of these kernels holds
 
 template <int K>
 struct alignas(128) CholRowsSmem {
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(K, kCtas) als_chol_rows_kernel(SolveParams<flo
   const bool implicit = (P.feedback == 0);
   const int total = P.n_list_dev ? __ldg(P.n_list_dev) : P.n_list;
   double cta_loss = 0.0;
-  uint32_t tmem = 0, mma_phase = 0, mma_phase1 = 0;
+  uint32_t tmem = 0, mma_phase = 0;
   if constexpr (kTc) {
     if (tid == 0) {
       mbar_init(&S.mma_done[0], 1);
@@ -269,129 +271,6 @@ __global__ void __launch_bounds__(K, kCtas) als_chol_rows_kernel(SolveParams<flo
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // ordered before the next row's MMAs by its barriers
-    } else if constexpr (kTc == 2) {
-      // ---- Gram on the tensor core, pipelined: 16 gathered rows per chunk, two tile buffers (2 x 33,792 B = the bytes of
-      //      Lt exactly), chunk c is staged while the MMAs of chunk c-1 run; the only blocking wait is the last one ----------
-      constexpr int kRows2 = 16;
-      constexpr int kSBO2 = (kRows2 / 4) * 128 + 16;        // 528: bytes between 8-feature groups (+16: bank spread)
-      constexpr int kTile2 = (K / 8) * kSBO2;               // 8,448 B per hi (or lo) tile
-      constexpr int kMaxChunks2 = (kCholMaxN + kRows2 - 1) / kRows2;   // 5
-      static_assert(2 * 4 * kTile2 <= (int)sizeof(S.Lt), "two tile buffers must fit the bytes of Lt");
-      unsigned char* const opb = reinterpret_cast<unsigned char*>(&S.Lt[0]);   // [buffer][A hi, A lo, B hi, B lo][kTile2]
-      const int n_chunks = (n + kRows2 - 1) / kRows2;
-      float4 vv[kMaxChunks2][4];   // this warp's 4-row group of every chunk, requested up front (one memory round trip)
-#pragma unroll
-      for (int ch = 0; ch < kMaxChunks2; ch++)
-#pragma unroll
-        for (int kk = 0; kk < 4; kk++) {
-          const int j = ch * kRows2 + warp * 4 + kk;
-          vv[ch][kk] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (j < n) vv[ch][kk] = ldg_f4(P.X + (size_t)s_idx[j] * K + lane * 4);
-        }
-#pragma unroll
-      for (int ch = 0; ch < kMaxChunks2; ch++) {
-        if (ch >= n_chunks) break;   // CTA-uniform
-        const int jbase = ch * kRows2, b = ch & 1;
-        unsigned char* const ob = opb + b * 4 * kTile2;
-        if (ch >= 2) {   // the MMAs that read this buffer two chunks ago must have completed
-          if (b == 0) { mbar_wait(&S.mma_done[0], mma_phase); mma_phase ^= 1; }
-          else { mbar_wait(&S.mma_done[1], mma_phase1); mma_phase1 ^= 1; }
-        }
-        {
-          const int kb = warp;
-          const float4 (&v)[4] = vv[ch];
-          float wv[4];
-#pragma unroll
-          for (int kk = 0; kk < 4; kk++) {
-            const int j = jbase + kb * 4 + kk;
-            wv[kk] = (j < n) ? (implicit ? (s_cs[j] - 1.0f) : 1.0f) : 0.f;
-          }
-          const float col[4][4] = {{v[0].x, v[1].x, v[2].x, v[3].x}, {v[0].y, v[1].y, v[2].y, v[3].y},
-                                   {v[0].z, v[1].z, v[2].z, v[3].z}, {v[0].w, v[1].w, v[2].w, v[3].w}};
-#pragma unroll
-          for (int jj = 0; jj < 4; jj++) {
-            const int m = 4 * lane + jj;   // feature
-            float4 bh, bl, ah, al;
-            const float x0 = col[jj][0], x1 = col[jj][1], x2 = col[jj][2], x3 = col[jj][3];
-            const float y0 = x0 * wv[0], y1 = x1 * wv[1], y2 = x2 * wv[2], y3 = x3 * wv[3];
-            bh.x = tf32_hi(x0); bl.x = x0 - bh.x;
-            bh.y = tf32_hi(x1); bl.y = x1 - bh.y;
-            bh.z = tf32_hi(x2); bl.z = x2 - bh.z;
-            bh.w = tf32_hi(x3); bl.w = x3 - bh.w;
-            ah.x = tf32_hi(y0); al.x = y0 - ah.x;
-            ah.y = tf32_hi(y1); al.y = y1 - ah.y;
-            ah.z = tf32_hi(y2); al.z = y2 - ah.z;
-            ah.w = tf32_hi(y3); al.w = y3 - ah.w;
-            const int off = (m >> 3) * kSBO2 + kb * kTcLBO + (m & 7) * 16;
-            *reinterpret_cast<float4*>(ob + 0 * kTile2 + off) = ah;
-            *reinterpret_cast<float4*>(ob + 1 * kTile2 + off) = al;
-            *reinterpret_cast<float4*>(ob + 2 * kTile2 + off) = bh;
-            *reinterpret_cast<float4*>(ob + 3 * kTile2 + off) = bl;
-          }
-        }
-        fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core's async proxy
-        __syncthreads();
-        if (tid == 0) {
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const int ksteps = min(kRows2 / 8, (n - jbase + 7) / 8);
-          for (int ks = 0; ks < ksteps; ks++) {
-            const uint64_t dah = rt_desc(ob + 0 * kTile2 + ks * 2 * kTcLBO, kTcLBO, kSBO2);
-            const uint64_t dal = rt_desc(ob + 1 * kTile2 + ks * 2 * kTcLBO, kTcLBO, kSBO2);
-            const uint64_t dbh = rt_desc(ob + 2 * kTile2 + ks * 2 * kTcLBO, kTcLBO, kSBO2);
-            const uint64_t dbl = rt_desc(ob + 3 * kTile2 + ks * 2 * kTcLBO, kTcLBO, kSBO2);
-            tc_mma_tf32(tmem, dah, dbh, (ch == 0 && ks == 0) ? 0u : 1u);
-            tc_mma_tf32(tmem, dah, dbl, 1u);
-            tc_mma_tf32(tmem, dal, dbh, 1u);
-          }
-          tc_commit(&S.mma_done[b]);
-        }
-        {   // rhs from this chunk's B tiles (hi + lo = x exactly); the buffer is not rewritten before two more barriers
-          const int roff = (r >> 3) * kSBO2 + (r & 7) * 16;
-#pragma unroll
-          for (int kb = 0; kb < kRows2 / 4; kb++) {
-            if (jbase + 4 * kb >= n) break;   // CTA-uniform
-            const float4 h4 = *reinterpret_cast<const float4*>(ob + 2 * kTile2 + roff + kb * kTcLBO);
-            const float4 l4 = *reinterpret_cast<const float4*>(ob + 3 * kTile2 + roff + kb * kTcLBO);
-            const int j = jbase + 4 * kb;
-            const float c0 = s_cs[j], c1 = (j + 1 < n) ? s_cs[j + 1] : 0.f, c2 = (j + 2 < n) ? s_cs[j + 2] : 0.f,
-                        c3 = (j + 3 < n) ? s_cs[j + 3] : 0.f;
-            br = fmaf(c0, h4.x + l4.x, fmaf(c1, h4.y + l4.y, fmaf(c2, h4.z + l4.z, fmaf(c3, h4.w + l4.w, br))));
-          }
-        }
-      }
-      // the last (up to) two commits have not been waited for yet: older chunk first
-      if (n_chunks >= 2) {
-        if (((n_chunks - 2) & 1) == 0) { mbar_wait(&S.mma_done[0], mma_phase); mma_phase ^= 1; }
-        else { mbar_wait(&S.mma_done[1], mma_phase1); mma_phase1 ^= 1; }
-      }
-      if (((n_chunks - 1) & 1) == 0) { mbar_wait(&S.mma_done[0], mma_phase); mma_phase ^= 1; }
-      else { mbar_wait(&S.mma_done[1], mma_phase1); mma_phase1 ^= 1; }
-      __syncthreads();   // every thread has read its rhs entries before Lt overwrites the tiles
-      init_a();
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-      for (int c0 = 0; c0 < K; c0 += 32) {
-        if (c0 > wmax) break;   // warp-uniform
-        uint32_t d[32];
-        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]),
-              "=r"(d[9]), "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15]), "=r"(d[16]),
-              "=r"(d[17]), "=r"(d[18]), "=r"(d[19]), "=r"(d[20]), "=r"(d[21]), "=r"(d[22]), "=r"(d[23]), "=r"(d[24]),
-              "=r"(d[25]), "=r"(d[26]), "=r"(d[27]), "=r"(d[28]), "=r"(d[29]), "=r"(d[30]), "=r"(d[31])
-            : "r"(taddr)
-            : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          a[(c0 + c) >> 1].x += __uint_as_float(d[c]);
-          a[(c0 + c) >> 1].y += __uint_as_float(d[c + 1]);
-        }
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     } else {
       // ---- Gram + rhs: a[c] += (w_j x_j[r]) x_j[c],  b_r += c_j x_j[r] ----------------------------------------------
   #pragma unroll 2

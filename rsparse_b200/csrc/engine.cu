@@ -20,9 +20,7 @@
 #include <vector>
 
 #include "../../include/b200als.h"
-#include "als_chol_tile.cuh"
 #include "als_chol_rows.cuh"
-#include "als_chol_rows_split.cuh"
 #include "als_chol_warp64.cuh"
 #include "als_generic.cuh"
 #include "als_resident.cuh"

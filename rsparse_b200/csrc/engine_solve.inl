@@ -19,26 +19,42 @@ struct HalfOpts {
 constexpr int kDefaultCtas = 3;
 constexpr int kDefaultStage = 1;  // LDGSTS: measured 6 % faster than the UBLKCP variant on C3 (profiles/)
 
+// rows with 1..80 entries / longer rows / empty rows for the Cholesky kernels: stable compactions (ascending row ids),
+// so the launch order and with it the loss summation order is the same on every run
+struct LenInRange {
+  const int32_t* ptr;
+  int lo, hi;
+  __host__ __device__ bool operator()(const int& r) const {
+    const int n = ptr[r + 1] - ptr[r];
+    return n >= lo && n <= hi;
+  }
+};
 template <typename T>
 static int classify_rows(Ctx& c, CscDev<T>& A) {
   if (A.n_short >= 0) return B200ALS_OK;
   CU(A.short_list.ensure(sizeof(int32_t) * (size_t)std::max(1, A.n_cols)));
   CU(A.long_list.ensure(sizeof(int32_t) * (size_t)std::max(1, A.n_cols)));
-  DevBuf counts;
-  CU(counts.ensure(3 * sizeof(int)));
-  CU(cudaMemsetAsync(counts.p, 0, 3 * sizeof(int), c.stream));
+  DevBuf counts, temp;
+  CU(counts.ensure(2 * sizeof(int)));
+  CU(cudaMemsetAsync(counts.p, 0, 2 * sizeof(int), c.stream));
   if (A.n_cols > 0) {
-    classify_rows_kernel<<<(A.n_cols + 255) / 256, 256, 0, c.stream>>>(A.ptr.i32(), A.n_cols, kResMaxN,
-                                                                      A.short_list.i32(), A.long_list.i32(),
-                                                                      counts.i32());
-    LAUNCHED(); CU(cudaGetLastError());
+    cub::CountingInputIterator<int> rows(0);
+    size_t temp_bytes = 0;
+    CU(cub::DeviceSelect::If(nullptr, temp_bytes, rows, (int32_t*)nullptr, (int*)nullptr, A.n_cols, LenInRange{nullptr, 0, 0}, c.stream));
+    CU(temp.ensure(temp_bytes));
+    CU(cub::DeviceSelect::If(temp.p, temp_bytes, rows, A.short_list.i32(), counts.i32(), A.n_cols,
+                             LenInRange{A.ptr.i32(), 1, kCholMaxN}, c.stream));
+    LAUNCHED();
+    CU(cub::DeviceSelect::If(temp.p, temp_bytes, rows, A.long_list.i32(), counts.i32() + 1, A.n_cols,
+                             LenInRange{A.ptr.i32(), kCholMaxN + 1, std::numeric_limits<int>::max()}, c.stream));
+    LAUNCHED();
   }
-  int h[3];
+  int h[2];
   CU(cudaMemcpyAsync(h, counts.p, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
   CU(cudaStreamSynchronize(c.stream));
   A.n_short = h[0];
   A.n_long = h[1];
-  A.n_empty = h[2];
+  A.n_empty = A.n_cols - h[0] - h[1];
   A.all_short = (h[0] == A.n_cols);
   return B200ALS_OK;
 }
@@ -57,14 +73,6 @@ static int launch_cg_generic(Ctx& c, const SolveParams<T>& P, int n_work, int* g
 // that 4, 2 or 1 CTAs of als_cg_tile_kernel share an SM / longer rows (streaming kernel) / empty rows (zeroed).
 // Lists come from stable compactions (cub::DeviceSelect::If over a counting iterator): ascending row ids, so the
 // launch order, hence the loss summation order, is the same on every run.
-struct LenInRange {
-  const int32_t* ptr;
-  int lo, hi;
-  __host__ __device__ bool operator()(const int& r) const {
-    const int n = ptr[r + 1] - ptr[r];
-    return n >= lo && n <= hi;
-  }
-};
 static int tile_kpad(int k) { return k <= 16 ? 16 : k <= 32 ? 32 : k <= 64 ? 64 : k <= 128 ? 128 : 256; }
 static int tile_cap_for(int kpad, int warps, size_t budget) {
   int cap = 0;
@@ -81,8 +89,8 @@ static int plan_rows(Ctx& c, CscDev<T>& A, int k, bool resident_ok) {
   if (A.plan_key == key) return B200ALS_OK;
   using RC = typename CscDev<T>::RowClass;
   const int kpad = tile_kpad(k);
-  int warpsL = 8;
-  if (const char* e = getenv("B200ALS_TILE_WARPS_L")) warpsL = std::max(1, std::min(16, atoi(e)));
+  int warpsL = 16;   // one CTA per SM: 16 warps (two-stage cross-warp sum); B200ALS_TILE_WARPS_L = 4 | 8 | 16 for A/B runs
+  if (const char* e = getenv("B200ALS_TILE_WARPS_L")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16) warpsL = v; }
   const size_t sm_bytes = c.smem_optin + 1024;   // per-SM shared memory (the opt-in per-block limit + the 1 KB reserve)
   const int shape[3][2] = {{4, 4}, {8, 2}, {warpsL, 1}};   // {warps per CTA, CTAs per SM} of the three tile classes
   int lo = 1;
@@ -253,7 +261,7 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
       tiled = (o.solver == B200ALS_CHOLESKY) && (k == 64 || k == 128) && o.kernel != 1 && !sub_range && !biased;
     if (!tiled) return run_generic_chol(nullptr, 0);
     if constexpr (sizeof(T) == 4) {
-      // rows with 1..80 non-zeros: row-per-thread (or tile) kernel; longer rows: generic kernel; empty rows: zero
+      // rows with 1..80 non-zeros: row-per-thread / warp-per-system kernels; longer rows: generic kernel; empty rows: zero
       TRY(classify_rows(c, A));
       if (A.n_empty > 0) {
         zero_empty_rows_kernel<T><<<(unsigned)(((long long)A.n_cols * k + 255) / 256), 256, 0, c.stream>>>(P.ptr, A.n_cols, k, Y);
@@ -262,37 +270,32 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
       if (A.n_short > 0) {
         P.row_list = A.all_short ? nullptr : A.short_list.i32();
         P.n_list = A.n_short;
-        // default (and kernel = 4): row-per-thread panel kernel (als_chol_rows.cuh), measured 2.0x (rank 64) / 1.6x
-        // (rank 128) faster than its predecessor, the 16 x 16 register-block kernel, which stays selectable as kernel = 5
-        const bool rows_kernel = (o.kernel != 5);
+        // Kernel choice (measured round 2, profiles/r2/): rank 128 -- row-per-thread panel Cholesky with the per-row Gram on
+        // tcgen05 (3xTF32 into TMEM), 111 ms per 1 M rows of 80 entries vs 134 ms for the FFMA2 Gram (kernel = 4);
+        // rank 64 -- warp per system (kernel = 9), 22.8 ms vs 25.2 ms per 1 M rows of 50 for the two-warp CTA (kernel = 4).
         // persistent CTAs: exactly as many as are co-resident (registers AND shared memory), else a second wave
         int per_sm = 1, grid = 1;
-        const int min_per_sm = (k == 128 && (o.kernel == 6 || o.kernel == 7)) ? 3 : 1;
+        const bool tc_gram = (k == 128 && o.kernel != 4);
+        const int min_per_sm = tc_gram ? 3 : 1;
         auto launch = [&](auto kern, int threads, size_t smem) -> cudaError_t {
           cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
           if (e != cudaSuccess) return e;
           e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
           if (e != cudaSuccess) return e;
-          // kernels that allocate tensor memory report 1 CTA/SM here although 3 are co-resident (registers, shared
-          // memory and 3 x 128 TMEM columns all fit): measured round 2 (profiles/r2/chol_tc_occupancy.txt)
+          // the occupancy query answers 1 CTA/SM for the kernel that allocates tensor memory although 3 are co-resident
+          // (registers, shared memory and 3 x 128 of the 512 TMEM columns all fit): with the grid it suggested the kernel
+          // ran 2.1x slower (profiles/r2/chol_tc_occupancy.txt)
           per_sm = std::max(per_sm, min_per_sm);
-          if (const char* e = getenv("B200ALS_CHOL_PER_SM")) per_sm = std::max(1, atoi(e));
+          if (const char* ev = getenv("B200ALS_CHOL_PER_SM")) per_sm = std::max(1, atoi(ev));
           grid = std::min(c.sm_count * std::max(1, per_sm), A.n_short);
           kern<<<grid, threads, smem, c.stream>>>(P);
           return cudaSuccess;
         };
-        if (rows_kernel) {
-          if (k == 64 && o.kernel == 9) CU(launch(als_chol_warp64_kernel, 32, sizeof(CholRowsSmem<64>)));   // warp per system (experimental, not yet run on a GPU)
-          else if (k == 64) CU(launch(als_chol_rows_kernel<64, 8>, 64, sizeof(CholRowsSmem<64>)));
-          else if (o.kernel == 6) CU(launch(als_chol_rows_kernel<128, 3, 1>, 128, sizeof(CholRowsSmem<128>)));   // tcgen05 Gram, single-buffered (experimental)
-          else if (o.kernel == 8) CU(launch(als_chol_rows_split_kernel, kSplitThreads, sizeof(CholRowsSmem<128>)));   // split rows (experimental, not yet run on a GPU)
-          else if (o.kernel == 7) CU(launch(als_chol_rows_kernel<128, 3, 2>, 128, sizeof(CholRowsSmem<128>)));   // tcgen05 Gram, pipelined (experimental, not yet run on a GPU)
-          else if (o.ctas == 2) CU(launch(als_chol_rows_kernel<128, 2>, 128, sizeof(CholRowsSmem<128>)));
-          else CU(launch(als_chol_rows_kernel<128, 3>, 128, sizeof(CholRowsSmem<128>)));   // measured: 134.5 vs 171.2 ms / 1 M rows
-        } else {
-          if (k == 64) CU(launch(als_chol_tile_kernel<64>, kCholThreads, sizeof(CholTileSmem<64>)));
-          else CU(launch(als_chol_tile_kernel<128>, kCholThreads, sizeof(CholTileSmem<128>)));
-        }
+        if (k == 64 && o.kernel != 4) CU(launch(als_chol_warp64_kernel, 32, sizeof(CholRowsSmem<64>)));
+        else if (k == 64) CU(launch(als_chol_rows_kernel<64, 8>, 64, sizeof(CholRowsSmem<64>)));
+        else if (tc_gram) CU(launch(als_chol_rows_kernel<128, 3, 1>, 128, sizeof(CholRowsSmem<128>)));
+        else if (o.ctas == 2) CU(launch(als_chol_rows_kernel<128, 2>, 128, sizeof(CholRowsSmem<128>)));
+        else CU(launch(als_chol_rows_kernel<128, 3>, 128, sizeof(CholRowsSmem<128>)));
         LAUNCHED(); CU(cudaGetLastError());
         sum_partials_kernel<<<1, 32, 0, c.stream>>>(P.loss_partials, grid, c.loss_acc.f64(), 1);
         LAUNCHED(); CU(cudaGetLastError());

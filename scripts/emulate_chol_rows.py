@@ -93,97 +93,3 @@ if __name__ == "__main__":
         print(K, "relF", np.linalg.norm(y - ref) / np.linalg.norm(ref), "nan" if np.isnan(y).any() else "finite")
 
 
-def emulate_split128(A, b):
-    """als_chol_rows_split_kernel (rank 128, 192 threads): rows 64..127 are split over two threads -- a `left` one for
-    columns 0..63 and a `right` one for columns 64..127 -- so that every thread holds 64 registers.  Same panels; while the
-    panel is left of column 64 the right threads read their row's l and z from shared memory and update in place."""
-    f = np.float32
-    K, LDT = 128, 132
-    rbase = [96, 64, 32, 0, 96, 64]
-    threads = []
-    for w in range(6):
-        for lane in range(32):
-            r = rbase[w] + lane
-            left = w < 4
-            cb = 0 if left else 64
-            rmax = rbase[w] + 31
-            cmax = min(rmax, 63) if left else rmax
-            threads.append(dict(r=r, left=left, cb=cb, rmax=rmax, cmax=cmax, a=np.full(64, np.nan, f), br=f(b[r])))
-    for t in threads:
-        for c in range(t["cb"], t["cb"] + 64):
-            if 4 * (c // 4) <= t["cmax"]:
-                t["a"][c - t["cb"]] = A[t["r"], c]
-    Lt = np.full((K, LDT), np.nan, f)
-    zz = np.full(K, np.nan, f)
-    rs = np.full(K, np.nan, f)
-    for p in range(K // 4):
-        j0 = 4 * p
-        phase_a = j0 < 64
-        D = np.zeros((4, 8), f)
-        for t in threads:
-            if j0 <= t["r"] < j0 + 4 and t["left"] == phase_a:
-                D[t["r"] - j0, 0:4] = t["a"][0:4]
-                D[t["r"] - j0, 4] = t["br"]
-        d0, d1, d2, d3 = D[0], D[1], D[2], D[3]
-        b0, b1, b2, b3 = D[0, 4], D[1, 4], D[2, 4], D[3, 4]
-        i0 = f(1) / np.sqrt(d0[0]); L10 = d1[0] * i0; L20 = d2[0] * i0; L30 = d3[0] * i0
-        i1 = f(1) / np.sqrt(d1[1] - L10 * L10); L21 = (d2[1] - L20 * L10) * i1; L31 = (d3[1] - L30 * L10) * i1
-        i2 = f(1) / np.sqrt(d2[2] - L20 * L20 - L21 * L21); L32 = (d3[2] - L30 * L20 - L31 * L21) * i2
-        i3 = f(1) / np.sqrt(d3[3] - L30 * L30 - L31 * L31 - L32 * L32)
-        z0 = b0 * i0; z1 = (b1 - L10 * z0) * i1; z2 = (b2 - L20 * z0 - L21 * z1) * i2
-        z3 = (b3 - L30 * z0 - L31 * z1 - L32 * z2) * i3
-        zz[j0:j0 + 4] = [z0, z1, z2, z3]
-        rs[j0:j0 + 4] = [i0, i1, i2, i3]
-        own = [t for t in threads if t["left"] == phase_a and t["rmax"] >= j0]
-        for t in own:
-            a = t["a"]
-            with np.errstate(all="ignore"):
-                l0 = a[0] * i0
-                l1 = (a[1] - l0 * L10) * i1
-                l2 = (a[2] - l0 * L20 - l1 * L21) * i2
-                l3 = (a[3] - l0 * L30 - l1 * L31 - l2 * L32) * i3
-                for q, l in enumerate((l0, l1, l2, l3)):
-                    Lt[j0 + q, t["r"]] = l
-                t["br"] = t["br"] - l0 * z0 - l1 * z1 - l2 * z2 - l3 * z3
-            t["l"] = (l0, l1, l2, l3)
-        # barrier 2
-        for t in own:
-            l0, l1, l2, l3 = t["l"]
-            a = t["a"]
-            for ib in range(15):
-                c = j0 + 4 + 4 * ib
-                if c > t["cmax"]:
-                    break
-                with np.errstate(all="ignore"):
-                    for e in range(4):
-                        a[4 * ib + e] = a[4 * ib + 4 + e] - l0 * Lt[j0, c + e] - l1 * Lt[j0 + 1, c + e] \
-                            - l2 * Lt[j0 + 2, c + e] - l3 * Lt[j0 + 3, c + e]
-        if phase_a:
-            for t in threads:
-                if t["left"]:
-                    continue
-                a = t["a"]
-                l0, l1, l2, l3 = (Lt[j0 + q, t["r"]] for q in range(4))
-                t["br"] = t["br"] - l0 * zz[j0] - l1 * zz[j0 + 1] - l2 * zz[j0 + 2] - l3 * zz[j0 + 3]
-                for ib in range(16):
-                    c = 64 + 4 * ib
-                    if c > t["cmax"]:
-                        break
-                    for e in range(4):
-                        a[4 * ib + e] = a[4 * ib + e] - l0 * Lt[j0, c + e] - l1 * Lt[j0 + 1, c + e] \
-                            - l2 * Lt[j0 + 2, c + e] - l3 * Lt[j0 + 3, c + e]
-    for b0_ in range(K - 32, -1, -32):
-        if b0_ + 32 < K:
-            for i in range(b0_, b0_ + 32):
-                part = f(0)
-                for l in range(b0_ + 32, K):
-                    part += Lt[i, l] * zz[l]
-                zz[i] -= part
-        zi = zz[b0_:b0_ + 32].copy()
-        ri = rs[b0_:b0_ + 32]
-        for s in range(31, -1, -1):
-            ys = zi[s] * ri[s]
-            for lane in range(s):
-                zi[lane] = zi[lane] - Lt[b0_ + lane, b0_ + s] * ys
-        zz[b0_:b0_ + 32] = zi * ri
-    return zz

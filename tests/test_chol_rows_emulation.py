@@ -10,7 +10,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "scripts"))
-from emulate_chol_rows import emulate, emulate_split128  # noqa: E402
+from emulate_chol_rows import emulate  # noqa: E402
 
 
 @pytest.mark.parametrize("K,n", [(64, 50), (64, 3), (128, 80), (128, 1)])
@@ -22,22 +22,6 @@ def test_row_panel_cholesky_index_logic(K, n):
     A = (G.T @ G + 0.1 * np.eye(K) + (X.T * w) @ X).astype(np.float32)
     b = (X.T @ (w + 1)).astype(np.float32)
     y = emulate(K, A, b)
-    ref = np.linalg.solve(A.astype(np.float64), b.astype(np.float64))
-    assert np.isfinite(y).all()
-    assert np.linalg.norm(y - ref) / np.linalg.norm(ref) < 1e-5
-
-
-@pytest.mark.parametrize("n", [80, 7])
-def test_split_row_rank128_index_logic(n):
-    """als_chol_rows_split_kernel: rows 64..127 split over a `left` and a `right` thread (192 threads, 64 registers each)."""
-    K = 128
-    rng = np.random.default_rng(1000 + n)
-    X = (rng.standard_normal((n, K)) * 0.1).astype(np.float32)
-    w = rng.integers(1, 10, n).astype(np.float32)
-    G = (rng.standard_normal((500, K)) * 0.1).astype(np.float32)
-    A = (G.T @ G + 0.1 * np.eye(K) + (X.T * w) @ X).astype(np.float32)
-    b = (X.T @ (w + 1)).astype(np.float32)
-    y = emulate_split128(A, b)
     ref = np.linalg.solve(A.astype(np.float64), b.astype(np.float64))
     assert np.isfinite(y).all()
     assert np.linalg.norm(y - ref) / np.linalg.norm(ref) < 1e-5
