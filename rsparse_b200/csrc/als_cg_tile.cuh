@@ -58,8 +58,11 @@ struct TileCgLayout {
   int kpad, cap, warps, full_g;
   __host__ __device__ size_t tile_off(int b) const { return (size_t)b * cap * kpad * 4; }
   __host__ __device__ size_t ybuf_off(int b) const { return tile_off(2) + (size_t)b * kpad * 4; }
+  // cross-warp exchange: double-buffered per sweep with <= 4 warps (one barrier per sweep); a single buffer with more
+  // warps (the two-stage sum has a second barrier per sweep, which also separates consecutive sweeps)
+  __host__ __device__ int n_vbuf() const { return warps > 4 ? 1 : 2; }
   __host__ __device__ size_t vbuf_off(int b) const { return ybuf_off(2) + (size_t)b * warps * kpad * 4; }
-  __host__ __device__ size_t sum_off() const { return vbuf_off(2); }                                    // [2][kpad] two-stage cross-warp sum
+  __host__ __device__ size_t sum_off() const { return vbuf_off(n_vbuf()); }                                    // [2][kpad] two-stage cross-warp sum
   __host__ __device__ size_t vec_off() const { return sum_off() + (size_t)2 * kpad * 4; }               // [warps][kpad], kFullG only
   __host__ __device__ size_t idx_off(int s) const { return vec_off() + (full_g ? (size_t)warps * kpad * 4 : 0) + (size_t)s * cap * 4; }
   __host__ __device__ size_t val_off(int s) const { return idx_off(3) + (size_t)s * cap * 4; }
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
           acc[c].w += __shfl_xor_sync(kFull, acc[c].w, m);
         }
       }
-      float* vb = vbuf_of(sweep & 1);
+      float* vb = vbuf_of((W > 4) ? 0 : (sweep & 1));
       if (gi == 0) {
 #pragma unroll
         for (int c = 0; c < C; c++) *reinterpret_cast<float4*>(vb + (size_t)w * KPAD + foff[c]) = acc[c];

@@ -269,6 +269,7 @@ __global__ void __launch_bounds__(256) als_chol_generic_kernel(SolveParams<T> P)
   __shared__ double s_red[32];
   __shared__ int s_row;
   __shared__ int s_fail;
+  __shared__ double s_jit;
   const int k = P.k;
   const int ks = k + 1;  // odd-ish stride: breaks bank conflicts between rows
   T* A = reinterpret_cast<T*>(smem_raw);          // (k+1) * ks
@@ -300,11 +301,19 @@ __global__ void __launch_bounds__(256) als_chol_generic_kernel(SolveParams<T> P)
     }
     const int n = max(p2 - p1, 0);
     const T lam_use = implicit ? T(0) : (T)(P.lambda * (P.dynamic_lambda ? (double)static_cast<T>(n) : 1.));
+    // A singular / indefinite system (the reference's default lambda = 0 on explicit feedback makes every row with fewer
+    // entries than the rank singular; its arma::solve(..., fast) then falls back to an approximate solution,
+    // wrmf_explicit.hpp:108) is not an error of the whole call: the row is re-assembled and re-factored with a relative
+    // diagonal shift (1e-6, then 1e-3 of the mean diagonal in fp32; 1e-12 / 1e-8 in fp64).  Only a row that still fails
+    // sets the status word (B200ALS_ENOTSPD).  The shifted solution is NOT the reference's pseudo-inverse-like answer.
+    T jitter = T(0);
+    int failed = 0;
+    for (int attempt = 0;; attempt++) {
     // lhs = XtX (already + lambda I)      wrmf_implicit.hpp:207 ; or lambda_use I   wrmf_explicit.hpp:103-104
     for (int a = ty; a <= k; a += 16)
       for (int b = tx; b < k; b += 16) {
         T v = T(0);
-        if (a < k && b <= a) v = implicit ? __ldg(P.G + (size_t)a * k + b) : ((a == b) ? lam_use : T(0));
+        if (a < k && b <= a) v = (implicit ? __ldg(P.G + (size_t)a * k + b) : ((a == b) ? lam_use : T(0))) + ((a == b) ? jitter : T(0));
         if (a == k && P.rhs_init) v = __ldg(P.rhs_init + b);   // rhs = rhs_init + ...   (wrmf_implicit.hpp:226,229)
         A[a * ks + b] = v;
       }
@@ -377,12 +386,13 @@ __global__ void __launch_bounds__(256) als_chol_generic_kernel(SolveParams<T> P)
         }
       }
       __syncthreads();
-    } else {
+      break;
+    }
     // right-looking Cholesky on rows 0..k (row k = rhs => ends up holding z = L^-1 rhs)
     for (int j = 0; j < k; j++) {
       const T d = A[j * ks + j];
       if (!(d > T(0))) {
-        if (tid == 0) { s_fail = 1; atomicExch(P.status, 1); }
+        if (tid == 0) s_fail = 1;
         break;
       }
       const T inv = T(1) / sqrt(d);
@@ -398,9 +408,38 @@ __global__ void __launch_bounds__(256) als_chol_generic_kernel(SolveParams<T> P)
       __syncthreads();
     }
     __syncthreads();
-    if (s_fail) {  // leave Y untouched for this row; status reports B200ALS_ENOTSPD
+    failed = s_fail;
+    __syncthreads();
+    if (failed && attempt < 2) {
+      // mean diagonal of the unshifted system = (sum of the gathered rows' weighted squared norms + tr(XtX) or k lambda) / k;
+      // recomputed cheaply from the data that is still at hand: the first pivot-free quantity is the rhs-independent trace
+      if (tid == 0) s_fail = 0;
+      T tr = T(0);
+      for (int j = warp_id(); j < n; j += 8) {
+        const int src = __ldg(P.idx + p1 + j);
+        const T* xj = P.X + (size_t)src * k;
+        T d = T(0);
+        for (int f = lane_id(); f < k; f += 32) { const T v = __ldg(xj + f); d += v * v; }
+        d = warp_sum(d);
+        const T cc = __ldg(P.val + p1 + j);
+        if (lane_id() == 0) tr += d * (implicit ? (cc - T(1)) : T(1));
+      }
+      double trd = block_sum_double((double)tr, s_red);
+      if (tid == 0) {
+        if (implicit) for (int a = 0; a < k; a++) trd += (double)__ldg(P.G + (size_t)a * k + a);
+        else trd += (double)lam_use * k;
+        s_jit = fabs(trd) / k;
+      }
+      __syncthreads();
+      const double rel = (sizeof(T) == 4) ? (attempt == 0 ? 1e-6 : 1e-3) : (attempt == 0 ? 1e-12 : 1e-8);
+      jitter = (T)fmax(s_jit * rel, (sizeof(T) == 4) ? 1e-30 : 1e-200);
       continue;
     }
+    if (failed && tid == 0) atomicExch(P.status, 1);
+    break;
+    }  // attempts
+    if (failed) continue;   // leave Y untouched for this row; status reports B200ALS_ENOTSPD
+    if (P.solver != 2) {
     // back substitution L' y = z by warp 0 (z = row k of A); result into colj[0..k)
     if (tid < 32) {
       for (int f = tid; f < k; f += 32) colj[f] = A[k * ks + f];

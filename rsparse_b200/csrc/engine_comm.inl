@@ -12,6 +12,8 @@ struct NcclApi {
   decltype(&::ncclAllReduce) AllReduce = nullptr;
   decltype(&::ncclAllGather) AllGather = nullptr;
   decltype(&::ncclBroadcast) Broadcast = nullptr;
+  decltype(&::ncclSend) Send = nullptr;
+  decltype(&::ncclRecv) Recv = nullptr;
   decltype(&::ncclGroupStart) GroupStart = nullptr;
   decltype(&::ncclGroupEnd) GroupEnd = nullptr;
   decltype(&::ncclGetErrorString) GetErrorString = nullptr;
@@ -25,7 +27,7 @@ struct NcclApi {
     if (!name) return fail(B200ALS_ENCCL, "libnccl.so.2 lacks nccl" #name)
     B200ALS_SYM(GetUniqueId); B200ALS_SYM(CommInitRank); B200ALS_SYM(CommDestroy); B200ALS_SYM(AllReduce);
     B200ALS_SYM(AllGather); B200ALS_SYM(Broadcast); B200ALS_SYM(GroupStart); B200ALS_SYM(GroupEnd);
-    B200ALS_SYM(GetErrorString);
+    B200ALS_SYM(GetErrorString); B200ALS_SYM(Send); B200ALS_SYM(Recv);
 #undef B200ALS_SYM
     return B200ALS_OK;
   }

@@ -186,6 +186,7 @@ static int transpose_on_device(Ctx& c, const CscDev<float>& src, CscDev<float>& 
   dst.n_cols = src.n_rows;
   dst.nnz = src.nnz;
   dst.n_short = -1;
+  dst.plan_key = -1;
   const long long nnz = src.nnz;
   CU(dst.ptr.ensure(sizeof(int32_t) * ((size_t)dst.n_cols + 1)));
   CU(dst.idx.ensure(sizeof(int32_t) * (size_t)nnz));
@@ -221,13 +222,142 @@ static int transpose_on_device(Ctx& c, const CscDev<float>& src, CscDev<float>& 
   return B200ALS_OK;
 }
 
+// ---- the same on a sharded matrix (multi-GPU) ---------------------------------------------------------------------
+// Every rank holds a block of columns of orientation `have` (say its users, idx = item ids) and needs its block of
+// columns of the other orientation (its items, idx = user ids).  (1) Each rank transposes its own block on the
+// device: entries grouped by item, users ascending.  (2) The entries of the items owned by rank r are one contiguous
+// range of that result; ranks exchange these ranges (and the matching column pointers) with grouped ncclSend /
+// ncclRecv over NVLink.  (3) The received pieces arrive ordered by (source rank, item, user); sources own ascending
+// user blocks, so a STABLE sort by item alone yields (item, user ascending): the dgCMatrix invariant, bit-identical
+// to a single-GPU transpose of the whole matrix.
+__global__ void add_offset_kernel(int32_t* __restrict__ a, long long n, int32_t off) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] += off;
+}
+// col_of[e] = c for the entries of column c of a piece whose pointers are ptr[0..n_cols] (absolute; piece starts at ptr[0])
+__global__ void expand_piece_kernel(const int32_t* __restrict__ ptr, int n_cols, int32_t* __restrict__ col_of) {
+  const int cidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cidx >= n_cols) return;
+  const int base = ptr[0];
+  for (int e = ptr[cidx] - base; e < ptr[cidx + 1] - base; e++) col_of[e] = cidx;
+}
+static void block_of(long long n, int r, int world, int32_t* b, int32_t* e) {   // same split as parallel.shard_range
+  const long long base = n / world, rem = n % world;
+  *b = (int32_t)(r * base + std::min<long long>(r, rem));
+  *e = (int32_t)(*b + base + (r < rem ? 1 : 0));
+}
+static int transpose_sharded(b200als_session* s, int have, int need) {
+  Ctx& c = ctx();
+  const int W = g_comm.world, me = g_comm.rank;
+  const int32_t n_other = (need == B200ALS_ITEMS) ? s->n_item : s->n_user;   // columns of the needed orientation (global)
+  const int32_t n_have_global = (have == B200ALS_ITEMS) ? s->n_item : s->n_user;
+  // (1) local transpose: columns = all n_other ids, idx = LOCAL column ids of the block -> made global
+  CscDev<float> T;
+  CscDev<float>& src = s->csc[have];
+  if (src.n_rows != n_other) return fail(B200ALS_EINVAL, "sharded transpose: the uploaded block does not span the other dimension");
+  TRY(transpose_on_device(c, src, T));
+  if (T.nnz > 0 && s->shard_begin[have] != 0) {
+    add_offset_kernel<<<(unsigned)((T.nnz + 255) / 256), 256, 0, c.stream>>>(T.idx.i32(), T.nnz, s->shard_begin[have]);
+    LAUNCHED(); CU(cudaGetLastError());
+  }
+  // (2) ranges per destination
+  std::vector<int32_t> nb(W), ne(W);
+  for (int r = 0; r < W; r++) block_of(n_other, r, W, &nb[r], &ne[r]);
+  std::vector<int32_t> bounds(W + 1);
+  for (int r = 0; r < W; r++)
+    CU(cudaMemcpyAsync(&bounds[r], T.ptr.i32() + nb[r], sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaMemcpyAsync(&bounds[W], T.ptr.i32() + n_other, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaStreamSynchronize(c.stream));
+  std::vector<long long> cnt((size_t)W * W, 0);   // cnt[src * W + dst]
+  for (int r = 0; r < W; r++) cnt[(size_t)me * W + r] = (long long)bounds[r + 1] - bounds[r];
+  DevBuf dcnt;
+  CU(dcnt.ensure(sizeof(long long) * (size_t)W * W));
+  CU(cudaMemcpyAsync(dcnt.as<long long>() + (size_t)me * W, &cnt[(size_t)me * W], sizeof(long long) * W, cudaMemcpyHostToDevice, c.stream));
+  NC(g_nccl.AllGather(dcnt.as<long long>() + (size_t)me * W, dcnt.p, W, ncclInt64, g_comm.comm, c.stream));
+  CU(cudaMemcpyAsync(cnt.data(), dcnt.p, sizeof(long long) * (size_t)W * W, cudaMemcpyDeviceToHost, c.stream));
+  CU(cudaStreamSynchronize(c.stream));
+  const int32_t n_loc = ne[me] - nb[me];
+  std::vector<long long> roff(W + 1, 0);
+  for (int r = 0; r < W; r++) roff[r + 1] = roff[r] + cnt[(size_t)r * W + me];
+  const long long nnz_in = roff[W];
+  if (nnz_in > 2147483647LL) return fail(B200ALS_EUNSUPPORTED, "a shard of the transposed matrix exceeds 2^31-1 entries");
+  DevBuf ridx, rval, rptr, col_of, iota, perm, keys_out, temp;
+  CU(ridx.ensure(sizeof(int32_t) * (size_t)std::max<long long>(1, nnz_in)));
+  CU(rval.ensure(sizeof(float) * (size_t)std::max<long long>(1, nnz_in)));
+  CU(rptr.ensure(sizeof(int32_t) * (size_t)W * ((size_t)n_loc + 1)));
+  NC(g_nccl.GroupStart());
+  for (int r = 0; r < W; r++) {
+    const long long sc = cnt[(size_t)me * W + r], rc = cnt[(size_t)r * W + me];
+    NC(g_nccl.Send(T.ptr.i32() + nb[r], (size_t)(ne[r] - nb[r]) + 1, ncclInt32, r, g_comm.comm, c.stream));
+    NC(g_nccl.Recv(rptr.i32() + (size_t)r * ((size_t)n_loc + 1), (size_t)n_loc + 1, ncclInt32, r, g_comm.comm, c.stream));
+    if (sc > 0) {
+      NC(g_nccl.Send(T.idx.i32() + bounds[r], (size_t)sc, ncclInt32, r, g_comm.comm, c.stream));
+      NC(g_nccl.Send(T.val.f32() + bounds[r], (size_t)sc, ncclFloat, r, g_comm.comm, c.stream));
+    }
+    if (rc > 0) {
+      NC(g_nccl.Recv(ridx.i32() + roff[r], (size_t)rc, ncclInt32, r, g_comm.comm, c.stream));
+      NC(g_nccl.Recv(rval.f32() + roff[r], (size_t)rc, ncclFloat, r, g_comm.comm, c.stream));
+    }
+  }
+  NC(g_nccl.GroupEnd());
+  // (3) stable sort of the received pieces by local column
+  CscDev<float>& dst = s->csc[need];
+  dst.n_rows = n_have_global;
+  dst.n_cols = n_loc;
+  dst.nnz = nnz_in;
+  dst.n_short = -1;
+  dst.plan_key = -1;
+  CU(dst.ptr.ensure(sizeof(int32_t) * ((size_t)n_loc + 1)));
+  CU(dst.idx.ensure(sizeof(int32_t) * (size_t)std::max<long long>(1, nnz_in)));
+  CU(dst.val.ensure(sizeof(float) * (size_t)std::max<long long>(1, nnz_in)));
+  if (nnz_in == 0) {
+    CU(cudaMemsetAsync(dst.ptr.p, 0, sizeof(int32_t) * ((size_t)n_loc + 1), c.stream));
+  } else {
+    CU(col_of.ensure(sizeof(int32_t) * (size_t)nnz_in));
+    CU(iota.ensure(sizeof(int32_t) * (size_t)nnz_in));
+    CU(perm.ensure(sizeof(int32_t) * (size_t)nnz_in));
+    CU(keys_out.ensure(sizeof(int32_t) * (size_t)nnz_in));
+    for (int r = 0; r < W; r++) {
+      if (cnt[(size_t)r * W + me] == 0 || n_loc == 0) continue;
+      expand_piece_kernel<<<(n_loc + 255) / 256, 256, 0, c.stream>>>(rptr.i32() + (size_t)r * ((size_t)n_loc + 1), n_loc,
+                                                                   col_of.i32() + roff[r]);
+      LAUNCHED(); CU(cudaGetLastError());
+    }
+    iota_kernel<<<(unsigned)((nnz_in + 255) / 256), 256, 0, c.stream>>>(iota.i32(), nnz_in);
+    LAUNCHED(); CU(cudaGetLastError());
+    int bits = 1;
+    while (bits < 31 && (1ll << bits) < (long long)std::max(1, n_loc)) bits++;
+    size_t temp_bytes = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, col_of.i32(), keys_out.i32(), iota.i32(), perm.i32(), (int)nnz_in, 0, bits, c.stream));
+    CU(temp.ensure(temp_bytes));
+    CU(cub::DeviceRadixSort::SortPairs(temp.p, temp_bytes, col_of.i32(), keys_out.i32(), iota.i32(), perm.i32(), (int)nnz_in, 0, bits, c.stream));
+    LAUNCHED();
+    // dst.idx[t] = ridx[perm[t]], dst.val[t] = rval[perm[t]]  (gather_transposed_kernel with col_of := ridx)
+    gather_transposed_kernel<<<(unsigned)((nnz_in + 255) / 256), 256, 0, c.stream>>>(perm.i32(), ridx.i32(), rval.f32(), nnz_in,
+                                                                                   dst.idx.i32(), dst.val.f32());
+    LAUNCHED(); CU(cudaGetLastError());
+    row_starts_kernel<<<(n_loc + 1 + 255) / 256, 256, 0, c.stream>>>(keys_out.i32(), nnz_in, n_loc, dst.ptr.i32());
+    LAUNCHED(); CU(cudaGetLastError());
+  }
+  CU(cudaStreamSynchronize(c.stream));
+  s->has[need] = true;
+  s->shard_begin[need] = nb[me];
+  s->shard_end[need] = ne[me];
+  s->nnz_global[need] = s->nnz_global[have];
+  s->ranges[need].clear();
+  return B200ALS_OK;
+}
+
 extern "C" int b200als_build_missing_orientation(b200als_session* s) {
   Ctx& c = ctx();
   if (!s) return fail(B200ALS_EINVAL, "null session");
   if (s->has[0] && s->has[1]) return B200ALS_OK;
   if (!s->has[0] && !s->has[1]) return fail(B200ALS_EINVAL, "the session holds no sparse matrix");
-  if (g_comm.world > 1) return fail(B200ALS_EUNSUPPORTED, "device-side transpose of a sharded matrix is not implemented");
   const int have = s->has[0] ? 0 : 1, need = 1 - have;
+  if (g_comm.world > 1) {
+    TRY(transpose_sharded(s, have, need));
+    return session_counts(s);
+  }
   TRY(transpose_on_device(c, s->csc[have], s->csc[need]));
   s->has[need] = true;
   s->shard_begin[need] = 0;
@@ -414,7 +544,7 @@ static int gather_ranges(b200als_session* s, int which) {
   Ctx& c = ctx();
   // chunked solves (exchange overlapped with the solve) need every row of the block in ONE length class of the CG path
   const bool cg_fast = (s->k % 4 == 0) && (s->k <= 256);
-  if (cg_fast) TRY(plan_rows(c, s->csc[which], s->k, s->k == kResK && s->opt.kernel != 10));
+  if (cg_fast) TRY(plan_rows(c, s->csc[which], s->k, s->k == kResK && s->opt.kernel != 10, false));
   const bool one_class = cg_fast && s->csc[which].plan_single >= 0 && s->csc[which].plan_single != CscDev<float>::kClsLong;
   std::vector<int32_t> ranges(3 * g_comm.world);
   DevBuf d;
@@ -647,7 +777,11 @@ static int session_half(b200als_session* s, int which, int solver, float* Yout, 
   double rows_sum = 0.0;
   {
     double h = 0.0;
-    if (g_comm.world > 1) NC(g_nccl.AllReduce(c.loss_acc.p, c.loss_acc.p, 1, ncclDouble, ncclSum, g_comm.comm, c.stream));
+    if (g_comm.world > 1) {
+      NC(g_nccl.AllReduce(c.loss_acc.p, c.loss_acc.p, 1, ncclDouble, ncclSum, g_comm.comm, c.stream));
+      // a non-SPD row on ONE rank must fail the call on EVERY rank (the others would otherwise run ahead into the next collective)
+      NC(g_nccl.AllReduce(c.status.p, c.status.p, 1, ncclInt32, ncclMax, g_comm.comm, c.stream));
+    }
     CU(cudaMemcpyAsync(&h, c.loss_acc.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     CU(cudaStreamSynchronize(c.stream));
     rows_sum = h;

@@ -74,18 +74,18 @@ static int launch_cg_generic(Ctx& c, const SolveParams<T>& P, int n_work, int* g
 // Lists come from stable compactions (cub::DeviceSelect::If over a counting iterator): ascending row ids, so the
 // launch order, hence the loss summation order, is the same on every run.
 static int tile_kpad(int k) { return k <= 16 ? 16 : k <= 32 ? 32 : k <= 64 ? 64 : k <= 128 ? 128 : 256; }
-static int tile_cap_for(int kpad, int warps, size_t budget) {
+static int tile_cap_for(int kpad, int warps, size_t budget, bool full_g) {
   int cap = 0;
   for (int cnd = 4; cnd <= 8192; cnd += 4) {
-    const TileCgLayout L{kpad, cnd, warps, 1};
+    const TileCgLayout L{kpad, cnd, warps, full_g ? 1 : 0};
     if (L.bytes() > budget) break;
     cap = cnd;
   }
   return cap;
 }
 template <typename T>
-static int plan_rows(Ctx& c, CscDev<T>& A, int k, bool resident_ok) {
-  const int key = k * 2 + (resident_ok ? 1 : 0);
+static int plan_rows(Ctx& c, CscDev<T>& A, int k, bool resident_ok, bool full_g) {
+  const int key = k * 4 + (resident_ok ? 1 : 0) + (full_g ? 2 : 0);
   if (A.plan_key == key) return B200ALS_OK;
   using RC = typename CscDev<T>::RowClass;
   const int kpad = tile_kpad(k);
@@ -100,7 +100,7 @@ static int plan_rows(Ctx& c, CscDev<T>& A, int k, bool resident_ok) {
   for (int t = 0; t < 3; t++) {
     RC& C = A.cls[CscDev<T>::kClsTile0 + t];
     C.warps = shape[t][0];
-    C.cap = tile_cap_for(kpad, C.warps, sm_bytes / shape[t][1] - 1024);
+    C.cap = tile_cap_for(kpad, C.warps, sm_bytes / shape[t][1] - 1024, full_g);
     C.lo = lo;
     C.hi = std::max(lo - 1, C.cap);
     lo = C.hi + 1;
@@ -325,14 +325,14 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
   if constexpr (sizeof(T) == 4) {
     using CD = CscDev<T>;
     const bool resident_ok = (k == kResK) && (o.kernel != 10);
-    TRY(plan_rows(c, A, k, resident_ok));
+    const bool full_g = (o.feedback == B200ALS_IMPLICIT) && !diag;
+    TRY(plan_rows(c, A, k, resident_ok, full_g));
     if (sub_range && (A.plan_single < 0 || A.plan_single == CD::kClsLong))
       return fail(B200ALS_EINVAL, "row sub-ranges need a block whose rows all fall into one length class");
     if (A.plan_empty > 0) {
       zero_empty_rows_kernel<T><<<(unsigned)(((long long)A.n_cols * k + 255) / 256), 256, 0, c.stream>>>(P.ptr, A.n_cols, k, Y);
       LAUNCHED(); CU(cudaGetLastError());
     }
-    const bool full_g = (o.feedback == B200ALS_IMPLICIT) && !diag;
     const typename CD::RowClass& RC = A.cls[CD::kClsResident];
     if (RC.count > 0) {
       ResidentParams R;

