@@ -43,23 +43,29 @@ def _metric_name():
 
 METRIC = _metric_name()
 
+def _wl(n_user, n_item, nnz, k, cg=3, lam=0.1, feedback="implicit", solver=1, col_dist=0, len_dist=0):
+    return dict(n_user=n_user, n_item=n_item, nnz=nnz, k=k, cg=cg, lam=lam, feedback=feedback, solver=solver,
+                col_dist=col_dist, len_dist=len_dist)
+
+
 WORKLOADS = {
-    # name: (n_user, n_item, nnz_per_row, rank, cg_steps, lambda)
-    "c3": (10_000_000, 1_000_000, 80, 128, 3, 0.1),
-    "c3-small": (1_000_000, 1_000_000, 80, 128, 3, 0.1),   # ncu captures
-    "c3-tiny": (100_000, 50_000, 80, 128, 3, 0.1),         # CPU-side dry runs
-    "c4": (10_000_000, 1_000_000, 80, 128, 3, 0.1),        # BASELINE configs[3]: explicit feedback (MMMF)
-    "c2": (1_000_000, 100_000, 50, 64, 3, 0.1),            # BASELINE configs[1]: implicit, rank 64, Cholesky
-    "c3-chol": (1_000_000, 1_000_000, 80, 128, 3, 0.1),    # transform_-shaped: C3's row shape solved by Cholesky (a10)
-    "c5": (50_000_000, 5_000_000, 100, 256, 3, 0.1),       # BASELINE configs[4]: rank 256, 8 GPUs (5e9 nnz: >= 4 ranks)
-    "c5-slice": (6_250_000, 5_000_000, 100, 256, 3, 0.1),  # one rank's share of C5 at 8 GPUs, as a single-GPU run
-    "c5-small": (500_000, 5_000_000, 100, 256, 3, 0.1),    # ncu captures
-    "c3-k64": (10_000_000, 1_000_000, 80, 64, 3, 0.1),     # C3's shape at rank 64 (tile kernel, half-warp per gathered row)
+    "c3": _wl(10_000_000, 1_000_000, 80, 128),                       # BASELINE configs[2]: the metric's configuration
+    "c3-small": _wl(1_000_000, 1_000_000, 80, 128),                  # ncu captures
+    "c3-tiny": _wl(100_000, 50_000, 80, 128),                        # CPU-side dry runs
+    "c4": _wl(10_000_000, 1_000_000, 80, 128, feedback="explicit"),  # BASELINE configs[3]: explicit feedback (MMMF)
+    "c2": _wl(1_000_000, 100_000, 50, 64, solver=0),                 # BASELINE configs[1]: implicit, rank 64, Cholesky
+    "c3-chol": _wl(1_000_000, 1_000_000, 80, 128, solver=0),         # transform_-shaped: C3's rows solved by Cholesky (a10)
+    "c5": _wl(50_000_000, 5_000_000, 100, 256),                      # BASELINE configs[4]: rank 256, 8 GPUs (5e9 nnz: >= 4 ranks)
+    "c5-slice": _wl(6_250_000, 5_000_000, 100, 256),                 # one rank's share of C5 at 8 GPUs, as a single-GPU run
+    "c5-small": _wl(500_000, 5_000_000, 100, 256),                   # ncu captures
+    "c3-k64": _wl(10_000_000, 1_000_000, 80, 64),                    # C3's shape at rank 64 (tile kernel, half-warp per gathered row)
+    # robustness points: Zipf(1.0)-like item popularity; the same with log-normal row lengths (sigma 1, mean 80)
+    "c3-zipf": _wl(10_000_000, 1_000_000, 80, 128, col_dist=1),
+    "c3-ragged": _wl(10_000_000, 1_000_000, 80, 128, col_dist=1, len_dist=1),
+    "c3-ragged-small": _wl(1_000_000, 1_000_000, 80, 128, col_dist=1, len_dist=1),
 }
 # side workload "topk": MatrixFactorizationRecommender$predict's top_product
 TOPK = dict(n_user=65536, n_item=1_000_000, rank=128, k=10, nnz=80)
-# (feedback, solver) per workload; everything not listed is implicit CG
-WORKLOAD_MODE = {"c4": ("explicit", 1), "c2": ("implicit", 0), "c3-chol": ("implicit", 0)}
 BYTES_PER_ROW = lambda n, k: 4 * n * k + 8 * n + 4 + 4 * k + 4 * k   # 42,628 at n=80, k=128
 FLOPS_PER_ROW = lambda n, k, s: (s + 1) * (4 * n * k + 2 * k * k)
 
@@ -140,7 +146,8 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import oracle
-    n_user, n_item, nnz, k, cg, lam = WORKLOADS[args.workload]
+    wl = WORKLOADS[args.workload]
+    n_user, n_item, nnz, k, cg, lam = (wl[x] for x in ("n_user", "n_item", "nnz", "k", "cg", "lam"))
     # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the baseline uses every host core it may run on
     threads = oracle.host_threads()
     sample = min(n_user, args.cpu_rows)
@@ -249,6 +256,8 @@ def main():
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic; CG: 2 resident full-XtX, 3 resident eigenbasis, 10 shared-memory tile kernel only; Cholesky: 0 = tcgen05-Gram rows kernel (rank 128) / warp per system (rank 64), 4 FFMA2-Gram rows kernel")
     ap.add_argument("--stage", type=int, default=0, help="resident-kernel tile staging: 0 default, 1 cp.async.bulk, 2 cp.async")
     ap.add_argument("--ctas", type=int, default=0, help="CTAs per SM the kernel is built for: CG resident 0/3/4, rank-128 row-per-thread Cholesky 0/2/3")
+    ap.add_argument("--gram", default="default", choices=["default", "bf16", "ffma", "tf32x3"], help="arithmetic of XtX (BASELINE configs[4]: fp32 vs tensor-core bf16 Gram)")
+    ap.add_argument("--half", default="users", choices=["users", "items"], help="which half-iteration is the step (items: the item-major orientation is built on the device(s) first)")
     ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="rows in the CPU baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
@@ -266,36 +275,43 @@ def main():
         return run_topk(args)
     from rsparse_b200 import Session
     from rsparse_b200 import _lib as L
-    n_user, n_item, nnz, k, cg, lam = WORKLOADS[args.workload]
+    wl = WORKLOADS[args.workload]
+    n_user, n_item, nnz, k, cg, lam = (wl[x] for x in ("n_user", "n_item", "nnz", "k", "cg", "lam"))
+    feedback, solver = wl["feedback"], wl["solver"]
     if L.device_count() == 0:
         raise SystemExit("bench.py needs a CUDA device: libb200als.so has no CPU fallback")
     L.check(L.lib().b200als_set_device(local_rank))
     parallel.init_engine_comm()
     begin, end = parallel.shard_range(n_user, rank, world)
     n_local = end - begin
-
-    feedback, solver = WORKLOAD_MODE.get(args.workload, ("implicit", L.CONJUGATE_GRADIENT))
-    if (feedback, solver) != ("implicit", L.CONJUGATE_GRADIENT) or k != 128:
+    items_half = (args.half == "items")
+    main_metric = (args.workload == "c3" and not items_half and args.kernel == 0)
+    if not (feedback == "implicit" and solver == L.CONJUGATE_GRADIENT and k == 128 and not items_half and wl["len_dist"] == 0):
         args.no_e2e = args.no_cpu = True     # side workloads: device-resident number only
     if n_user // world * nnz > 2**31 - 1:
         raise SystemExit("workload %s needs more GPUs: %d nnz per rank exceed the 32-bit row pointers of a shard" % (args.workload, n_user // world * nnz))
     s = Session.synthetic(n_local, begin, n_user, n_item, nnz, 42, k, feedback, solver, cg, True, lam,
-                          args.kernel, args.stage, args.ctas)
-    # Inputs: users at R's initialisation scale N(0,1)/100 (R/model_WRMF.R:203-215); items "trained-like":
-    # N(0,1) * 0.1 * (1+f)^-0.5, so XtX has a ~128:1 spectrum and CG takes all its steps.  (i.i.d. item factors
+                          args.kernel, args.stage, args.ctas, wl["col_dist"], wl["len_dist"],
+                          {"default": 0, "bf16": 1, "ffma": 2, "tf32x3": 3}[args.gram])
+    if items_half:
+        s.build_missing_orientation()     # item-major orientation on the device(s): sharded transpose when N > 1
+    # Inputs: the SOLVED side at R's initialisation scale N(0,1)/100 (R/model_WRMF.R:203-215); the FIXED side "trained-like":
+    # N(0,1) * 0.1 * (1+f)^-0.5, so XtX has a ~rank:1 spectrum and CG takes all its steps.  (i.i.d. fixed factors
     # make XtX ~ c*I: every row then leaves the CG loop after ONE step through `rsnew < CG_TOL`,
     # wrmf_implicit.hpp:27, which would flatter the throughput by ~1.7x.)
-    s.randomize_factors(L.ITEMS, 1234, ITEM_SCALE, ITEM_DECAY)
-    s.randomize_factors(L.USERS, 5678, 0.01, 0.0)
+    solved, fixed = (L.ITEMS, L.USERS) if items_half else (L.USERS, L.ITEMS)
+    n_solved = n_item if items_half else n_user
+    s.randomize_factors(fixed, 1234, ITEM_SCALE, ITEM_DECAY)
+    s.randomize_factors(solved, 5678, 0.01, 0.0)
 
-    # Every step starts from freshly initialised user factors (R's N(0,1)/100), like the first user half-iteration
-    # of a fit: repeating the half-iteration on its own output converges the rows, after which the reference's
-    # `rsnew < CG_TOL` exit (wrmf_implicit.hpp:27) leaves CG after one step and the step gets ~1.7x cheaper.
+    # Every step starts from freshly initialised factors on the solved side (R's N(0,1)/100), like the first
+    # half-iteration of a fit: repeating the half-iteration on its own output converges the rows, after which the
+    # reference's `rsnew < CG_TOL` exit (wrmf_implicit.hpp:27) leaves CG after one step and the step gets ~1.7x cheaper.
     # The re-initialisation kernel runs between the timed brackets; each step is bracketed by CUDA events on the
     # engine's stream (b200als_timer_start/_stop) and the K device times are summed.
     for w_ in range(args.warmup):
-        s.randomize_factors(L.USERS, 900 + w_, 0.01, 0.0)
-        s.half_iteration(L.USERS)
+        s.randomize_factors(solved, 900 + w_, 0.01, 0.0)
+        s.half_iteration(solved)
     sampler = ClockSampler(local_rank)
     launches0 = L.lib().b200als_launch_count()
     parts = {"gram_ms": 0.0, "prep_ms": 0.0, "solve_ms": 0.0, "comm_ms": 0.0}
@@ -303,10 +319,10 @@ def main():
     ms_sum = 0.0
     sampler.start()
     for st_ in range(args.steps):
-        s.randomize_factors(L.USERS, 5678 + st_, 0.01, 0.0)
+        s.randomize_factors(solved, 5678 + st_, 0.01, 0.0)
         parallel.barrier()
         L.check(L.lib().b200als_timer_start())
-        loss = s.half_iteration(L.USERS)
+        loss = s.half_iteration(solved)
         ms = C.c_float(0)
         L.check(L.lib().b200als_timer_stop(C.byref(ms)))
         ms_sum += parallel.max_over_ranks(ms.value)
@@ -318,12 +334,18 @@ def main():
     launches = int(L.lib().b200als_launch_count() - launches0) - args.steps   # minus the re-initialisation launches
     ms_total = ms_sum
     ms_per_step = ms_total / args.steps
-    value = n_user * args.steps / (ms_total / 1e3)
+    value = n_solved * args.steps / (ms_total / 1e3)
 
-    # roofline of the dominant kernel (als_cg_resident_kernel): algorithmic bytes / its own device time
+    # roofline of the solve kernel(s): algorithmic bytes (4nk + 8n + 4 + 4k + 4k per row, summed over the
+    # rows this rank solves) / the solve phase's own device time
     hbm_peak, peak_src = measured_peaks()
     solve_ms = parallel.max_over_ranks(parts["solve_ms"]) / args.steps
-    achieved = n_local * BYTES_PER_ROW(nnz, k) / (solve_ms / 1e3) / 1e9
+    plan = s.row_plan(solved) if solver == L.CONJUGATE_GRADIENT else None
+    nnz_local = s.row_plan(solved)["nnz_local"]
+    rows_local = (parallel.shard_range(n_item, rank, world)[1] - parallel.shard_range(n_item, rank, world)[0]) if items_half else n_local
+    algo_bytes = (4 * k + 8) * nnz_local + rows_local * (4 + 8 * k)
+    achieved = algo_bytes / (solve_ms / 1e3) / 1e9
+    nnz_avg = nnz_local / max(1, rows_local)
     if solver == L.CHOLESKY:   # compute-bound path: 2nk^2 + 2nk + k^3/3 + 2k^2 flop per row
         fl = 2 * nnz * k * k + 2 * nnz * k + k ** 3 / 3 + 2 * k * k
         roofline = {"bound": "tensor", "kernel": ("als_chol_rows_kernel<128,3,1> (row-per-thread panel Cholesky, per-row Gram on tcgen05 3xTF32)" if (k == 128 and args.kernel != 4)
@@ -332,27 +354,17 @@ def main():
                     "achieved": n_local * fl / (solve_ms / 1e3) / 1e12, "peak": None, "unit": "TFLOP/s", "frac": None,
                     "traffic": None, "kernel_ms": solve_ms}
     else:
-      roofline = {"bound": "hbm", "kernel": ("als_cg_resident_kernel" if (k == 128 and nnz <= 80 and args.kernel not in (1, 10)) else
-                                             "als_cg_generic_kernel" if args.kernel == 1 else "als_cg_tile_kernel"),
-                "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic_per_launch(args.workload, world),
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": n_local * BYTES_PER_ROW(nnz, k),
-                "kernel_ms": solve_ms, "fp32_tflops": n_local * FLOPS_PER_ROW(nnz, k, cg) / (solve_ms / 1e3) / 1e12}
-    if solver == L.CHOLESKY:
-        # rank 128: the per-row Gram (2nk^2 of the flops) runs on tcgen05 as 3xTF32 => effective tensor peak = TF32 dense / 3
-        # = measured bf16 sustained / 2 / 3; rank 64: fp32 FFMA2 kernel => nominal fp32 peak (148 SMs x 128 lanes x 2 x clock)
-        try:
-            pk16 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
-        except Exception:
-            pk16 = 1364.4
-        if k == 128 and args.kernel != 4:
-            pk, src = pk16 / 6.0, "3xTF32 effective = measured bf16 sustained / 2 (TF32 rate) / 3 (split passes)"
-        else:
-            roofline["bound"] = "fp32"
-            pk, src = 148 * 128 * 2 * 1.965e9 / 1e12, "nominal fp32 FMA peak (148 SMs x 128 lanes x 2 flop x 1.965 GHz)"
-        roofline["peak"], roofline["frac"], roofline["peak_source"] = pk, roofline["achieved"] / pk, src
-        roofline["gram_share_of_flops"] = 2 * nnz * k * k / fl
-
+        rows = plan["rows"]
+        by = {"als_cg_resident_kernel": rows["resident"], "als_cg_tile_kernel": rows["tile_4cta"] + rows["tile_2cta"] + rows["tile_1cta"],
+              "als_cg_generic_kernel": rows["streaming"]}
+        if args.kernel == 1:
+            by = {"als_cg_generic_kernel": rows_local}
+        dominant = max(by, key=by.get)
+        roofline = {"bound": "hbm", "kernel": dominant, "rows_by_kernel": plan["rows"] if args.kernel != 1 else by,
+                    "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": traffic_per_launch(args.workload if not items_half else args.workload + "-items", world),
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": solve_ms,
+                    "fp32_tflops": (cg + 1) * (4 * nnz_local * k + 2 * k * k * rows_local) / (solve_ms / 1e3) / 1e12}
     # ---- e2e: stateless C-ABI call, host buffers, copies inside the timed region -----------------------
     e2e = None
     if not args.no_e2e:
@@ -409,19 +421,22 @@ def main():
                "seconds": dt}
 
     if rank == 0:
-        out = {"metric": METRIC if args.workload in ("c3", "c3-small", "c3-tiny") else "%s (side workload %s)" % (METRIC, args.workload),
-               "value": value, "unit": "user-updates/s",
+        side = args.workload + (" items half" if items_half else "")
+        out = {"metric": METRIC if (args.workload in ("c3", "c3-small", "c3-tiny") and not items_half) else "%s (side workload %s)" % (METRIC, side),
+               "value": value, "unit": "item-updates/s" if items_half else "user-updates/s",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": "%s: %dx%d CSR, %d nnz/row, WRMF %s rank=%d %s lambda=%g, user half-iteration"
-                                      % (args.workload, n_user, n_item, nnz, feedback, k,
-                                         "CG(%d)" % cg if solver == 1 else "Cholesky", lam),
+               "config": {"workload": "%s: %dx%d CSR, %s nnz/row%s, WRMF %s rank=%d %s lambda=%g, %s half-iteration"
+                                      % (args.workload, n_user, n_item, ("%d" % nnz) if not wl["len_dist"] else ("log-normal (sigma 1, mean %d)" % nnz),
+                                         ", Zipf(1.0)-like item popularity" if wl["col_dist"] else "", feedback, k,
+                                         "CG(%d)" % cg if solver == 1 else "Cholesky", lam, "item" if items_half else "user"),
+                          "rows_solved_per_step": n_solved, "mean_nnz_per_solved_row_this_rank": nnz_avg,
                           "parallelism": "rows sharded over %d GPU(s), exchange of updated factors: %s" % (
                               world, {"none": "none (single GPU)", "p2p": "peer-memory pushes over NVLink (copy engines)",
                                       "nccl": "grouped NCCL broadcasts"}[exchange]),
                           "l2": "inputs larger than L2 (CSR %.1f GB + factors %.1f GB per step vs 126 MB L2); no flush needed"
                                 % (n_local * nnz * 8 / 1e9, (n_local + n_item) * k * 4 / 1e9),
-                          "kernel": args.kernel, "stage": args.stage, "ctas": args.ctas, "loss": loss},
+                          "kernel": args.kernel, "stage": args.stage, "ctas": args.ctas, "gram": args.gram, "loss": loss},
                "step_breakdown_ms": {kk: v / args.steps for kk, v in parts.items()},
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(out), flush=True)

@@ -165,17 +165,18 @@ typedef struct b200als_options {
   int cg_steps;        /* R default 3                                                            */
   int dynamic_lambda;  /* explicit feedback only (wrmf_explicit.hpp:78)                          */
   double lambda;
-  int kernel;          /* kernel choice: 0 = auto; 1 = generic streaming kernels (CG and Cholesky); CG only: 2 = register-
-                          resident kernel with the full XtX (rank 128), 3 = register-resident kernel in the eigenbasis of
-                          XtX even for small inputs (implicit, rank 128); Cholesky only (rank 64 / 128): 4 = row-per-thread
-                          panel kernel (the default), 5 = its predecessor, the 16 x 16 register-block kernel, 6 / 7 = the
-                          default kernel with the per-row Gram on tcgen05 (rank 128; experimental: 6 single-buffered,
-                          parity-checked but slower today; 7 pipelined, not yet run on hardware), 8 = rank-128 rows
-                          split over two threads for occupancy, 9 = rank-64 warp per system (both experimental, not
-                          yet run on hardware)                                                                        */
+  int kernel;          /* kernel choice: 0 = auto.  1 = generic streaming kernels (CG and Cholesky; the reference's arithmetic,
+                          full XtX).  CG only: 2 = register-resident kernel with the full XtX (rank 128), 3 = eigenbasis of
+                          XtX even for small inputs (implicit; any rank % 4 == 0 up to 256), 10 = as 3 but without the
+                          register-resident kernel (every row goes to the shared-memory tile kernel or, if too long, the
+                          streaming kernel).  Cholesky only (rank 64 / 128): 0 = row-per-thread panel kernel with the per-row
+                          Gram on tcgen05 (rank 128) / warp per system (rank 64); 4 = row-per-thread panel kernel with the
+                          fp32 FFMA2 Gram at both ranks                                                                  */
   int reserved[7];     /* reserved[0]: tile staging of the register-resident CG kernel -- 0 default, 1 cp.async.bulk
                           (TMA engine), 2 cp.async (LDGSTS); reserved[1]: CTAs/SM the kernel is built for (CG resident
-                          kernel: 0 default, 3, 4; rank-128 row-per-thread Cholesky: 0 default (= 3), 2, 3); the rest must be 0 */
+                          kernel: 0 default, 3, 4; rank-128 FFMA2-Gram Cholesky: 0 default (= 3), 2, 3); reserved[2]: arithmetic
+                          of XtX -- 0 default (environment B200ALS_GRAM, else 3xTF32 on tcgen05 at rank 128 / 256), 1 = bf16
+                          operands on tcgen05 (fp32 accumulate), 2 = fp32 FMA, 3 = 3xTF32 explicitly; the rest must be 0    */
 } b200als_options;
 
 void b200als_default_options(b200als_options* o);
@@ -257,6 +258,18 @@ int b200als_synth_csr_host(int32_t n_rows, int32_t n_cols, int32_t nnz_per_row, 
 int b200als_create_synthetic(b200als_session** out, int32_t n_user_local, int64_t user_offset,
                              int32_t n_user_global, int32_t n_item, int32_t nnz_per_row,
                              uint64_t seed, int rank, const b200als_options* opts);
+/* Which kernel took how many rows in the last CG half-iteration of orientation `which` (bench.py reports it):
+ * counts[0] register-resident kernel, [1..3] shared-memory tile kernel (4 / 2 / 1 CTAs per SM), [4] streaming kernel,
+ * [5] empty rows; caps[0..4] = longest row each class takes.  nnz_local = entries of the local block. */
+int b200als_row_plan(b200als_session* s, int which, int32_t counts[6], int32_t caps[5], int64_t* nnz_local);
+
+/* Skewed synthetic data for the robustness points of bench.py: col_dist 0 = one id per equal-width stratum
+ * (as above), 1 = Zipf(1.0)-like popularity (ids log-uniform over [0, n_item), made distinct and ascending per row);
+ * len_dist 0 = exactly nnz_per_row entries per row, 1 = log-normal row lengths (sigma = 1) with mean nnz_per_row.
+ * A row's content depends only on its global id, so shards of different world sizes hold the same matrix. */
+int b200als_create_synthetic_ex(b200als_session** out, int32_t n_user_local, int64_t user_offset,
+                                int32_t n_user_global, int32_t n_item, int32_t nnz_per_row,
+                                uint64_t seed, int rank, const b200als_options* opts, int col_dist, int len_dist);
 
 #ifdef __cplusplus
 }

@@ -77,6 +77,7 @@ _PROTOS = {
     "b200als_fit": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.POINTER(C.c_int)]),
     "b200als_transform": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
     "b200als_exchange_mode": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "b200als_row_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
     "b200als_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                       C.POINTER(C.c_float)]),
     "b200als_comm_unique_id": (C.c_int, [C.c_void_p]),
@@ -88,6 +89,8 @@ _PROTOS = {
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200als_create_synthetic": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                            C.c_uint64, C.c_int, C.POINTER(Options)]),
+    "b200als_create_synthetic_ex": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                           C.c_uint64, C.c_int, C.POINTER(Options), C.c_int, C.c_int]),
 }
 
 

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(K, kCtas) als_chol_rows_kernel(SolveParams<flo
       for (int ch = 0; ch < kMaxChunks; ch++) {
         if (ch >= n_chunks) break;   // CTA-uniform
         const int jbase = ch * kTcRows;
-        // stage: this warp transposes the 4-row groups {warp, warp + 4} of the chunk (cf. gram_tc_kernel)
+        // stage: this warp transposes the 4-row groups {warp, warp + 4} of the chunk (cf. gram_tc_blocks_kernel)
 #pragma unroll
         for (int g = 0; g < kTcRows / 16; g++) {
           const int kb = warp + 4 * g;

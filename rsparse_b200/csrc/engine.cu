@@ -8,6 +8,7 @@
 #include <cub/cub.cuh>
 #include <dlfcn.h>
 #include <nccl.h>  // types and prototypes only: the library is resolved lazily with dlopen (see NcclApi)
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: ranges are no-ops unless a profiler (nsys / ncu --nvtx) is attached
 
 #include <algorithm>
 #include <cmath>
@@ -61,6 +62,16 @@ static int fail(int code, const std::string& msg) {
     int rc__ = (expr);           \
     if (rc__ != B200ALS_OK) return rc__; \
   } while (0)
+
+// NVTX range over a phase of a half-iteration ("gram", "eigenbasis", "solve", "exchange", "loss", ...): host-side push/pop
+// around the ENQUEUE of the phase's kernels; with `ncu --nvtx --nvtx-include "b200als/solve/"` or nsys the launches inside
+// are attributed to it.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 static unsigned long long g_launches = 0;  // kernels launched by this library (bench.py reports the delta)
 #define LAUNCHED() (++g_launches)

@@ -96,10 +96,17 @@ static int upload_csc(const b200als_csc* A, CscDev<T>& D, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------------
 // Gram
 // ------------------------------------------------------------------------------------------------------
-// B200ALS_GRAM=ffma forces the fp32 FMA kernel; default at rank 128 / fp32 is the tcgen05 3xTF32 kernel
-static bool gram_use_tensor_cores() {
+// Gram arithmetic: 0 = default (tcgen05 3xTF32 at rank 128 / 256 with >= 8192 rows, else fp32 FMA), 1 = tcgen05 with bf16
+// operands (BASELINE configs[4]: "fp32 vs tensor-core bf16 Gram"), 2 = fp32 FMA everywhere.  The session option
+// (b200als_options.reserved[2]) wins over the environment (B200ALS_GRAM = tf32x3 | bf16 | ffma).
+static int g_gram_mode_override = -1;   // set around a session's half-iteration
+static int gram_mode() {
+  if (g_gram_mode_override >= 0) return g_gram_mode_override;
   const char* e = getenv("B200ALS_GRAM");
-  return !(e && (e[0] == 'f' || e[0] == 'F'));
+  if (!e) return 0;
+  if (e[0] == 'f' || e[0] == 'F') return 2;
+  if (e[0] == 'b' || e[0] == 'B') return 1;
+  return 0;
 }
 template <typename T>
 static int run_gram(Ctx& c, const T* X, int k, long long n, double lambda, T* G, double* G64) {
@@ -110,16 +117,25 @@ static int run_gram(Ctx& c, const T* X, int k, long long n, double lambda, T* G,
     return B200ALS_OK;
   }
   if constexpr (sizeof(T) == 4) {
-    if (k == kTcK && n >= 8192 && gram_use_tensor_cores()) {   // small inputs: the exact fp32 FMA kernel
-      long long rows_per = std::max<long long>(1024, (n + 887) / 888);
+    const int mode = gram_mode();
+    if ((k == kTcK || k == 2 * kTcK) && n >= 8192 && mode != 2) {   // small inputs: the exact fp32 FMA kernel
+      const int nt1 = k / kTcK, n_tiles = nt1 * (nt1 + 1) / 2;
+      const long long target = std::max(1, 888 / n_tiles);            // ~6 CTAs per SM in flight over all tiles
+      long long rows_per = std::max<long long>(1024, (n + target - 1) / target);
       rows_per = ((rows_per + 255) / 256) * 256;   // whole drain windows
       const long long n_cta = (n + rows_per - 1) / rows_per;
-      CU(c.gram_partials.ensure(sizeof(double) * (size_t)n_cta * kTcK * kTcK));
-      const size_t smem = sizeof(GramTcSmem);
-      CU(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      gram_tc_kernel<<<(unsigned)n_cta, 128, smem, c.stream>>>((const float*)X, n, rows_per, c.gram_partials.f64());
+      CU(c.gram_partials.ensure(sizeof(double) * (size_t)n_cta * n_tiles * kTcK * kTcK));
+      const size_t smem = sizeof(GramTcSmem2);
+      const dim3 grid((unsigned)n_cta, (unsigned)n_tiles);
+      if (mode == 1) {
+        CU(cudaFuncSetAttribute(gram_tc_blocks_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gram_tc_blocks_kernel<true><<<grid, 128, smem, c.stream>>>((const float*)X, k, n, rows_per, c.gram_partials.f64());
+      } else {
+        CU(cudaFuncSetAttribute(gram_tc_blocks_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gram_tc_blocks_kernel<false><<<grid, 128, smem, c.stream>>>((const float*)X, k, n, rows_per, c.gram_partials.f64());
+      }
       LAUNCHED(); CU(cudaGetLastError());
-      gram_reduce_kernel<T><<<(k * k + 255) / 256, 256, 0, c.stream>>>(c.gram_partials.f64(), (int)n_cta, 1, k, lambda, G, G64);
+      gram_reduce_kernel<T><<<(k * k + 255) / 256, 256, 0, c.stream>>>(c.gram_partials.f64(), (int)n_cta, n_tiles, k, lambda, G, G64);
       LAUNCHED(); CU(cudaGetLastError());
       return B200ALS_OK;
     }

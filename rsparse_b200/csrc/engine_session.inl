@@ -681,6 +681,11 @@ static int session_half(b200als_session* s, int which, int solver, float* Yout, 
   HalfOpts o{s->opt.feedback, solver, s->opt.cg_steps, s->opt.dynamic_lambda, s->opt.kernel, s->opt.lambda, s->opt.reserved[0], s->opt.reserved[1]};
   CscDev<float>& A = s->csc[which];
   const bool implicit = (o.feedback == B200ALS_IMPLICIT);
+  NvtxRange nv_half(which == B200ALS_USERS ? "b200als/half_iteration/users" : "b200als/half_iteration/items");
+  struct GramModeScope {   // the session's Gram arithmetic (options.reserved[2]) applies to every run_gram of this call
+    explicit GramModeScope(int m) { g_gram_mode_override = (m >= 1 && m <= 3) ? (m == 3 ? 0 : m) : -1; }
+    ~GramModeScope() { g_gram_mode_override = -1; }
+  } gram_scope(s->opt.reserved[2]);
   CU(cudaEventRecord(s->ev[0], c.stream));
   const float* G = nullptr;
   const float* diag = nullptr;
@@ -695,6 +700,7 @@ static int session_half(b200als_session* s, int which, int solver, float* Yout, 
     NC(g_nccl.AllReduce(c.status.p, c.status.p, 1, ncclInt32, ncclSum, g_comm.comm, c.stream));
   }
   if (implicit) {
+    NvtxRange nv("b200als/gram");
     if (g_comm.world > 1) {
       // each rank reduces its 1/world slice of the fixed matrix; the k x k partials are summed over NVLink
       const long long b = n_fixed * g_comm.rank / g_comm.world, e = n_fixed * (g_comm.rank + 1) / g_comm.world;
@@ -717,6 +723,7 @@ static int session_half(b200als_session* s, int which, int solver, float* Yout, 
                   o.kernel != 2 && !Yout;
   if (use_diag && o.kernel != 3 && o.kernel != 10 && n_solved_global < 50000) use_diag = false;
   if (use_diag) {
+    NvtxRange nv("b200als/eigenbasis");
     const size_t jsm = sizeof(double) * (size_t)s->k * (s->k + 1);
     const int a_in_smem = (jsm + 8192 <= c.smem_optin) ? 1 : 0;
     if (a_in_smem) CU(cudaFuncSetAttribute(jacobi_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm));
@@ -735,6 +742,7 @@ static int session_half(b200als_session* s, int which, int solver, float* Yout, 
     G = nullptr;
   }
   CU(cudaEventRecord(s->ev[2], c.stream));
+  nvtxRangePushA("b200als/solve+exchange");
   if (g_comm.world > 1 && !Yout) {
     // the block is solved in chunks; chunk c travels to the other ranks (priority stream) while chunk c+1 is solved
     // every rank must take the same decision: chunk only if every block qualifies.  More chunks = shorter
@@ -773,6 +781,8 @@ static int session_half(b200als_session* s, int which, int solver, float* Yout, 
     CU(cudaEventRecord(s->ev[3], c.stream));
   }
   CU(cudaEventRecord(s->ev[4], c.stream));
+  nvtxRangePop();
+  NvtxRange nv_loss("b200als/loss");
   // loss: local row sums -> global
   double rows_sum = 0.0;
   {
@@ -828,6 +838,18 @@ extern "C" int b200als_transform(b200als_session* s, float* host_out, double* lo
   const int solver = (s->opt.solver == B200ALS_CONJUGATE_GRADIENT) ? B200ALS_CHOLESKY : s->opt.solver;  // avoid_cg (:112)
   TRY(session_half(s, B200ALS_USERS, solver, res.f32(), loss));
   return export_rotated(s, res.f32(), A.n_cols, host_out);
+}
+
+extern "C" int b200als_row_plan(b200als_session* s, int which, int32_t counts[6], int32_t caps[5], int64_t* nnz_local) {
+  if (!s || which < 0 || which > 1 || !s->has[which]) return fail(B200ALS_EINVAL, "orientation not present");
+  const CscDev<float>& A = s->csc[which];
+  for (int q = 0; q < 5; q++) {
+    if (counts) counts[q] = (A.plan_key >= 0) ? A.cls[q].count : 0;
+    if (caps) caps[q] = (A.plan_key >= 0) ? A.cls[q].hi : 0;
+  }
+  if (counts) counts[5] = (A.plan_key >= 0) ? A.plan_empty : 0;
+  if (nnz_local) *nnz_local = A.nnz;
+  return B200ALS_OK;
 }
 
 extern "C" int b200als_last_timing(b200als_session* s, float* gram_ms, float* prep_ms, float* solve_ms, float* comm_ms) {

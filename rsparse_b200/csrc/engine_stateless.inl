@@ -152,6 +152,7 @@ static int stateless_pipelined(const b200als_csc* A, const float* X, float* Y, c
                                const HalfOpts& o, double* loss) {
   Ctx& c = ctx();
   PipeCtx& pc = pipe_ctx();
+  NvtxRange nv("b200als/stateless_pipelined");
   TRY(pc.init());
   const int k = kResK;
   const bool implicit = (o.feedback == B200ALS_IMPLICIT);

@@ -29,7 +29,7 @@ class Session:
     """Thin RAII wrapper over the session API of include/b200als.h."""
 
     def __init__(self, c_ui, c_iu, n_user, n_item, rank, feedback, solver, cg_steps=3, dynamic_lambda=True,
-                 lambda_=0.0, kernel=0, stage=0, ctas=0):
+                 lambda_=0.0, kernel=0, stage=0, ctas=0, gram=0):
         self._h = C.c_void_p(None)
         o = L.Options()
         L.lib().b200als_default_options(C.byref(o))
@@ -41,6 +41,7 @@ class Session:
         o.kernel = int(kernel)
         o.reserved[0] = int(stage)   # resident-kernel tile staging: 0 default, 1 cp.async.bulk, 2 cp.async
         o.reserved[1] = int(ctas)    # resident-kernel CTAs/SM: 0 default, 3, 4
+        o.reserved[2] = int(gram)    # XtX arithmetic: 0 default, 1 bf16 tensor-core, 2 fp32 FMA, 3 3xTF32
         self.rank, self.n_user, self.n_item = int(rank), int(n_user), int(n_item)
         keep = []
         s_ui = s_iu = None
@@ -56,7 +57,8 @@ class Session:
 
     @classmethod
     def synthetic(cls, n_user_local, user_offset, n_user_global, n_item, nnz_per_row, seed, rank, feedback="implicit",
-                  solver=L.CONJUGATE_GRADIENT, cg_steps=3, dynamic_lambda=True, lambda_=0.1, kernel=0, stage=0, ctas=0):
+                  solver=L.CONJUGATE_GRADIENT, cg_steps=3, dynamic_lambda=True, lambda_=0.1, kernel=0, stage=0, ctas=0,
+                  col_dist=0, len_dist=0, gram=0):
         self = cls.__new__(cls)
         self._h = C.c_void_p(None)
         o = L.Options()
@@ -65,9 +67,11 @@ class Session:
         o.solver, o.cg_steps, o.dynamic_lambda, o.lambda_, o.kernel = int(solver), int(cg_steps), int(dynamic_lambda), float(lambda_), int(kernel)
         o.reserved[0] = int(stage)
         o.reserved[1] = int(ctas)
+        o.reserved[2] = int(gram)
         self.rank, self.n_user, self.n_item = int(rank), int(n_user_global), int(n_item)
-        L.check(L.lib().b200als_create_synthetic(C.byref(self._h), int(n_user_local), int(user_offset), int(n_user_global),
-                                                 int(n_item), int(nnz_per_row), int(seed), int(rank), C.byref(o)))
+        L.check(L.lib().b200als_create_synthetic_ex(C.byref(self._h), int(n_user_local), int(user_offset), int(n_user_global),
+                                                    int(n_item), int(nnz_per_row), int(seed), int(rank), C.byref(o),
+                                                    int(col_dist), int(len_dist)))
         return self
 
     def close(self):
@@ -133,6 +137,16 @@ class Session:
         m = C.c_int(0)
         L.check(L.lib().b200als_exchange_mode(self._h, C.byref(m)))
         return ("none", "p2p", "nccl")[m.value]
+
+    def row_plan(self, which):
+        """Rows per kernel of the last CG half-iteration of `which` and the local number of entries."""
+        counts = np.zeros(6, np.int32)
+        caps = np.zeros(5, np.int32)
+        nnz = C.c_int64(0)
+        L.check(L.lib().b200als_row_plan(self._h, which, L.vp(counts), L.vp(caps), C.byref(nnz)))
+        names = ["resident", "tile_4cta", "tile_2cta", "tile_1cta", "streaming", "empty"]
+        return {"rows": dict(zip(names, [int(v) for v in counts])), "longest_row": dict(zip(names[:5], [int(v) for v in caps])),
+                "nnz_local": int(nnz.value)}
 
     def last_timing(self):
         t = [C.c_float(0) for _ in range(4)]

@@ -423,6 +423,27 @@ def test_tensor_core_gram_and_rotation_paths(cases, golden_half, monkeypatch):
         assert relF(res[mode][2], X) < 2e-6, mode
 
 
+@pytest.mark.parametrize("k", [128, 256])
+def test_gram_tensor_core_blocks_and_bf16(k, monkeypatch):
+    """gram_tc_blocks_kernel: XtX in 128 x 128 blocks on tcgen05 (rank 256 = three blocks of the lower triangle).
+    3xTF32 is fp32-grade (<= 3e-6 against fp64); the bf16-operand mode of BASELINE configs[4] is a different,
+    stated accuracy class: operands rounded to 8 significant bits, relative Frobenius error of XtX ~1e-3."""
+    n = 20000
+    X = np.ascontiguousarray(wc.det_factors(n, k, 700 + k, 0.1) * (1.0 + np.arange(k, dtype=np.float32)) ** -0.5)
+    ref = X.astype(np.float64).T @ X.astype(np.float64) + 0.3 * np.eye(k)
+    monkeypatch.setenv("B200ALS_GRAM", "tf32x3")
+    G = gram(X, 0.3)
+    assert np.allclose(G, ref, rtol=3e-6, atol=1e-7) and np.array_equal(G, G.T)
+    monkeypatch.setenv("B200ALS_GRAM", "ffma")
+    Gf = gram(X, 0.3)
+    assert np.allclose(Gf, ref, rtol=3e-6, atol=1e-7)
+    monkeypatch.setenv("B200ALS_GRAM", "bf16")
+    Gb = gram(X, 0.3)
+    err = relF(Gb, ref)
+    assert 1e-6 < err < 5e-3, err          # bf16 operands: visibly not fp32-grade, but a usable Gram
+    assert np.array_equal(Gb, Gb.T)
+
+
 def _topk_case(n_user, n_item, rank, seed, density=0.1):
     import scipy.sparse as sp
     x = wc.det_factors(n_user, rank, seed, 1.0)
