@@ -257,6 +257,10 @@ def main():
     ap.add_argument("--stage", type=int, default=0, help="resident-kernel tile staging: 0 default, 1 cp.async.bulk, 2 cp.async")
     ap.add_argument("--ctas", type=int, default=0, help="CTAs per SM the kernel is built for: CG resident 0/3/4, rank-128 row-per-thread Cholesky 0/2/3")
     ap.add_argument("--gram", default="default", choices=["default", "bf16", "ffma", "tf32x3"], help="arithmetic of XtX (BASELINE configs[4]: fp32 vs tensor-core bf16 Gram)")
+    ap.add_argument("--fit-iters", type=int, default=0, help="after the timed steps, run this many full ALS iterations (item half + user half, "
+                    "R/model_WRMF.R:318-338) from R's initialisation and report the device time of every half-iteration (side workload)")
+    ap.add_argument("--warm-eig", action="store_true", help="keep the warm start of the eigen-decomposition between steps (the bench repeats a "
+                    "half-iteration against an UNCHANGED fixed matrix, which would make the decomposition free; off by default)")
     ap.add_argument("--half", default="users", choices=["users", "items"], help="which half-iteration is the step (items: the item-major orientation is built on the device(s) first)")
     ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="rows in the CPU baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -265,6 +269,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
+    if not args.warm_eig:
+        os.environ["B200ALS_EIG_WARM"] = "0"
     rank, world, local_rank = (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
                                int(os.environ.get("LOCAL_RANK", "0")))
     if args.impl == "reference":
@@ -280,6 +286,7 @@ def main():
     feedback, solver = wl["feedback"], wl["solver"]
     if L.device_count() == 0:
         raise SystemExit("bench.py needs a CUDA device: libb200als.so has no CPU fallback")
+    numa = parallel.bind_to_gpu_numa(local_rank) if world > 1 else "numa: single process, not bound"
     L.check(L.lib().b200als_set_device(local_rank))
     parallel.init_engine_comm()
     begin, end = parallel.shard_range(n_user, rank, world)
@@ -389,6 +396,7 @@ def main():
         h2d = ptr.nbytes + idx.nbytes + val.nbytes + Xh.nbytes + Yh.nbytes
         e2e = {"value": n_user * args.e2e_steps / dt, "unit": "user-updates/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(Yh.nbytes), "ms_per_step": 1e3 * dt / args.e2e_steps, "steps": args.e2e_steps,
+               "h2d_gbs_per_rank": h2d / (dt / args.e2e_steps) / 1e9, "host_binding_rank0": numa,
                "api": "b200als_als_implicit_float (stateless, host pointers, CSR values double as in R's dgCMatrix)"}
 
     # ---- CPU baseline (rank 0, N = 1): the oracle timed on this box's host cores -------------------------
@@ -420,6 +428,26 @@ def main():
                          "same CSR against the full item matrix, %d threads, XtX precomputed" % (sample, threads),
                "seconds": dt}
 
+    # ---- full ALS iterations (item half + user half), device-resident: what a fit costs per iteration ----------
+    fit = None
+    if args.fit_iters > 0:
+        os.environ.pop("B200ALS_EIG_WARM", None)      # a real fit: the eigen-decomposition is warm-started from the previous iteration
+        s.build_missing_orientation()
+        s.init_factors(7)                             # users N(0,1)/100, items zero (CG): R/model_WRMF.R:203-230
+        fit = {"iterations": []}
+        for it in range(args.fit_iters):
+            row = {}
+            for nm, side in (("items", L.ITEMS), ("users", L.USERS)):
+                parallel.barrier()
+                L.check(L.lib().b200als_timer_start())
+                ls = s.half_iteration(side)
+                ms = C.c_float(0)
+                L.check(L.lib().b200als_timer_stop(C.byref(ms)))
+                row[nm] = dict(ms=parallel.max_over_ranks(ms.value), loss=ls, **s.last_timing(), rows=s.row_plan(side)["rows"])
+            fit["iterations"].append(row)
+        last = fit["iterations"][-1]
+        fit["ms_per_iteration_last"] = last["items"]["ms"] + last["users"]["ms"]
+
     if rank == 0:
         side = args.workload + (" items half" if items_half else "")
         out = {"metric": METRIC if (args.workload in ("c3", "c3-small", "c3-tiny") and not items_half) else "%s (side workload %s)" % (METRIC, side),
@@ -439,6 +467,8 @@ def main():
                           "kernel": args.kernel, "stage": args.stage, "ctas": args.ctas, "gram": args.gram, "loss": loss},
                "step_breakdown_ms": {kk: v / args.steps for kk, v in parts.items()},
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        if fit is not None:
+            out["fit"] = fit
         print(json.dumps(out), flush=True)
     s.close()
 

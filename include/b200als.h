@@ -258,6 +258,13 @@ int b200als_synth_csr_host(int32_t n_rows, int32_t n_cols, int32_t nnz_per_row, 
 int b200als_create_synthetic(b200als_session** out, int32_t n_user_local, int64_t user_offset,
                              int32_t n_user_global, int32_t n_item, int32_t nnz_per_row,
                              uint64_t seed, int rank, const b200als_options* opts);
+/* Bias terms inside the session (R/model_WRMF.R:260-297; wrmf_implicit.hpp:105-157, wrmf_explicit.hpp:57-64): with
+ * with_user_item_bias the session must have been created with rank = R's private$rank = rank + 2 and the factor matrices
+ * carry the reference's layouts (users [1, ..., user_bias], items [item_bias, ..., 1]); global_bias is the value
+ * initialize_biases returned (implicit feedback; explicit feedback subtracts it from the values beforehand, as R does).
+ * Every half-iteration, fit and transform of the session then runs the bias-aware kernels on the device. Single GPU. */
+int b200als_set_bias(b200als_session* s, int with_user_item_bias, double global_bias);
+
 /* Which kernel took how many rows in the last CG half-iteration of orientation `which` (bench.py reports it):
  * counts[0] register-resident kernel, [1..3] shared-memory tile kernel (4 / 2 / 1 CTAs per SM), [4] streaming kernel,
  * [5] empty rows; caps[0..4] = longest row each class takes.  nnz_local = entries of the local block. */

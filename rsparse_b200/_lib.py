@@ -77,6 +77,7 @@ _PROTOS = {
     "b200als_fit": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.POINTER(C.c_int)]),
     "b200als_transform": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
     "b200als_exchange_mode": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "b200als_set_bias": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "b200als_row_plan": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
     "b200als_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                       C.POINTER(C.c_float)]),

@@ -113,12 +113,14 @@ __global__ void __launch_bounds__(kJacobiThreads) jacobi_eig_kernel(double* __re
 }
 
 // C = A * B (k x k, row-major, double) -- basis bookkeeping B <- B Q ; trivially small.
-__global__ void matmul_kk_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, int k) {
+// transA != 0: C = A' * B
+__global__ void matmul_kk_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, int k, int transA = 0) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= k * k) return;
   const int i = e / k, j = e % k;
   double s = 0.0;
-  for (int l = 0; l < k; l++) s += A[i * k + l] * B[l * k + j];
+  if (transA) for (int l = 0; l < k; l++) s += A[l * k + i] * B[l * k + j];
+  else for (int l = 0; l < k; l++) s += A[i * k + l] * B[l * k + j];
   C[e] = s;
 }
 // out(fp32)[i][j] = transpose ? in[j][i] : in[i][j]

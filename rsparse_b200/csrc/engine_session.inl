@@ -14,6 +14,15 @@ struct b200als_session {
   DevBuf fac[2];   // full factor matrices (stored in basis B): [ITEMS] k x n_item, [USERS] k x n_user
   DevBuf cnt[2];   // cnt[w][j] = nnz of row j of factor matrix w (global), for the dynamic-lambda regulariser
   DevBuf G, G64, Vt, Q, Qt, diag, B64, Btmp, Bf, scratch;
+  // warm start of the eigen-decomposition: Weig[f] = the stored basis right after a half-iteration in which side f was the fixed
+  // matrix = the eigenvectors of that side's Gram in TRUE coordinates; V0, T1, A0: k x k fp64 work space
+  DevBuf Weig[2], V0, T1, A0;
+  bool eig_warm[2] = {false, false};
+  // bias terms (with_user_item_bias / global_bias, b200als_set_bias): factor matrices are `k` = rank + 2 wide as in R
+  int with_biases = 0;
+  double global_bias = 0.0;
+  DevBuf gbb;                      // global_bias_base, [k]
+  BiasScratch<float> bias_w;
   bool basis_identity = true;
   std::vector<int32_t> ranges[2];   // [3*world]: every rank's [begin, end, can_chunk) per orientation (multi-GPU)
   cudaStream_t comm_stream = nullptr;
@@ -56,6 +65,10 @@ static int session_alloc(b200als_session* s) {
   CU(s->B64.ensure(sizeof(double) * k * k));
   CU(s->Btmp.ensure(sizeof(double) * k * k));
   CU(s->Bf.ensure(sizeof(float) * k * k));
+  for (int w = 0; w < 2; w++) CU(s->Weig[w].ensure(sizeof(double) * k * k));
+  CU(s->V0.ensure(sizeof(double) * k * k));
+  CU(s->T1.ensure(sizeof(double) * k * k));
+  CU(s->A0.ensure(sizeof(double) * k * k));
   set_identity_kernel<<<(unsigned)((k * k + 255) / 256), 256, 0, c.stream>>>(s->B64.f64(), (int)k);
   LAUNCHED(); CU(cudaGetLastError());
   s->basis_identity = true;
@@ -478,6 +491,7 @@ extern "C" int b200als_set_factors(b200als_session* s, int which, const float* h
   if (!s || !host || which < 0 || which > 1) return fail(B200ALS_EINVAL, "bad argument");
   const long long n = (which == B200ALS_ITEMS) ? s->n_item : s->n_user;
   CU(cudaMemcpyAsync(s->fac[which].p, host, sizeof(float) * (size_t)s->k * (size_t)n, cudaMemcpyHostToDevice, c.stream));
+  s->eig_warm[which] = false;   // a replaced matrix has an unrelated Gram
   if (!s->basis_identity) {
     convert_kk_kernel<<<(s->k * s->k + 255) / 256, 256, 0, c.stream>>>(s->B64.f64(), s->Bf.f32(), s->k, 0);
     LAUNCHED(); CU(cudaGetLastError());
@@ -524,6 +538,7 @@ extern "C" int b200als_init_factors(b200als_session* s, uint64_t seed) {
   set_identity_kernel<<<(s->k * s->k + 255) / 256, 256, 0, c.stream>>>(s->B64.f64(), s->k);
   LAUNCHED(); CU(cudaGetLastError());
   s->basis_identity = true;
+  s->eig_warm[0] = s->eig_warm[1] = false;
   CU(cudaStreamSynchronize(c.stream));
   return B200ALS_OK;
 }
@@ -534,6 +549,7 @@ extern "C" int b200als_randomize_factors(b200als_session* s, int which, uint64_t
   const long long n = (long long)s->k * ((which == B200ALS_ITEMS) ? s->n_item : s->n_user);
   if (n) init_normal_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(s->fac[which].f32(), n, seed, scale, s->k, decay);
   LAUNCHED(); CU(cudaGetLastError());
+  s->eig_warm[which] = false;   // a replaced matrix has an unrelated Gram
   CU(cudaStreamSynchronize(c.stream));
   return B200ALS_OK;
 }
@@ -660,6 +676,10 @@ static int p2p_join(b200als_session* s, cudaStream_t st) {
   }
   return B200ALS_OK;
 }
+__global__ void set_col_kernel(float* __restrict__ M, int ld, int col, int n, float v) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) M[(size_t)r * ld + col] = v;
+}
 __global__ void finalize_gram_kernel(double* __restrict__ G64, float* __restrict__ G, int k, double lambda) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= k * k) return;
@@ -681,6 +701,22 @@ static int session_half(b200als_session* s, int which, int solver, float* Yout, 
   HalfOpts o{s->opt.feedback, solver, s->opt.cg_steps, s->opt.dynamic_lambda, s->opt.kernel, s->opt.lambda, s->opt.reserved[0], s->opt.reserved[1]};
   CscDev<float>& A = s->csc[which];
   const bool implicit = (o.feedback == B200ALS_IMPLICIT);
+  if (s->with_biases || (implicit && s->global_bias >= std::sqrt((double)std::numeric_limits<float>::epsilon()))) {
+    // bias terms inside the device-resident session (wrmf_implicit.hpp:105-157,190-232 / wrmf_explicit.hpp:57-64,87-91):
+    // the same device code as the stateless calls (half_on_device), no host round trip.  The ITEM half is the call with
+    // is_bias_last_row = TRUE, the USER half (and transform_) the one with FALSE (R/model_WRMF.R:321,327,436).
+    if (g_comm.world > 1) return fail(B200ALS_EUNSUPPORTED, "bias terms in a multi-GPU session are not implemented");
+    NvtxRange nvb("b200als/half_iteration/biased");
+    CU(s->gbb.ensure(sizeof(float) * (size_t)s->k));
+    CU(cudaEventRecord(s->ev[0], c.stream));
+    TRY(half_on_device<float>(c, A, s->k, X, Y, n_fixed, (long long)A.n_cols, nullptr, o, s->with_biases,
+                              which == B200ALS_ITEMS ? 1 : 0, s->global_bias, s->gbb.f32(), 1, s->bias_w));
+    CU(cudaEventRecord(s->ev[3], c.stream));
+    TRY(finish_loss<float>(c, X, s->k, n_fixed, s->cnt[fixed].f32(), o, s->nnz_global[which], 0.0, false, loss));
+    s->t_gram = s->t_prep = s->t_comm = 0.f;
+    cudaEventElapsedTime(&s->t_solve, s->ev[0], s->ev[3]);
+    return B200ALS_OK;
+  }
   NvtxRange nv_half(which == B200ALS_USERS ? "b200als/half_iteration/users" : "b200als/half_iteration/items");
   struct GramModeScope {   // the session's Gram arithmetic (options.reserved[2]) applies to every run_gram of this call
     explicit GramModeScope(int m) { g_gram_mode_override = (m >= 1 && m <= 3) ? (m == 3 ? 0 : m) : -1; }
@@ -727,16 +763,39 @@ static int session_half(b200als_session* s, int which, int solver, float* Yout, 
     const size_t jsm = sizeof(double) * (size_t)s->k * (s->k + 1);
     const int a_in_smem = (jsm + 8192 <= c.smem_optin) ? 1 : 0;
     if (a_in_smem) CU(cudaFuncSetAttribute(jacobi_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jsm));
-    jacobi_eig_kernel<<<1, kJacobiThreads, a_in_smem ? jsm : 0, c.stream>>>(s->G64.f64(), s->Vt.f64(), s->k, s->Q.f32(),
-                                                                          s->diag.f32(), s->Btmp.f64(), 30, a_in_smem);
-    LAUNCHED(); CU(cudaGetLastError());
+    // Warm start (B200ALS_EIG_WARM=0 disables): the Gram of a side changes slowly from one ALS iteration to the next, so
+    // its previous eigenvectors W (kept in true coordinates) nearly diagonalise it.  In the stored basis B they read
+    // V0 = B' W; Jacobi then runs on A0 = V0' G V0 (2-3 sweeps instead of ~9) and Q = V0 V1.
+    const char* ew = getenv("B200ALS_EIG_WARM");
+    const bool warm = s->eig_warm[fixed] && !(ew && ew[0] == '0');
+    const unsigned kkb = (unsigned)((s->k * s->k + 255) / 256);
+    if (warm) {
+      matmul_kk_kernel<<<kkb, 256, 0, c.stream>>>(s->B64.f64(), s->Weig[fixed].f64(), s->V0.f64(), s->k, 1);   // V0 = B' W
+      LAUNCHED();
+      matmul_kk_kernel<<<kkb, 256, 0, c.stream>>>(s->G64.f64(), s->V0.f64(), s->T1.f64(), s->k, 0);            // T1 = G V0
+      LAUNCHED();
+      matmul_kk_kernel<<<kkb, 256, 0, c.stream>>>(s->V0.f64(), s->T1.f64(), s->A0.f64(), s->k, 1);             // A0 = V0' T1
+      LAUNCHED();
+      jacobi_eig_kernel<<<1, kJacobiThreads, a_in_smem ? jsm : 0, c.stream>>>(s->A0.f64(), s->Vt.f64(), s->k, s->Q.f32(),
+                                                                            s->diag.f32(), s->T1.f64(), 30, a_in_smem);
+      LAUNCHED(); CU(cudaGetLastError());
+      matmul_kk_kernel<<<kkb, 256, 0, c.stream>>>(s->V0.f64(), s->T1.f64(), s->Btmp.f64(), s->k, 0);           // Q = V0 V1
+      LAUNCHED();
+      convert_kk_kernel<<<kkb, 256, 0, c.stream>>>(s->Btmp.f64(), s->Q.f32(), s->k, 0);
+      LAUNCHED(); CU(cudaGetLastError());
+    } else {
+      jacobi_eig_kernel<<<1, kJacobiThreads, a_in_smem ? jsm : 0, c.stream>>>(s->G64.f64(), s->Vt.f64(), s->k, s->Q.f32(),
+                                                                            s->diag.f32(), s->Btmp.f64(), 30, a_in_smem);
+      LAUNCHED(); CU(cudaGetLastError());
+    }
     // fixed <- fixed Q (whole matrix), solved slice <- slice Q, B <- B Q
     TRY(rotate_matrix(c, X, n_fixed, s->Q.f32(), s->k));
     TRY(rotate_matrix(c, Y, A.n_cols, s->Q.f32(), s->k));
-    matmul_kk_kernel<<<(s->k * s->k + 255) / 256, 256, 0, c.stream>>>(s->B64.f64(), s->Btmp.f64(),
-                                                                     s->Vt.f64(), s->k);
+    matmul_kk_kernel<<<kkb, 256, 0, c.stream>>>(s->B64.f64(), s->Btmp.f64(), s->Vt.f64(), s->k);
     LAUNCHED(); CU(cudaGetLastError());
     CU(cudaMemcpyAsync(s->B64.p, s->Vt.p, sizeof(double) * (size_t)s->k * s->k, cudaMemcpyDeviceToDevice, c.stream));
+    CU(cudaMemcpyAsync(s->Weig[fixed].p, s->Vt.p, sizeof(double) * (size_t)s->k * s->k, cudaMemcpyDeviceToDevice, c.stream));
+    s->eig_warm[fixed] = true;
     s->basis_identity = false;
     diag = s->diag.f32();
     G = nullptr;
@@ -835,9 +894,21 @@ extern "C" int b200als_transform(b200als_session* s, float* host_out, double* lo
   const size_t bytes = sizeof(float) * (size_t)s->k * (size_t)A.n_cols;
   CU(res.ensure(bytes));
   CU(cudaMemsetAsync(res.p, 0, bytes, c.stream));  // res = zeros (R/model_WRMF.R:423-427)
+  if (s->with_biases && A.n_cols > 0) {            // res[1, ] = 1 (R/model_WRMF.R:429-431)
+    set_col_kernel<<<(A.n_cols + 255) / 256, 256, 0, c.stream>>>(res.f32(), s->k, 0, A.n_cols, 1.0f);
+    LAUNCHED(); CU(cudaGetLastError());
+  }
   const int solver = (s->opt.solver == B200ALS_CONJUGATE_GRADIENT) ? B200ALS_CHOLESKY : s->opt.solver;  // avoid_cg (:112)
   TRY(session_half(s, B200ALS_USERS, solver, res.f32(), loss));
   return export_rotated(s, res.f32(), A.n_cols, host_out);
+}
+
+extern "C" int b200als_set_bias(b200als_session* s, int with_user_item_bias, double global_bias) {
+  if (!s) return fail(B200ALS_EINVAL, "null session");
+  if (with_user_item_bias && s->k < 3) return fail(B200ALS_EINVAL, "with_user_item_bias needs factor matrices of rank + 2 >= 3 rows");
+  s->with_biases = with_user_item_bias ? 1 : 0;
+  s->global_bias = global_bias;
+  return B200ALS_OK;
 }
 
 extern "C" int b200als_row_plan(b200als_session* s, int which, int32_t counts[6], int32_t caps[5], int64_t* nnz_local) {

@@ -17,6 +17,91 @@ struct BiasArgs {
 //   otherwise:           X = [x_bias, ..., 1]   Y = [1, ..., y_bias]     X_nnz = X rows 1..rank-1, x_biases = first row
 // Here the views are materialised once on the device as compact matrices Xc (n_src x k), xb (n_src), Yc (n_tgt x k),
 // k = rank - 1, the generic kernels run on those, and the solved rows are scattered back into Y.
+//
+// half_on_device: everything between the uploads and the downloads of a half-iteration with (or without) bias terms, on
+// DEVICE buffers -- shared by the stateless calls (host pointers around it) and the device-resident session.
+//   dX: n_src x rank (fixed), dY: n_tgt x rank (solved in place), dG: XtX of the (rank - with_biases)-wide view or nullptr
+//   (computed here), d_gbb: device copy of global_bias_base ([ks], in/out; only without user/item biases).
+// On return `o` carries the regulariser window of the loss (reg_ld / reg_lo / reg_hi) for finish_loss.
+template <typename T>
+struct BiasScratch {
+  DevBuf Xc, Yc, Xb, Rhs, G;
+};
+template <typename T>
+static int half_on_device(Ctx& c, CscDev<T>& D, int rank, const T* dX, T* dY, long long n_src, long long n_tgt, const T* dG,
+                          HalfOpts& o, int with_biases, int is_x_bias_last_row, double global_bias, T* d_gbb,
+                          int initialize_bias_base, BiasScratch<T>& W) {
+  const bool implicit = (o.feedback == B200ALS_IMPLICIT);
+  const bool wb = with_biases != 0, is_last = is_x_bias_last_row != 0;
+  double gbias = implicit ? global_bias : 0.0;
+  if (gbias < std::sqrt((double)std::numeric_limits<T>::epsilon())) gbias = 0.0;          // wrmf_implicit.hpp:108-109
+  if (wb && rank < 2) return fail(B200ALS_EINVAL, "with_biases needs at least 2 rows in X / Y");
+  if (!wb && gbias != 0.0 && !d_gbb) return fail(B200ALS_EINVAL, "global_bias needs global_bias_base");
+  const int ks = wb ? rank - 1 : rank;           // size of the solved system
+  const int xo = (wb && !is_last) ? 1 : 0;       // X_nnz = drop_row(X_nnz, is_x_bias_last_row)          (:190 / :88)
+  const int xbcol = is_last ? rank - 1 : 0;      // x_biases                                             (:115-119)
+  const int io = (wb && is_last) ? 1 : 0;        // init = drop_row(init, !is_x_bias_last_row), sic      (:191 / :90)
+  const int oo = (wb && !is_last) ? 1 : 0;       // Y.head(rank-1) / Y.tail(rank-1)                      (:240-252)
+  const T* Xs = dX;   // what the kernels gather from
+  T* Ys = dY;         // what they solve in place
+  const int cp_grid = c.sm_count * 8;
+  if (wb) {
+    CU(W.Xc.ensure(sizeof(T) * (size_t)ks * (size_t)std::max<long long>(1, n_src)));
+    CU(W.Yc.ensure(sizeof(T) * (size_t)ks * (size_t)std::max<long long>(1, n_tgt)));
+    CU(W.Xb.ensure(sizeof(T) * (size_t)std::max<long long>(1, n_src)));
+    pack_cols_kernel<T><<<cp_grid, 256, 0, c.stream>>>(dX, rank, xo, ks, n_src, W.Xc.template as<T>());
+    LAUNCHED(); CU(cudaGetLastError());
+    pack_cols_kernel<T><<<cp_grid, 256, 0, c.stream>>>(dX, rank, xbcol, 1, n_src, W.Xb.template as<T>());
+    LAUNCHED(); CU(cudaGetLastError());
+    pack_cols_kernel<T><<<cp_grid, 256, 0, c.stream>>>(dY, rank, io, ks, n_tgt, W.Yc.template as<T>());
+    LAUNCHED(); CU(cudaGetLastError());
+    Xs = W.Xc.template as<T>();
+    Ys = W.Yc.template as<T>();
+    o.with_biases = 1;
+    o.xbias = W.Xb.p;
+    o.reg_ld = rank;                     // every learned row of X: all but the row of ones (:286-302 / :148-172)
+    o.reg_lo = is_last ? 1 : 0;
+    o.reg_hi = is_last ? rank : rank - 1;
+  }
+  o.gbias = gbias;
+  const T* G = nullptr;
+  if (implicit) {
+    if (dG) {
+      G = dG;
+    } else {
+      CU(W.G.ensure(sizeof(T) * (size_t)ks * ks));
+      TRY(run_gram<T>(c, Xs, ks, n_src, o.lambda, W.G.template as<T>(), nullptr));   // R/model_WRMF.R:474-486
+      G = W.G.template as<T>();
+    }
+    if (wb || gbias != 0.0) {
+      // rhs_init = -X_nnz-view * (x_biases + global_bias) (:143-154) ; global_bias_base = sum(X, 1) * (-global_bias) (:111-112)
+      CU(W.Rhs.ensure(sizeof(T) * (size_t)ks));
+      const bool compute = wb || initialize_bias_base;
+      if (compute) {
+        if (ks > 256) return fail(B200ALS_EUNSUPPORTED, "bias terms: rank > 256 is not supported");
+        const int cs_grid = c.sm_count * 4;
+        CU(c.reg_partials.ensure(sizeof(double) * (size_t)cs_grid * ks));
+        weighted_colsum_kernel<T><<<cs_grid, 256, 0, c.stream>>>(Xs, ks, n_src, wb ? W.Xb.template as<T>() : nullptr,
+                                                               wb ? (T)gbias : T(1), c.reg_partials.f64());
+        LAUNCHED(); CU(cudaGetLastError());
+        finish_colsum_kernel<T><<<(ks + 127) / 128, 128, 0, c.stream>>>(c.reg_partials.f64(), cs_grid, ks, wb ? -1.0 : -gbias,
+                                                                       W.Rhs.template as<T>());
+        LAUNCHED(); CU(cudaGetLastError());
+        if (!wb) CU(cudaMemcpyAsync(d_gbb, W.Rhs.p, sizeof(T) * (size_t)ks, cudaMemcpyDeviceToDevice, c.stream));
+      } else {
+        CU(cudaMemcpyAsync(W.Rhs.p, d_gbb, sizeof(T) * (size_t)ks, cudaMemcpyDeviceToDevice, c.stream));
+      }
+      o.rhs_init = W.Rhs.p;
+    }
+  }
+  TRY(solve_rows<T>(c, D, Xs, Ys, G, nullptr, ks, o));
+  if (wb) {
+    unpack_cols_kernel<T><<<cp_grid, 256, 0, c.stream>>>(W.Yc.template as<T>(), ks, n_tgt, dY, rank, oo);
+    LAUNCHED(); CU(cudaGetLastError());
+  }
+  return B200ALS_OK;
+}
+
 template <typename T>
 static int stateless_half(const b200als_csc* A, int rank, const T* X, T* Y, const T* XtX, const T* cnt_X, HalfOpts o,
                           double* loss, const BiasArgs<T>& ba = BiasArgs<T>()) {
@@ -25,73 +110,29 @@ static int stateless_half(const b200als_csc* A, int rank, const T* X, T* Y, cons
   if (!A || !X || !Y) return fail(B200ALS_EINVAL, "null argument");
   if (rank <= 0) return fail(B200ALS_EINVAL, "rank must be positive");
   const bool implicit = (o.feedback == B200ALS_IMPLICIT);
-  const bool wb = ba.with_biases != 0, is_last = ba.is_x_bias_last_row != 0;
-  double gbias = implicit ? ba.global_bias : 0.0;
-  if (gbias < std::sqrt((double)std::numeric_limits<T>::epsilon())) gbias = 0.0;          // wrmf_implicit.hpp:108-109
-  if (wb && rank < 2) return fail(B200ALS_EINVAL, "with_biases needs at least 2 rows in X / Y");
-  if (!wb && gbias != 0.0 && !ba.global_bias_base) return fail(B200ALS_EINVAL, "global_bias needs global_bias_base");
-  const int ks = wb ? rank - 1 : rank;           // size of the solved system
-  const int xo = (wb && !is_last) ? 1 : 0;       // X_nnz = drop_row(X_nnz, is_x_bias_last_row)          (:190 / :88)
-  const int xbcol = is_last ? rank - 1 : 0;      // x_biases                                             (:115-119)
-  const int io = (wb && is_last) ? 1 : 0;        // init = drop_row(init, !is_x_bias_last_row), sic      (:191 / :90)
-  const int oo = (wb && !is_last) ? 1 : 0;       // Y.head(rank-1) / Y.tail(rank-1)                      (:240-252)
+  const bool wb = ba.with_biases != 0;
+  const int ks = wb ? rank - 1 : rank;
   CscDev<T> D;
   TRY(upload_csc<T>(A, D, c.stream));
   const size_t k = (size_t)rank;
   const size_t n_src = (size_t)A->n_rows, n_tgt = (size_t)A->n_cols;
-  DevBuf dX, dY, dG, dCnt, dXc, dYc, dXb, dRhs;
+  DevBuf dX, dY, dG, dCnt, dGbb;
+  BiasScratch<T> W;
   CU(dX.ensure(sizeof(T) * k * n_src));
   CU(dY.ensure(sizeof(T) * k * n_tgt));
   CU(cudaMemcpyAsync(dX.p, X, sizeof(T) * k * n_src, cudaMemcpyHostToDevice, c.stream));
   CU(cudaMemcpyAsync(dY.p, Y, sizeof(T) * k * n_tgt, cudaMemcpyHostToDevice, c.stream));
-  const T* Xs = dX.template as<T>();   // what the kernels gather from
-  T* Ys = dY.template as<T>();         // what they solve in place
-  const int cp_grid = c.sm_count * 8;
-  if (wb) {
-    CU(dXc.ensure(sizeof(T) * (size_t)ks * std::max<size_t>(1, n_src)));
-    CU(dYc.ensure(sizeof(T) * (size_t)ks * std::max<size_t>(1, n_tgt)));
-    CU(dXb.ensure(sizeof(T) * std::max<size_t>(1, n_src)));
-    pack_cols_kernel<T><<<cp_grid, 256, 0, c.stream>>>(dX.template as<T>(), rank, xo, ks, (long long)n_src, dXc.template as<T>());
-    LAUNCHED(); CU(cudaGetLastError());
-    pack_cols_kernel<T><<<cp_grid, 256, 0, c.stream>>>(dX.template as<T>(), rank, xbcol, 1, (long long)n_src, dXb.template as<T>());
-    LAUNCHED(); CU(cudaGetLastError());
-    pack_cols_kernel<T><<<cp_grid, 256, 0, c.stream>>>(dY.template as<T>(), rank, io, ks, (long long)n_tgt, dYc.template as<T>());
-    LAUNCHED(); CU(cudaGetLastError());
-    Xs = dXc.template as<T>();
-    Ys = dYc.template as<T>();
-    o.with_biases = 1;
-    o.xbias = dXb.p;
-    o.reg_ld = rank;                     // every learned row of X: all but the row of ones (:286-302 / :148-172)
-    o.reg_lo = is_last ? 1 : 0;
-    o.reg_hi = is_last ? rank : rank - 1;
-  }
-  o.gbias = gbias;
   const T* G = nullptr;
-  if (implicit) {
+  if (implicit && XtX) {
     CU(dG.ensure(sizeof(T) * (size_t)ks * ks));
-    if (XtX) CU(cudaMemcpyAsync(dG.p, XtX, sizeof(T) * (size_t)ks * ks, cudaMemcpyHostToDevice, c.stream));
-    else TRY(run_gram<T>(c, Xs, ks, A->n_rows, o.lambda, dG.template as<T>(), nullptr));   // R/model_WRMF.R:474-486
+    CU(cudaMemcpyAsync(dG.p, XtX, sizeof(T) * (size_t)ks * ks, cudaMemcpyHostToDevice, c.stream));
     G = dG.template as<T>();
-    if (wb || gbias != 0.0) {
-      // rhs_init = -X_nnz-view * (x_biases + global_bias) (:143-154) ; global_bias_base = sum(X, 1) * (-global_bias) (:111-112)
-      CU(dRhs.ensure(sizeof(T) * (size_t)ks));
-      const bool compute = wb || ba.initialize_bias_base;
-      if (compute) {
-        if (ks > 256) return fail(B200ALS_EUNSUPPORTED, "bias terms: rank > 256 is not supported");
-        const int cs_grid = c.sm_count * 4;
-        CU(c.reg_partials.ensure(sizeof(double) * (size_t)cs_grid * ks));
-        weighted_colsum_kernel<T><<<cs_grid, 256, 0, c.stream>>>(Xs, ks, (long long)n_src, wb ? dXb.template as<T>() : nullptr,
-                                                               wb ? (T)gbias : T(1), c.reg_partials.f64());
-        LAUNCHED(); CU(cudaGetLastError());
-        finish_colsum_kernel<T><<<(ks + 127) / 128, 128, 0, c.stream>>>(c.reg_partials.f64(), cs_grid, ks, wb ? -1.0 : -gbias,
-                                                                       dRhs.template as<T>());
-        LAUNCHED(); CU(cudaGetLastError());
-        if (!wb) CU(cudaMemcpyAsync(ba.global_bias_base, dRhs.p, sizeof(T) * (size_t)ks, cudaMemcpyDeviceToHost, c.stream));
-      } else {
-        CU(cudaMemcpyAsync(dRhs.p, ba.global_bias_base, sizeof(T) * (size_t)ks, cudaMemcpyHostToDevice, c.stream));
-      }
-      o.rhs_init = dRhs.p;
-    }
+  }
+  T* d_gbb = nullptr;
+  if (implicit && !wb && ba.global_bias_base) {
+    CU(dGbb.ensure(sizeof(T) * (size_t)ks));
+    CU(cudaMemcpyAsync(dGbb.p, ba.global_bias_base, sizeof(T) * (size_t)ks, cudaMemcpyHostToDevice, c.stream));
+    d_gbb = dGbb.template as<T>();
   }
   const T* dcnt = nullptr;
   if (o.feedback == B200ALS_EXPLICIT && o.dynamic_lambda && o.lambda > 0) {
@@ -100,11 +141,10 @@ static int stateless_half(const b200als_csc* A, int rank, const T* X, T* Y, cons
     CU(cudaMemcpyAsync(dCnt.p, cnt_X, sizeof(T) * n_src, cudaMemcpyHostToDevice, c.stream));
     dcnt = dCnt.template as<T>();
   }
-  TRY(solve_rows<T>(c, D, Xs, Ys, G, nullptr, ks, o));
-  if (wb) {
-    unpack_cols_kernel<T><<<cp_grid, 256, 0, c.stream>>>(dYc.template as<T>(), ks, (long long)n_tgt, dY.template as<T>(), rank, oo);
-    LAUNCHED(); CU(cudaGetLastError());
-  }
+  TRY(half_on_device<T>(c, D, rank, dX.template as<T>(), dY.template as<T>(), (long long)n_src, (long long)n_tgt, G, o,
+                        ba.with_biases, ba.is_x_bias_last_row, ba.global_bias, d_gbb, ba.initialize_bias_base, W));
+  if (d_gbb && o.gbias != 0.0 && ba.initialize_bias_base)
+    CU(cudaMemcpyAsync(ba.global_bias_base, d_gbb, sizeof(T) * (size_t)ks, cudaMemcpyDeviceToHost, c.stream));
   CU(cudaMemcpyAsync(Y, dY.p, sizeof(T) * k * n_tgt, cudaMemcpyDeviceToHost, c.stream));
   TRY(finish_loss<T>(c, dX.template as<T>(), rank, A->n_rows, dcnt, o, A->nnz, 0.0, false, loss));
   return B200ALS_OK;

@@ -138,6 +138,9 @@ class Session:
         L.check(L.lib().b200als_exchange_mode(self._h, C.byref(m)))
         return ("none", "p2p", "nccl")[m.value]
 
+    def set_bias(self, with_user_item_bias, global_bias=0.0):
+        L.check(L.lib().b200als_set_bias(self._h, int(bool(with_user_item_bias)), float(global_bias)))
+
     def row_plan(self, which):
         """Rows per kernel of the last CG half-iteration of `which` and the local number of entries."""
         counts = np.zeros(6, np.int32)
@@ -268,8 +271,9 @@ class WRMF:
         self._cnt_u = cnt_u
         logger.info("starting factorization")
         biased = wuib or (self._feedback == "implicit" and self.global_bias != 0.0)
-        if self._precision == "float" and not biased:
-            res = self._fit_session(items, users, n_user, n_item, U, comp, n_iter, convergence_tol)
+        if self._precision == "float":
+            # device-resident session; bias terms included (b200als_set_bias)
+            res = self._fit_session(items, users, n_user, n_item, U, comp, n_iter, convergence_tol, biased)
         else:
             loss_prev = np.inf
             for i in range(int(n_iter)):
@@ -286,10 +290,12 @@ class WRMF:
             res = self._transform(users)
         return res
 
-    def _fit_session(self, items, users, n_user, n_item, U, comp, n_iter, convergence_tol):
+    def _fit_session(self, items, users, n_user, n_item, U, comp, n_iter, convergence_tol, biased=False):
         s = Session(items, users, n_user, n_item, self._rank, self._feedback, self._solver_code, self._cg_steps,
                     self._dynamic_lambda, self._lambda, self._kernel)
         try:
+            if biased:
+                s.set_bias(self._with_user_item_bias, self.global_bias if self._feedback == "implicit" else 0.0)
             s.set_factors(L.USERS, U)
             s.set_factors(L.ITEMS, comp)
             trace, done = s.fit(n_iter, convergence_tol)

@@ -8,7 +8,7 @@ import pytest
 
 import oracle
 import wrmf_cases as wc
-from rsparse_b200 import WRMF, als_explicit, als_implicit
+from rsparse_b200 import WRMF, Session, als_explicit, als_implicit
 from rsparse_b200 import _lib as L
 from rsparse_b200.ops import initialize_biases
 from test_oracle_bias import run_oracle_bias
@@ -195,3 +195,65 @@ def test_wrmf_class_with_global_bias(precision, feedback, solver, wuib):
         s = train.data.sum()
         assert abs(model.global_bias - s / (s + 900.0 * M.shape[1] - train.nnz)) < 1e-12
     assert relF(model.transform(train), emb) < (1e-4 if precision == "float" else 1e-9)
+
+
+@pytest.mark.parametrize("feedback,solver,gbias", [("implicit", wc.CHOL, 0.0), ("implicit", wc.CHOL, 0.05), ("explicit", wc.CG, 0.0),
+                                                   ("explicit", wc.CHOL, 0.0), ("implicit", wc.NNLS, 0.0)])
+def test_biased_session_matches_the_chain_of_reference_shaped_calls(feedback, solver, gbias):
+    """Bias terms inside the device-resident session (b200als_set_bias): two ALS iterations (item half with
+    is_bias_last_row = TRUE, user half with FALSE, R/model_WRMF.R:318-338) and the final transform_ give what the same chain
+    of reference-shaped stateless calls gives -- those are checked against the reference's golden vectors above -- and what
+    the fp64 oracle gives, without any host round trip between half-iterations."""
+    M = wc.load_movielens()
+    users, items = wc.targets_csc(M), wc.targets_csc(M.T)
+    n_user, n_item = M.shape
+    rank, lam = 6, 0.1
+    kf = rank + 2
+    U = wc.det_factors(n_user, kf, 81, 0.1)
+    I = wc.det_factors(n_item, kf, 82, 0.1)
+    if solver == wc.NNLS:
+        U, I = np.abs(U), np.abs(I)
+    U[:, 0] = 1.0            # users: [1, ..., user_bias]
+    I[:, kf - 1] = 1.0       # items: [item_bias, ..., 1]
+    cnt_i = np.diff(users[0]).astype(np.float32)      # nnz per user: cnt_X of the item half
+    cnt_u = np.diff(items[0]).astype(np.float32)      # nnz per item: cnt_X of the user half
+    s = Session(items, users, n_user, n_item, kf, feedback, solver, 3, True, lam)
+    s.set_bias(True, gbias)
+    s.set_factors(L.USERS, U)
+    s.set_factors(L.ITEMS, I)
+    trace, done = s.fit(2, -1.0)
+    Us, Is = s.get_factors(L.USERS), s.get_factors(L.ITEMS)
+    emb, _ = s.transform()
+    s.close()
+    assert done == 2 and np.all(Us[:, 0] == 1) and np.all(Is[:, kf - 1] == 1) and np.all(emb[:, 0] == 1)
+
+    def chain(dt, fi, fe):
+        Uc, Ic = U.astype(dt), I.astype(dt)
+        losses = []
+        for _ in range(2):
+            for mat, X, Y, last, cnt in ((items, Uc, Ic, True, cnt_i), (users, Ic, Uc, False, cnt_u)):
+                if feedback == "implicit":
+                    gbb = np.zeros(kf - 1, dt)
+                    losses.append(fi(mat, X, Y, last, gbb))
+                else:
+                    losses.append(fe(mat, X, Y, last, cnt.astype(dt)))
+        return Uc, Ic, losses
+
+    # (1) the same chain through the stateless, reference-shaped calls (fp32, GPU)
+    U1, I1, l1 = chain(np.float32,
+                       lambda m, X, Y, last, gbb: als_implicit(m[0], m[1], m[2], X, Y, lam, solver, 3, with_user_item_bias=True,
+                                                               is_bias_last_row=last, global_bias=gbias, global_bias_base=gbb,
+                                                               initialize_bias_base=True),
+                       lambda m, X, Y, last, cnt: als_explicit(m[0], m[1], m[2], X, Y, cnt, lam, solver, 3, True,
+                                                               with_user_item_bias=True, is_bias_last_row=last))
+    tol = 5e-3 if solver == wc.NNLS else 2e-5
+    assert relF(Us, U1) < tol and relF(Is, I1) < tol
+    assert np.allclose(trace, l1, rtol=1e-3 if solver == wc.NNLS else 1e-5)
+    # (2) the fp64 oracle (CPU restatement of every bias branch, pinned to the reference in test_oracle_bias.py)
+    U2, I2, l2 = chain(np.float64,
+                       lambda m, X, Y, last, gbb: oracle.als_implicit_bias(m[0], m[1], m[2], X, Y, wc.xtx_for(dict(X=X, lam=lam, with_biases=True, is_last=last), np.float64),
+                                                                           lam, solver, 3, True, last, gbias, gbb, True),
+                       lambda m, X, Y, last, cnt: oracle.als_explicit_bias(m[0], m[1], m[2], X, Y, cnt, lam, solver, 3, True, True, last))
+    tol2 = 2e-2 if solver == wc.NNLS else 2e-4      # two chained iterations, fp32 vs fp64 (cf. the 3-iteration trace bound)
+    assert relF(Us, U2) < tol2 and relF(Is, I2) < tol2
+    assert np.allclose(trace, l2, rtol=1e-3 if solver == wc.NNLS else 5e-5)

@@ -144,15 +144,20 @@ def test_gram_kernel_vs_oracle():
         assert np.array_equal(G, gram(X, 0.3))   # fixed-order reduction => reproducible
 
 
-@pytest.mark.parametrize("name", ["ml100k_implicit_cg_k16", "ml100k_implicit_chol_k8", "ml100k_explicit_cg_k8"])
-def test_session_fit_matches_reference_trace(name, golden_traces):
-    """b200als_fit (the loop of R/model_WRMF.R:318-338) + transform_ vs the reference-generated trace."""
+@pytest.mark.parametrize("name,kernel,warm", [("ml100k_implicit_cg_k16", 0, "1"), ("ml100k_implicit_chol_k8", 0, "1"),
+                                              ("ml100k_explicit_cg_k8", 0, "1"), ("ml100k_implicit_cg_k16", 10, "1"),
+                                              ("ml100k_implicit_cg_k16", 10, "0"), ("ml100k_implicit_cg_k16", 3, "1")])
+def test_session_fit_matches_reference_trace(name, kernel, warm, golden_traces, monkeypatch):
+    """b200als_fit (the loop of R/model_WRMF.R:318-338) + transform_ vs the reference-generated trace.  kernel = 10 / 3 force the
+    eigenbasis of XtX in every half-iteration of this small problem (ITEM and USER halves: the basis is re-diagonalised six
+    times, warm-started from each side's previous eigenvectors unless B200ALS_EIG_WARM=0)."""
+    monkeypatch.setenv("B200ALS_EIG_WARM", warm)
     M = wc.load_movielens()
     users, items = wc.targets_csc(M), wc.targets_csc(M.T)
     U0, I0 = golden_traces[name + "/U0"], golden_traces[name + "/I0"]
     k = U0.shape[1]
     s = Session(items, users, M.shape[0], M.shape[1], k, str(golden_traces[name + "/feedback"]),
-                int(golden_traces[name + "/solver"]), 3, True, float(golden_traces[name + "/lam"]))
+                int(golden_traces[name + "/solver"]), 3, True, float(golden_traces[name + "/lam"]), kernel)
     s.set_factors(L.USERS, U0)
     s.set_factors(L.ITEMS, I0)
     trace, done = s.fit(3, -1.0)
