@@ -436,16 +436,20 @@ def test_gram_tensor_core_blocks_and_bf16(k, monkeypatch):
     n = 20000
     X = np.ascontiguousarray(wc.det_factors(n, k, 700 + k, 0.1) * (1.0 + np.arange(k, dtype=np.float32)) ** -0.5)
     ref = X.astype(np.float64).T @ X.astype(np.float64) + 0.3 * np.eye(k)
+    # accuracy in the Frobenius norm and against the largest entry (off-diagonal entries of a Gram are sums with
+    # cancellation: their elementwise relative error is not a meaningful yardstick)
+    def errs(G):
+        return relF(G, ref), float(np.abs(G.astype(np.float64) - ref).max() / np.abs(ref).max())
     monkeypatch.setenv("B200ALS_GRAM", "tf32x3")
     G = gram(X, 0.3)
-    assert np.allclose(G, ref, rtol=3e-6, atol=1e-7) and np.array_equal(G, G.T)
+    assert max(errs(G)) < 3e-6 and np.array_equal(G, G.T), errs(G)
     monkeypatch.setenv("B200ALS_GRAM", "ffma")
     Gf = gram(X, 0.3)
-    assert np.allclose(Gf, ref, rtol=3e-6, atol=1e-7)
+    assert max(errs(Gf)) < 3e-6, errs(Gf)
     monkeypatch.setenv("B200ALS_GRAM", "bf16")
     Gb = gram(X, 0.3)
-    err = relF(Gb, ref)
-    assert 1e-6 < err < 5e-3, err          # bf16 operands: visibly not fp32-grade, but a usable Gram
+    eb = errs(Gb)
+    assert 1e-6 < eb[0] < 5e-3 and eb[1] < 5e-3, eb     # bf16 operands: visibly not fp32-grade, but a usable Gram
     assert np.array_equal(Gb, Gb.T)
 
 
