@@ -363,6 +363,7 @@ def main():
     else:
         rows = plan["rows"]
         by = {"als_cg_resident_kernel": rows["resident"], "als_cg_tile_kernel": rows["tile_4cta"] + rows["tile_2cta"] + rows["tile_1cta"],
+              "als_cg_tile_kernel (thread-block clusters)": rows["cluster2"] + rows["cluster4"] + rows["cluster8"],
               "als_cg_generic_kernel": rows["streaming"]}
         if args.kernel == 1:
             by = {"als_cg_generic_kernel": rows_local}

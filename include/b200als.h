@@ -266,9 +266,10 @@ int b200als_create_synthetic(b200als_session** out, int32_t n_user_local, int64_
 int b200als_set_bias(b200als_session* s, int with_user_item_bias, double global_bias);
 
 /* Which kernel took how many rows in the last CG half-iteration of orientation `which` (bench.py reports it):
- * counts[0] register-resident kernel, [1..3] shared-memory tile kernel (4 / 2 / 1 CTAs per SM), [4] streaming kernel,
- * [5] empty rows; caps[0..4] = longest row each class takes.  nnz_local = entries of the local block. */
-int b200als_row_plan(b200als_session* s, int which, int32_t counts[6], int32_t caps[5], int64_t* nnz_local);
+ * counts[0] register-resident kernel, [1..3] shared-memory tile kernel (4 / 2 / 1 CTAs per SM), [4..6] the same kernel
+ * on thread-block clusters of 2 / 4 / 8 CTAs, [7] streaming kernel, [8] empty rows; caps[0..7] = longest row each class
+ * takes.  nnz_local = entries of the local block. */
+int b200als_row_plan(b200als_session* s, int which, int32_t counts[9], int32_t caps[8], int64_t* nnz_local);
 
 /* Skewed synthetic data for the robustness points of bench.py: col_dist 0 = one id per equal-width stratum
  * (as above), 1 = Zipf(1.0)-like popularity (ids log-uniform over [0, n_item), made distinct and ascending per row);

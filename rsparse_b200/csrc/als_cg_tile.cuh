@@ -24,6 +24,11 @@
 //   * XtX p: d (.) p in the eigenbasis of XtX (eig.cuh), or (kFullG) every (warp, lane group) multiplies its slab
 //     of XtX rows from L1/L2 and the slabs ride the same reduction; lambda_use p for explicit feedback;
 //   * the loss term X_nnz' y comes from the u vectors already computed (X_nnz'y = X_nnz'x0 + sum_k alpha_k X_nnz'p_k).
+//   * rows too long for one CTA's buffers (the item half-iteration; heavy-tailed data) are solved by a THREAD-BLOCK
+//     CLUSTER of 2, 4 or 8 CTAs (kCluster): CTA r of the cluster stages and keeps the r-th contiguous slab of the row's
+//     tile, every sweep ends with one cluster barrier after which each CTA adds the per-CTA partial sums of all slabs in
+//     rank order through distributed shared memory (mapa + ld.shared::cluster) -- the tile is still read from HBM once.
+//     All CTAs of a cluster carry the same CG state and take the same exits; CTA 0 writes the row and its lambda |y|^2.
 // Algorithmic HBM bytes per row: 4nk + 8n + 4 + 4k + 4k.
 #pragma once
 #include "als_resident.cuh"   // packed-fp32 helpers (dot4, axpy4, fma4, ...)
@@ -63,7 +68,8 @@ struct TileCgLayout {
   __host__ __device__ int n_vbuf() const { return warps > 4 ? 1 : 2; }
   __host__ __device__ size_t vbuf_off(int b) const { return ybuf_off(2) + (size_t)b * warps * kpad * 4; }
   __host__ __device__ size_t sum_off() const { return vbuf_off(n_vbuf()); }                                    // [2][kpad] two-stage cross-warp sum
-  __host__ __device__ size_t vec_off() const { return sum_off() + (size_t)2 * kpad * 4; }               // [warps][kpad], kFullG only
+  __host__ __device__ size_t csum_off() const { return sum_off() + (size_t)2 * kpad * 4; }              // [2][kpad] this CTA's partial, read by its cluster peers
+  __host__ __device__ size_t vec_off() const { return csum_off() + (size_t)2 * kpad * 4; }              // [warps][kpad], kFullG only
   __host__ __device__ size_t idx_off(int s) const { return vec_off() + (full_g ? (size_t)warps * kpad * 4 : 0) + (size_t)s * cap * 4; }
   __host__ __device__ size_t val_off(int s) const { return idx_off(3) + (size_t)s * cap * 4; }
   __host__ __device__ size_t ubuf_off(int b) const { return val_off(3) + (size_t)b * cap * 4; }
@@ -72,7 +78,22 @@ struct TileCgLayout {
   __host__ __device__ size_t bytes() const { return red_off() + 32 * 8; }
 };
 
-template <int LPR, int C, bool kFullG>
+// thread-block cluster primitives (PTX): rank / size of the cluster, barrier with release / acquire semantics over the
+// cluster's shared memories, and a 4-byte load from the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem_f32(const float* local_ptr, uint32_t rank) {
+  uint32_t ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_ptr)), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+template <int LPR, int C, bool kFullG, bool kCluster = false>
 __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
   static_assert(LPR == 4 || LPR == 8 || LPR == 16 || LPR == 32, "lanes per gathered row");
   static_assert(C == 1 || (C == 2 && LPR == 32), "two chunks per lane only at rank 256");
@@ -101,13 +122,21 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
   float* vecw = reinterpret_cast<float*>(smem_raw + L.vec_off()) + (size_t)w * KPAD;   // kFullG: this warp's copy of v
 
   const bool implicit = (P.feedback == 0);
-  const int stride = gridDim.x;
+  // a cluster of CL CTAs works on one row; CTA `crank` of it owns the crank-th contiguous slab of the row's entries
+  const int CL = kCluster ? (int)cluster_nctarank() : 1;
+  const int crank = kCluster ? (int)cluster_ctarank() : 0;
+  const int first = (int)blockIdx.x / CL;
+  const int stride = (int)gridDim.x / CL;
   const long long n_list = P.n_list;
-  auto valid = [&](int i) -> bool { return (long long)blockIdx.x + (long long)i * stride < n_list; };
+  float* csum = reinterpret_cast<float*>(smem_raw + L.csum_off());
+  auto valid = [&](int i) -> bool { return (long long)first + (long long)i * stride < n_list; };
   auto row_of = [&](int i) -> int {
-    const long long t = (long long)blockIdx.x + (long long)i * stride;
+    const long long t = (long long)first + (long long)i * stride;
     return P.row_list ? __ldg(P.row_list + t) : (int)t + P.row_begin;
   };
+  // this CTA's slab of a row with n entries starting at p: [p + lo, p + lo + cnt)
+  auto slab_lo = [&](int n) -> int { const int sl = (n + CL - 1) / CL; return min(n, crank * sl); };
+  auto slab_cnt = [&](int n) -> int { const int sl = (n + CL - 1) / CL; const int lo = min(n, crank * sl); return min(n, lo + sl) - lo; };
   // which features this lane holds: chunk c covers [128 c + 4 gl, +4); beyond k (k % 4 == 0) the shared-memory copies
   // stay zero for the whole kernel (zero-filled below, never written by a copy), so only global accesses are guarded
   bool fvalid[C];
@@ -150,19 +179,19 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
     rid0 = row_of(0);
     const int p = __ldg(P.ptr + rid0) - P.ptr_base;
     n0 = __ldg(P.ptr + rid0 + 1) - P.ptr_base - p;
-    issue_meta(0, p, n0);
+    issue_meta(0, p + slab_lo(n0), slab_cnt(n0));
   }
   if (valid(1)) {
     rid1 = row_of(1);
     const int p = __ldg(P.ptr + rid1) - P.ptr_base;
     n1 = __ldg(P.ptr + rid1 + 1) - P.ptr_base - p;
-    issue_meta(1, p, n1);
+    issue_meta(1, p + slab_lo(n1), slab_cnt(n1));
   }
   if (valid(2)) { rid2 = row_of(2); p2 = __ldg(P.ptr + rid2) - P.ptr_base; n2 = __ldg(P.ptr + rid2 + 1) - P.ptr_base - p2; }
   if (valid(3)) rid3 = row_of(3);
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
-  if (valid(0)) issue_tile(0, 0, rid0, n0);
+  if (valid(0)) issue_tile(0, 0, rid0, slab_cnt(n0));
 
   float4 dg[C];
 #pragma unroll
@@ -181,20 +210,21 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
   };
 
   for (int i = 0; valid(i); i++) {
-    const int n = n0;
+    const int n_row = n0;              // entries of the whole row (lambda_use)
+    const int n = slab_cnt(n0);        // entries of this CTA's slab
     const int buf = i & 1, sl = i % 3;
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();   // tile i and the metadata of row i+1 have landed; every warp is done with row i-1
     // ---- prefetch (nothing here waits on memory) ----
-    if (valid(i + 1)) issue_tile(buf ^ 1, (i + 1) % 3, rid1, n1);
-    if (valid(i + 2)) issue_meta((i + 2) % 3, p2, n2);
+    if (valid(i + 1)) issue_tile(buf ^ 1, (i + 1) % 3, rid1, slab_cnt(n1));
+    if (valid(i + 2)) issue_meta((i + 2) % 3, p2 + slab_lo(n2), slab_cnt(n2));
     int p3 = 0, p3e = 0, rid4 = -1;
     if (valid(i + 3)) { p3 = ld_pinned_i32(P.ptr + rid3); p3e = ld_pinned_i32(P.ptr + rid3 + 1); }
-    if (valid(i + 4)) rid4 = P.row_list ? ld_pinned_i32(P.row_list + ((long long)blockIdx.x + (long long)(i + 4) * stride))
+    if (valid(i + 4)) rid4 = P.row_list ? ld_pinned_i32(P.row_list + ((long long)first + (long long)(i + 4) * stride))
                                         : row_of(i + 4);
 
     const float* sv = val_of(sl);
-    const float lam_use = implicit ? P.lambda : (P.lambda * (P.dynamic_lambda ? (float)n : 1.0f));
+    const float lam_use = implicit ? P.lambda : (P.lambda * (P.dynamic_lambda ? (float)n_row : 1.0f));
     // Row steps: step rs of warp w covers gathered rows (rs * W + w) * RPW + gi.  Register s of a batch holds row step
     // b0 + (s ^ slot): lanes of different slots keep their batch permuted, which makes both halving levels of the
     // reduction the same instruction stream for every lane (keep registers 0/1, send 2/3; keep 0, send 1) -- no selects.
@@ -307,7 +337,21 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
         // many warps: thread f < KPAD adds the W partials of feature f (conflict-free 4-byte reads), the sums are
         // published once and read back by everyone -- W + 1 reads per thread instead of W 16-byte reads per lane
         float* sb = sumv + (sweep & 1) * KPAD;
-        if (tid < KPAD) {
+        if constexpr (kCluster) {
+          // this CTA's slab sum -> csum; after the cluster barrier every CTA adds the CL slab sums in rank order
+          float* cs = csum + (sweep & 1) * KPAD;
+          if (tid < KPAD) {
+            float s1 = vb[tid];
+            for (int ww = 1; ww < W; ww++) s1 += vb[(size_t)ww * KPAD + tid];
+            cs[tid] = s1;
+          }
+          cluster_sync_all();
+          if (tid < KPAD) {
+            float s2 = ld_dsmem_f32(cs + tid, 0);
+            for (int rr = 1; rr < CL; rr++) s2 += ld_dsmem_f32(cs + tid, (uint32_t)rr);
+            sb[tid] = s2;
+          }
+        } else if (tid < KPAD) {
           float s1 = vb[tid];
           for (int ww = 1; ww < W; ww++) s1 += vb[(size_t)ww * KPAD + tid];
           sb[tid] = s1;
@@ -364,7 +408,7 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
       for (int c = 0; c < C; c++) p[c] = axpy4(bt, p[c], r[c]);
       rsold = rsnew;
     }
-    if (w == 0 && gi == 0) {
+    if (w == 0 && gi == 0 && crank == 0) {
 #pragma unroll
       for (int c = 0; c < C; c++)
         if (fvalid[c]) *reinterpret_cast<float4*>(P.Y + (size_t)rid0 * k + foff[c]) = x[c];
@@ -378,7 +422,7 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
         l += implicit ? d * d * cj : d * d;
       }
       l = warp_sum(l);
-      if (w == 0) l = fmaf(lam_use, vdot(x, x), l);
+      if (w == 0 && crank == 0) l = fmaf(lam_use, vdot(x, x), l);
       if (lane == 0) warp_loss += (double)l;
     }
     // ---- advance the pipeline ----
@@ -388,6 +432,7 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
     rid3 = rid4;
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
+  if constexpr (kCluster) cluster_sync_all();   // no CTA leaves while a peer may still read its shared memory
   const double tot = block_sum_double((lane == 0) ? warp_loss : 0.0, red);
   if (tid == 0) P.loss_partials[blockIdx.x] = tot;
 }

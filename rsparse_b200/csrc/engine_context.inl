@@ -44,10 +44,11 @@ struct CscDev {
   struct RowClass {
     int lo = 0, hi = 0;       // rows with lo <= nnz <= hi
     int cap = 0, warps = 0;   // tile kernel launch shape (0: not a tile class)
+    int cluster = 1;          // CTAs per thread-block cluster (rows of up to cluster * cap entries)
     int count = 0;
     DevBuf list;              // ascending row ids (stable compaction => deterministic launch order)
   };
-  static constexpr int kClsResident = 0, kClsTile0 = 1, kClsLong = 4, kNumCls = 5;
+  static constexpr int kClsResident = 0, kClsTile0 = 1, kNumTile = 6, kClsLong = 7, kNumCls = 8;   // tile classes: 4 / 2 / 1 CTAs per SM, clusters of 2 / 4 / 8
   RowClass cls[kNumCls];
   int plan_key = -1;          // rank * 2 + resident_eligible the plan was built for
   int plan_empty = 0;

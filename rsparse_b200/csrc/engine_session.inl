@@ -911,14 +911,14 @@ extern "C" int b200als_set_bias(b200als_session* s, int with_user_item_bias, dou
   return B200ALS_OK;
 }
 
-extern "C" int b200als_row_plan(b200als_session* s, int which, int32_t counts[6], int32_t caps[5], int64_t* nnz_local) {
+extern "C" int b200als_row_plan(b200als_session* s, int which, int32_t counts[9], int32_t caps[8], int64_t* nnz_local) {
   if (!s || which < 0 || which > 1 || !s->has[which]) return fail(B200ALS_EINVAL, "orientation not present");
   const CscDev<float>& A = s->csc[which];
-  for (int q = 0; q < 5; q++) {
+  for (int q = 0; q < CscDev<float>::kNumCls; q++) {
     if (counts) counts[q] = (A.plan_key >= 0) ? A.cls[q].count : 0;
     if (caps) caps[q] = (A.plan_key >= 0) ? A.cls[q].hi : 0;
   }
-  if (counts) counts[5] = (A.plan_key >= 0) ? A.plan_empty : 0;
+  if (counts) counts[8] = (A.plan_key >= 0) ? A.plan_empty : 0;
   if (nnz_local) *nnz_local = A.nnz;
   return B200ALS_OK;
 }

@@ -92,17 +92,22 @@ static int plan_rows(Ctx& c, CscDev<T>& A, int k, bool resident_ok, bool full_g)
   int warpsL = 16;   // one CTA per SM: 16 warps (two-stage cross-warp sum); B200ALS_TILE_WARPS_L = 4 | 8 | 16 for A/B runs
   if (const char* e = getenv("B200ALS_TILE_WARPS_L")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16) warpsL = v; }
   const size_t sm_bytes = c.smem_optin + 1024;   // per-SM shared memory (the opt-in per-block limit + the 1 KB reserve)
-  const int shape[3][2] = {{4, 4}, {8, 2}, {warpsL, 1}};   // {warps per CTA, CTAs per SM} of the three tile classes
+  // {warps per CTA, CTAs per SM, CTAs per cluster}: three single-CTA classes, then rows split over clusters of 2 / 4 / 8 CTAs
+  const int shape[6][3] = {{4, 4, 1}, {8, 2, 1}, {warpsL, 1, 1}, {16, 1, 2}, {16, 1, 4}, {16, 1, 8}};
+  int max_cluster = 8;   // B200ALS_TILE_CLUSTER = 1 | 2 | 4 | 8: largest cluster used (1: longer rows go to the streaming kernel)
+  if (const char* e = getenv("B200ALS_TILE_CLUSTER")) max_cluster = std::max(1, atoi(e));
   int lo = 1;
   RC& R = A.cls[CscDev<T>::kClsResident];
   R.lo = 1; R.hi = resident_ok ? kResMaxN : 0; R.cap = 0; R.warps = 0;
   if (resident_ok) lo = kResMaxN + 1;
-  for (int t = 0; t < 3; t++) {
+  for (int t = 0; t < CscDev<T>::kNumTile; t++) {
     RC& C = A.cls[CscDev<T>::kClsTile0 + t];
     C.warps = shape[t][0];
+    C.cluster = shape[t][2];
     C.cap = tile_cap_for(kpad, C.warps, sm_bytes / shape[t][1] - 1024, full_g);
     C.lo = lo;
-    C.hi = std::max(lo - 1, C.cap);
+    // a cluster of CL CTAs holds CL slabs of ceil(n / CL) <= cap entries each
+    C.hi = (C.cluster <= max_cluster) ? std::max(lo - 1, C.cap * C.cluster) : lo - 1;
     lo = C.hi + 1;
   }
   RC& Lg = A.cls[CscDev<T>::kClsLong];
@@ -140,7 +145,7 @@ static int plan_rows(Ctx& c, CscDev<T>& A, int k, bool resident_ok, bool full_g)
 }
 
 // launches als_cg_tile_kernel for one length class; *grid_out = CTAs launched (loss partials to sum)
-static int launch_cg_tile(Ctx& c, TileCgParams P, int warps, bool full_g, int* grid_out) {
+static int launch_cg_tile(Ctx& c, TileCgParams P, int warps, int cluster, bool full_g, int* grid_out) {
   const int kpad = tile_kpad(P.k);
   const TileCgLayout L{kpad, P.cap, warps, full_g ? 1 : 0};
   const size_t smem = L.bytes();
@@ -156,8 +161,37 @@ static int launch_cg_tile(Ctx& c, TileCgParams P, int warps, bool full_g, int* g
     kern<<<grid, threads, smem, c.stream>>>(P);
     return cudaSuccess;
   };
-#define B200ALS_TILE_CASE(LPR, CC)                                                             \
-  CU(full_g ? launch(als_cg_tile_kernel<LPR, CC, true>) : launch(als_cg_tile_kernel<LPR, CC, false>))
+  // thread-block clusters: one row per cluster, as many clusters as the device can hold at once
+  auto launch_cluster = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3((unsigned)cluster, 1, 1);
+    cfg.blockDim = dim3((unsigned)threads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c.stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n_clusters = 0;
+    e = cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg);
+    if (e != cudaSuccess) return e;
+    if (n_clusters < 1) return cudaErrorLaunchOutOfResources;
+    n_clusters = std::min(n_clusters, P.n_list);
+    grid = n_clusters * cluster;
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    return cudaLaunchKernelEx(&cfg, kern, P);
+  };
+#define B200ALS_TILE_CASE(LPR, CC)                                                                                    \
+  do {                                                                                                                \
+    if (cluster > 1) CU(full_g ? launch_cluster(als_cg_tile_kernel<LPR, CC, true, true>)                              \
+                               : launch_cluster(als_cg_tile_kernel<LPR, CC, false, true>));                           \
+    else CU(full_g ? launch(als_cg_tile_kernel<LPR, CC, true, false>) : launch(als_cg_tile_kernel<LPR, CC, false, false>)); \
+  } while (0)
   switch (kpad) {
     case 16: B200ALS_TILE_CASE(4, 1); break;
     case 32: B200ALS_TILE_CASE(8, 1); break;
@@ -374,7 +408,7 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
       sum_partials_kernel<<<1, 32, 0, c.stream>>>(P.loss_partials, grid, c.loss_acc.f64(), 1);
       LAUNCHED(); CU(cudaGetLastError());
     }
-    for (int t = 0; t < 3; t++) {
+    for (int t = 0; t < CD::kNumTile; t++) {
       const int q = CD::kClsTile0 + t;
       const typename CD::RowClass& TC = A.cls[q];
       if (TC.count == 0) continue;
@@ -398,7 +432,7 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
       TP.cap = TC.cap;
       TP.loss_partials = P.loss_partials;
       int grid = 0;
-      TRY(launch_cg_tile(c, TP, TC.warps, full_g, &grid));
+      TRY(launch_cg_tile(c, TP, TC.warps, TC.cluster, full_g, &grid));
       sum_partials_kernel<<<1, 32, 0, c.stream>>>(P.loss_partials, grid, c.loss_acc.f64(), 1);
       LAUNCHED(); CU(cudaGetLastError());
     }

@@ -115,6 +115,33 @@ def test_tile_cg_kernel_in_session(name, kernel, cases, golden_half):
     assert np.all(Y[np.diff(c["ptr"]) == 0] == 0)
 
 
+@pytest.mark.parametrize("k,feedback", [(128, "implicit"), (128, "explicit"), (256, "implicit"), (64, "implicit")])
+def test_cluster_tile_kernel_long_rows(k, feedback):
+    """Rows too long for one CTA's tile buffers are solved by thread-block clusters of 2 / 4 / 8 CTAs (slabs of the tile
+    in each CTA's shared memory, per-sweep sums over distributed shared memory); still longer rows by the streaming
+    kernel.  Ragged rows of 1 ... 2399 entries against the fp64 oracle, eigenbasis forced for implicit feedback."""
+    n_rows, n_src, lam = 40, 3000, 0.1
+    ptr, idx, val = wc.det_csr(n_rows, n_src, 1200, 77 + k, ragged=True, explicit=(feedback == "explicit"))
+    X = np.ascontiguousarray(wc.det_factors(n_src, k, 300 + k, 0.1) * (1.0 + np.arange(k, dtype=np.float32)) ** -0.5)
+    Y0 = wc.det_factors(n_rows, k, 301 + k)
+    X64, Yo = X.astype(np.float64), Y0.astype(np.float64)
+    if feedback == "implicit":
+        lo = oracle.als_implicit(ptr, idx, val, X64, Yo, X64.T @ X64 + lam * np.eye(k), lam, wc.CG, 3, 2)
+    else:
+        cnt = np.bincount(idx, minlength=n_src).astype(np.float64)
+        lo = oracle.als_explicit(ptr, idx, val, X64, Yo, cnt, lam, wc.CG, 3, True, 2)
+    s = Session(None, (ptr, idx, val), n_rows, n_src, k, feedback, wc.CG, 3, True, lam, 10)
+    s.set_factors(L.ITEMS, X)
+    s.set_factors(L.USERS, Y0)
+    loss = s.half_iteration(L.USERS)
+    Y = s.get_factors(L.USERS)
+    plan = s.row_plan(L.USERS)["rows"]
+    s.close()
+    assert plan["cluster2"] + plan["cluster4"] + plan["cluster8"] > 0, plan
+    assert relF(Y, Yo) < TOL_F32, (relF(Y, Yo), plan)
+    assert abs(loss - lo) <= TOL_F32 * abs(lo)
+
+
 def test_row_results_depend_only_on_their_own_indices(cases):
     """Bit-exact CSR indexing: permuting the order rows are presented in permutes the result rows bitwise."""
     c = cases["synth_ragged_implicit_cg_k128"]
