@@ -9,8 +9,9 @@
 //     two-warp kernel's stall samples were barrier stalls).
 // Cost: 96 accumulators + temporaries = ~165 registers and 22 KB of shared memory per warp => 10 warps per SM instead of
 // 16, each with twice the instruction-level parallelism.
-// EXPERIMENTAL (kernel = 9): written after the round's GPU budget was spent; compiled, and its per-row index logic is the
-// one emulated by scripts/emulate_chol_rows.py::emulate(K = 64), but it has not yet run on hardware.
+// Default at rank 64 since round 2: parity-green on first run (profiles/r2/), C2 22.8 ms per launch vs 25.2 ms for the
+// two-warp kernel (which stays selectable as kernel = 4).  Its per-row index logic is the one emulated by
+// scripts/emulate_chol_rows.py::emulate(K = 64).
 #pragma once
 #include "als_chol_rows.cuh"
 
