@@ -7,7 +7,9 @@
 #
 # (2) Optional fast path below: keep both factor matrices in HBM for the whole fit
 #     (R/model_WRMF.R:318-338 moves into b200als_fit).  Drop-in replacement for the loop body of
-#     WRMF$fit_transform when precision == "float" and no bias terms are requested.
+#     WRMF$fit_transform when precision == "float"; bias terms (with_user_item_bias / with_global_bias) stay on the
+#     device too: private$rank already counts the two bias rows (R/model_WRMF.R:162-166) and b200als_R_set_bias passes the
+#     flags after the reference's own initialisation code (R/model_WRMF.R:260-297) has filled the bias rows.
 #
 # Not executed in the authoring image (no R there); see INTEGRATION.md.
 
@@ -16,6 +18,9 @@ b200als_fit_transform = function(self, private, c_ui, c_iu, n_iter, convergence_
   feedback_code = if (private$feedback == "implicit") 0L else 1L
   session = .Call("b200als_R_create", c_ui, c_iu, private$rank, feedback_code, solver_code,
                   private$cg_steps, private$dynamic_lambda, private$lambda)
+  if (private$with_user_item_bias || self$global_bias != 0)
+    .Call("b200als_R_set_bias", session, private$with_user_item_bias,
+          if (private$feedback == "implicit") self$global_bias else 0)
   .Call("b200als_R_set_factors", session, 1L, private$U)          # users  (rank x n_user float32)
   .Call("b200als_R_set_factors", session, 0L, self$components)    # items  (rank x n_item float32)
   trace = .Call("b200als_R_fit", session, as.integer(n_iter), as.numeric(convergence_tol))
@@ -25,6 +30,8 @@ b200als_fit_transform = function(self, private, c_ui, c_iu, n_iter, convergence_
   }
   .Call("b200als_R_get_factors", session, 0L, self$components)    # in place, like the reference's solver
   .Call("b200als_R_get_factors", session, 1L, private$U)
+  if (private$feedback == "implicit" && !private$with_user_item_bias && self$global_bias != 0)   # wrmf_implicit.hpp:111-112
+    self$global_bias_base = float::fl(-self$global_bias * rowSums(float::dbl(self$components)))
   res = float::float(0, nrow = private$rank, ncol = ncol(c_iu))
   .Call("b200als_R_transform", session, res)                      # transform_ with avoid_cg (R/model_WRMF.R:412-452)
   t(res)

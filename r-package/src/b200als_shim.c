@@ -161,6 +161,11 @@ SEXP b200als_R_get_factors(SEXP ptr, SEXP which, SEXP fl_out) {
   check(b200als_get_factors((b200als_session*)R_ExternalPtrAddr(ptr), Rf_asInteger(which), float32_matrix(fl_out, NULL, NULL)));
   return R_NilValue;
 }
+/* bias terms inside the session (R/model_WRMF.R:260-297): call after initialize_biases, before the fit */
+SEXP b200als_R_set_bias(SEXP ptr, SEXP with_user_item_bias, SEXP global_bias) {
+  check(b200als_set_bias((b200als_session*)R_ExternalPtrAddr(ptr), Rf_asLogical(with_user_item_bias), Rf_asReal(global_bias)));
+  return R_NilValue;
+}
 SEXP b200als_R_fit(SEXP ptr, SEXP n_iter, SEXP tol) {
   const int n = Rf_asInteger(n_iter);
   SEXP trace = PROTECT(Rf_allocVector(REALSXP, 2 * (n > 0 ? n : 1)));
@@ -247,6 +252,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"b200als_R_create", (DL_FUNC)&b200als_R_create, 8},
     {"b200als_R_set_factors", (DL_FUNC)&b200als_R_set_factors, 3},
     {"b200als_R_get_factors", (DL_FUNC)&b200als_R_get_factors, 3},
+    {"b200als_R_set_bias", (DL_FUNC)&b200als_R_set_bias, 3},
     {"b200als_R_fit", (DL_FUNC)&b200als_R_fit, 3},
     {"b200als_R_transform", (DL_FUNC)&b200als_R_transform, 2},
     {NULL, NULL, 0}};

@@ -53,6 +53,7 @@ struct TileCgParams {
   int ptr_base;
   int row_begin;
   int cap;                  // tile-buffer capacity in gathered rows (every listed row has 1 <= nnz <= cap)
+  int nbuf;                 // 2: double-buffered tiles, 1: single buffer
   double* loss_partials;    // [gridDim.x]
 };
 
@@ -61,8 +62,10 @@ constexpr int kTileBatch = 4;   // row steps per reduction batch
 // shared-memory carve-up (bytes), shared by host and device
 struct TileCgLayout {
   int kpad, cap, warps, full_g;
+  int nbuf = 2;   // tile buffers: 2 = the next row's tile lands while this one computes; 1 = single buffer (twice the capacity
+                  // per byte of shared memory; the load of a row is then hidden by the OTHER CTAs of the SM)
   __host__ __device__ size_t tile_off(int b) const { return (size_t)b * cap * kpad * 4; }
-  __host__ __device__ size_t ybuf_off(int b) const { return tile_off(2) + (size_t)b * kpad * 4; }
+  __host__ __device__ size_t ybuf_off(int b) const { return tile_off(nbuf) + (size_t)b * kpad * 4; }
   // cross-warp exchange: double-buffered per sweep with <= 4 warps (one barrier per sweep); a single buffer with more
   // warps (the two-stage sum has a second barrier per sweep, which also separates consecutive sweeps)
   __host__ __device__ int n_vbuf() const { return warps > 4 ? 1 : 2; }
@@ -109,7 +112,8 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
   const int gi = lane / LPR, gl = lane % LPR;    // lane group within the warp, lane within the group
   const int slot = gl >> SLOT_SHIFT;             // which of a batch's 4 row steps this lane owns after the reduction
   const int k = P.k;
-  const TileCgLayout L{KPAD, P.cap, W, kFullG ? 1 : 0};
+  const TileCgLayout L{KPAD, P.cap, W, kFullG ? 1 : 0, P.nbuf};
+  const bool single = (P.nbuf == 1);
   auto tile_of = [&](int b) { return reinterpret_cast<float*>(smem_raw + L.tile_off(b)); };
   auto ybuf_of = [&](int b) { return reinterpret_cast<float*>(smem_raw + L.ybuf_off(b)); };
   auto vbuf_of = [&](int b) { return reinterpret_cast<float*>(smem_raw + L.vbuf_off(b)); };
@@ -191,7 +195,7 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
   if (valid(3)) rid3 = row_of(3);
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
-  if (valid(0)) issue_tile(0, 0, rid0, slab_cnt(n0));
+  if (valid(0) && !single) issue_tile(0, 0, rid0, slab_cnt(n0));
 
   float4 dg[C];
 #pragma unroll
@@ -212,11 +216,16 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
   for (int i = 0; valid(i); i++) {
     const int n_row = n0;              // entries of the whole row (lambda_use)
     const int n = slab_cnt(n0);        // entries of this CTA's slab
-    const int buf = i & 1, sl = i % 3;
+    const int buf = single ? 0 : (i & 1), sl = i % 3;
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();   // tile i and the metadata of row i+1 have landed; every warp is done with row i-1
+    if (single) {      // one buffer: this row's tile is fetched now (its metadata landed a row ago), other CTAs cover the wait
+      issue_tile(0, sl, rid0, n);
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncthreads();
+    }
     // ---- prefetch (nothing here waits on memory) ----
-    if (valid(i + 1)) issue_tile(buf ^ 1, (i + 1) % 3, rid1, slab_cnt(n1));
+    if (valid(i + 1) && !single) issue_tile(buf ^ 1, (i + 1) % 3, rid1, slab_cnt(n1));
     if (valid(i + 2)) issue_meta((i + 2) % 3, p2 + slab_lo(n2), slab_cnt(n2));
     int p3 = 0, p3e = 0, rid4 = -1;
     if (valid(i + 3)) { p3 = ld_pinned_i32(P.ptr + rid3); p3e = ld_pinned_i32(P.ptr + rid3 + 1); }

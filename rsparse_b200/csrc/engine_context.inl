@@ -45,6 +45,8 @@ struct CscDev {
     int lo = 0, hi = 0;       // rows with lo <= nnz <= hi
     int cap = 0, warps = 0;   // tile kernel launch shape (0: not a tile class)
     int cluster = 1;          // CTAs per thread-block cluster (rows of up to cluster * cap entries)
+    int nbuf = 2;             // tile buffers per CTA
+    bool stream = false;      // this range of row lengths goes to the streaming kernel (a cluster size switched off)
     int count = 0;
     DevBuf list;              // ascending row ids (stable compaction => deterministic launch order)
   };

@@ -74,10 +74,10 @@ static int launch_cg_generic(Ctx& c, const SolveParams<T>& P, int n_work, int* g
 // Lists come from stable compactions (cub::DeviceSelect::If over a counting iterator): ascending row ids, so the
 // launch order, hence the loss summation order, is the same on every run.
 static int tile_kpad(int k) { return k <= 16 ? 16 : k <= 32 ? 32 : k <= 64 ? 64 : k <= 128 ? 128 : 256; }
-static int tile_cap_for(int kpad, int warps, size_t budget, bool full_g) {
+static int tile_cap_for(int kpad, int warps, size_t budget, bool full_g, int nbuf) {
   int cap = 0;
   for (int cnd = 4; cnd <= 8192; cnd += 4) {
-    const TileCgLayout L{kpad, cnd, warps, full_g ? 1 : 0};
+    const TileCgLayout L{kpad, cnd, warps, full_g ? 1 : 0, nbuf};
     if (L.bytes() > budget) break;
     cap = cnd;
   }
@@ -85,7 +85,10 @@ static int tile_cap_for(int kpad, int warps, size_t budget, bool full_g) {
 }
 template <typename T>
 static int plan_rows(Ctx& c, CscDev<T>& A, int k, bool resident_ok, bool full_g) {
-  const int key = k * 4 + (resident_ok ? 1 : 0) + (full_g ? 2 : 0);
+  const char* es0 = getenv("B200ALS_TILE_SINGLE");
+  const char* ec0 = getenv("B200ALS_TILE_CLUSTER");
+  const char* ec1 = getenv("B200ALS_TILE_CLUSTER_MIN");
+  const int key = ((k * 8 + (resident_ok ? 1 : 0) + (full_g ? 2 : 0) + ((es0 && es0[0] == '1') ? 4 : 0)) * 16 + (ec0 ? atoi(ec0) : 0)) * 16 + (ec1 ? atoi(ec1) : 0);
   if (A.plan_key == key) return B200ALS_OK;
   using RC = typename CscDev<T>::RowClass;
   const int kpad = tile_kpad(k);
@@ -93,9 +96,16 @@ static int plan_rows(Ctx& c, CscDev<T>& A, int k, bool resident_ok, bool full_g)
   if (const char* e = getenv("B200ALS_TILE_WARPS_L")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16) warpsL = v; }
   const size_t sm_bytes = c.smem_optin + 1024;   // per-SM shared memory (the opt-in per-block limit + the 1 KB reserve)
   // {warps per CTA, CTAs per SM, CTAs per cluster}: three single-CTA classes, then rows split over clusters of 2 / 4 / 8 CTAs
-  const int shape[6][3] = {{4, 4, 1}, {8, 2, 1}, {warpsL, 1, 1}, {16, 1, 2}, {16, 1, 4}, {16, 1, 8}};
+  // B200ALS_TILE_SINGLE=1 (experiment): the 4- and 2-CTA/SM classes use ONE tile buffer (twice the rows per class, fewer
+  // warps repeating the CG algebra for a given row length; the other CTAs of the SM cover a row's load)
+  const char* es = getenv("B200ALS_TILE_SINGLE");
+  const int nb12 = (es && es[0] == '1') ? 1 : 2;
+  const int shape[6][4] = {{4, 4, 1, nb12}, {8, 2, 1, nb12}, {warpsL, 1, 1, 2}, {16, 1, 2, 2}, {16, 1, 4, 2}, {16, 1, 8, 2}};
   int max_cluster = 8;   // B200ALS_TILE_CLUSTER = 1 | 2 | 4 | 8: largest cluster used (1: longer rows go to the streaming kernel)
   if (const char* e = getenv("B200ALS_TILE_CLUSTER")) max_cluster = std::max(1, atoi(e));
+  int min_cluster = 2;   // B200ALS_TILE_CLUSTER_MIN = 2 | 4 | 8: smallest cluster used (rows between one CTA's capacity and
+                         // min_cluster / 2 times it go to the streaming kernel)
+  if (const char* e = getenv("B200ALS_TILE_CLUSTER_MIN")) min_cluster = std::max(2, atoi(e));
   int lo = 1;
   RC& R = A.cls[CscDev<T>::kClsResident];
   R.lo = 1; R.hi = resident_ok ? kResMaxN : 0; R.cap = 0; R.warps = 0;
@@ -104,10 +114,14 @@ static int plan_rows(Ctx& c, CscDev<T>& A, int k, bool resident_ok, bool full_g)
     RC& C = A.cls[CscDev<T>::kClsTile0 + t];
     C.warps = shape[t][0];
     C.cluster = shape[t][2];
-    C.cap = tile_cap_for(kpad, C.warps, sm_bytes / shape[t][1] - 1024, full_g);
+    C.nbuf = shape[t][3];
+    C.cap = tile_cap_for(kpad, C.warps, sm_bytes / shape[t][1] - 1024, full_g, C.nbuf);
     C.lo = lo;
     // a cluster of CL CTAs holds CL slabs of ceil(n / CL) <= cap entries each
-    C.hi = (C.cluster <= max_cluster) ? std::max(lo - 1, C.cap * C.cluster) : lo - 1;
+    // a cluster size below B200ALS_TILE_CLUSTER_MIN keeps its range of row lengths but hands it to the streaming kernel
+    C.stream = (C.cluster > 1 && C.cluster < min_cluster && C.cluster <= max_cluster);
+    const bool enabled = (C.cluster == 1) || (C.cluster <= max_cluster);
+    C.hi = enabled ? std::max(lo - 1, C.cap * C.cluster) : lo - 1;
     lo = C.hi + 1;
   }
   RC& Lg = A.cls[CscDev<T>::kClsLong];
@@ -147,7 +161,7 @@ static int plan_rows(Ctx& c, CscDev<T>& A, int k, bool resident_ok, bool full_g)
 // launches als_cg_tile_kernel for one length class; *grid_out = CTAs launched (loss partials to sum)
 static int launch_cg_tile(Ctx& c, TileCgParams P, int warps, int cluster, bool full_g, int* grid_out) {
   const int kpad = tile_kpad(P.k);
-  const TileCgLayout L{kpad, P.cap, warps, full_g ? 1 : 0};
+  const TileCgLayout L{kpad, P.cap, warps, full_g ? 1 : 0, P.nbuf};
   const size_t smem = L.bytes();
   if (smem > c.smem_optin) return fail(B200ALS_EUNSUPPORTED, "tile kernel: row class does not fit shared memory");
   int per_sm = 1, grid = 1;
@@ -361,7 +375,7 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
     const bool resident_ok = (k == kResK) && (o.kernel != 10);
     const bool full_g = (o.feedback == B200ALS_IMPLICIT) && !diag;
     TRY(plan_rows(c, A, k, resident_ok, full_g));
-    if (sub_range && (A.plan_single < 0 || A.plan_single == CD::kClsLong))
+    if (sub_range && (A.plan_single < 0 || A.plan_single == CD::kClsLong || A.cls[A.plan_single].stream))
       return fail(B200ALS_EINVAL, "row sub-ranges need a block whose rows all fall into one length class");
     if (A.plan_empty > 0) {
       zero_empty_rows_kernel<T><<<(unsigned)(((long long)A.n_cols * k + 255) / 256), 256, 0, c.stream>>>(P.ptr, A.n_cols, k, Y);
@@ -412,6 +426,11 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
       const int q = CD::kClsTile0 + t;
       const typename CD::RowClass& TC = A.cls[q];
       if (TC.count == 0) continue;
+      if (TC.stream) {
+        if (diag && !G) P.diag = (const T*)diag;
+        TRY(run_generic_cg(TC.list.i32(), TC.count));
+        continue;
+      }
       TileCgParams TP;
       TP.ptr = P.ptr;
       TP.idx = P.idx;
@@ -430,6 +449,7 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
       TP.ptr_base = 0;
       TP.row_begin = sub_range ? o.row_begin : 0;
       TP.cap = TC.cap;
+      TP.nbuf = TC.nbuf;
       TP.loss_partials = P.loss_partials;
       int grid = 0;
       TRY(launch_cg_tile(c, TP, TC.warps, TC.cluster, full_g, &grid));

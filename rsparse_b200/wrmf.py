@@ -306,6 +306,10 @@ class WRMF:
             comp = s.get_factors(L.ITEMS)
             self._U = s.get_factors(L.USERS)
             res, _ = s.transform()
+            if biased and self._feedback == "implicit" and not self._with_user_item_bias and len(self.global_bias_base):
+                # what the last user half-iteration left in self$global_bias_base (wrmf_implicit.hpp:111-112): the session kept
+                # it on the device; transform() reuses it (initialize_bias_base = FALSE, R/model_WRMF.R:130)
+                self.global_bias_base[:] = (-self.global_bias * comp.astype(np.float64).sum(axis=0)).astype(self._dt)
         finally:
             s.close()
         self._set_components(comp)
