@@ -266,10 +266,11 @@ int b200als_create_synthetic(b200als_session** out, int32_t n_user_local, int64_
 int b200als_set_bias(b200als_session* s, int with_user_item_bias, double global_bias);
 
 /* Which kernel took how many rows in the last CG half-iteration of orientation `which` (bench.py reports it):
- * counts[0] register-resident kernel, [1..3] shared-memory tile kernel (4 / 2 / 1 CTAs per SM), [4..6] the same kernel
- * on thread-block clusters of 2 / 4 / 8 CTAs, [7] streaming kernel, [8] empty rows; caps[0..7] = longest row each class
- * takes.  nnz_local = entries of the local block. */
-int b200als_row_plan(b200als_session* s, int which, int32_t counts[9], int32_t caps[8], int64_t* nnz_local);
+ * counts[0] register-resident kernel; [1..4] shared-memory tile kernel -- 4 warps x 4 CTAs/SM double- / single-buffered,
+ * 8 warps x 2 CTAs/SM single-buffered, 16 warps x 1 CTA/SM double-buffered; [5..7] the same kernel on thread-block clusters
+ * of 2 / 4 / 8 CTAs (opt-in); [8] long rows (rank 128: per-row Gram on tcgen05, als_cg_gram_kernel; otherwise the
+ * streaming kernel); [9] empty rows.  caps[0..8] = longest row each class takes.  nnz_local = entries of the local block. */
+int b200als_row_plan(b200als_session* s, int which, int32_t counts[10], int32_t caps[9], int64_t* nnz_local);
 
 /* Skewed synthetic data for the robustness points of bench.py: col_dist 0 = one id per equal-width stratum
  * (as above), 1 = Zipf(1.0)-like popularity (ids log-uniform over [0, n_item), made distinct and ascending per row);

@@ -304,8 +304,8 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
           float4 g[C];
 #pragma unroll
           for (int c = 0; c < C; c++) g[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-          const int U = W * RPW;
-          for (int j = w * RPW + gi; j < k; j += U) {
+          const int U = CL * W * RPW;   // the rows of XtX are split over every (CTA of the cluster, warp, lane group)
+          for (int j = (crank * W + w) * RPW + gi; j < k; j += U) {
             const float vj = vecw[j];
 #pragma unroll
             for (int c = 0; c < C; c++)

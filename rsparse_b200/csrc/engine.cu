@@ -26,6 +26,7 @@
 #include "als_generic.cuh"
 #include "als_resident.cuh"
 #include "als_cg_tile.cuh"
+#include "als_cg_gram.cuh"
 #include "eig.cuh"
 #include "gram.cuh"
 #include "gram_tc.cuh"

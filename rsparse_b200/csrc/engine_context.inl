@@ -50,9 +50,12 @@ struct CscDev {
     int count = 0;
     DevBuf list;              // ascending row ids (stable compaction => deterministic launch order)
   };
-  static constexpr int kClsResident = 0, kClsTile0 = 1, kNumTile = 6, kClsLong = 7, kNumCls = 8;   // tile classes: 4 / 2 / 1 CTAs per SM, clusters of 2 / 4 / 8
+  // tile classes: 4 warps x 4 CTAs/SM double- / single-buffered, 8 warps x 2 CTAs/SM single-buffered, 16 warps x 1 CTA/SM
+  // double-buffered, then thread-block clusters of 2 / 4 / 8 CTAs
+  static constexpr int kClsResident = 0, kClsTile0 = 1, kNumTile = 7, kClsLong = 8, kNumCls = 9;
   RowClass cls[kNumCls];
-  int plan_key = -1;          // rank * 2 + resident_eligible the plan was built for
+  int plan_key = -1;          // 0: a plan exists (built for plan_sig), -1: none
+  int plan_sig[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int plan_empty = 0;
   int plan_single = -1;       // >= 0: every row of the block lies in this one class (chunked solves allowed)
 };

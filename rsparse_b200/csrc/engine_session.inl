@@ -561,7 +561,8 @@ static int gather_ranges(b200als_session* s, int which) {
   // chunked solves (exchange overlapped with the solve) need every row of the block in ONE length class of the CG path
   const bool cg_fast = (s->k % 4 == 0) && (s->k <= 256);
   if (cg_fast) TRY(plan_rows(c, s->csc[which], s->k, s->k == kResK && s->opt.kernel != 10, false));
-  const bool one_class = cg_fast && s->csc[which].plan_single >= 0 && s->csc[which].plan_single != CscDev<float>::kClsLong &&
+  const bool one_class = cg_fast && s->csc[which].plan_single >= 0 &&
+                         (s->csc[which].plan_single != CscDev<float>::kClsLong || gram_rows_enabled(s->k)) &&
                          !s->csc[which].cls[s->csc[which].plan_single].stream;
   std::vector<int32_t> ranges(3 * g_comm.world);
   DevBuf d;
@@ -912,14 +913,14 @@ extern "C" int b200als_set_bias(b200als_session* s, int with_user_item_bias, dou
   return B200ALS_OK;
 }
 
-extern "C" int b200als_row_plan(b200als_session* s, int which, int32_t counts[9], int32_t caps[8], int64_t* nnz_local) {
+extern "C" int b200als_row_plan(b200als_session* s, int which, int32_t counts[10], int32_t caps[9], int64_t* nnz_local) {
   if (!s || which < 0 || which > 1 || !s->has[which]) return fail(B200ALS_EINVAL, "orientation not present");
   const CscDev<float>& A = s->csc[which];
   for (int q = 0; q < CscDev<float>::kNumCls; q++) {
     if (counts) counts[q] = (A.plan_key >= 0) ? A.cls[q].count : 0;
     if (caps) caps[q] = (A.plan_key >= 0) ? A.cls[q].hi : 0;
   }
-  if (counts) counts[8] = (A.plan_key >= 0) ? A.plan_empty : 0;
+  if (counts) counts[9] = (A.plan_key >= 0) ? A.plan_empty : 0;
   if (nnz_local) *nnz_local = A.nnz;
   return B200ALS_OK;
 }

@@ -73,6 +73,14 @@ static int launch_cg_generic(Ctx& c, const SolveParams<T>& P, int n_work, int* g
 // that 4, 2 or 1 CTAs of als_cg_tile_kernel share an SM / longer rows (streaming kernel) / empty rows (zeroed).
 // Lists come from stable compactions (cub::DeviceSelect::If over a counting iterator): ascending row ids, so the
 // launch order, hence the loss summation order, is the same on every run.
+// rank 128: rows beyond the single-CTA tile classes are solved by als_cg_gram_kernel (per-row Gram on tcgen05 + CG on the
+// explicit 128 x 128 system) instead of clusters / the streaming kernel.  B200ALS_GRAM_ROWS=0 switches it off,
+// B200ALS_GRAM_ROWS_MIN=n lowers the row length from which it takes over (A/B runs).
+static bool gram_rows_enabled(int k) {
+  if (k != kTcK) return false;
+  const char* e = getenv("B200ALS_GRAM_ROWS");
+  return !(e && e[0] == '0');
+}
 static int tile_kpad(int k) { return k <= 16 ? 16 : k <= 32 ? 32 : k <= 64 ? 64 : k <= 128 ? 128 : 256; }
 static int tile_cap_for(int kpad, int warps, size_t budget, bool full_g, int nbuf) {
   int cap = 0;
@@ -85,24 +93,28 @@ static int tile_cap_for(int kpad, int warps, size_t budget, bool full_g, int nbu
 }
 template <typename T>
 static int plan_rows(Ctx& c, CscDev<T>& A, int k, bool resident_ok, bool full_g) {
-  const char* es0 = getenv("B200ALS_TILE_SINGLE");
-  const char* ec0 = getenv("B200ALS_TILE_CLUSTER");
-  const char* ec1 = getenv("B200ALS_TILE_CLUSTER_MIN");
-  const int key = ((k * 8 + (resident_ok ? 1 : 0) + (full_g ? 2 : 0) + ((es0 && es0[0] == '1') ? 4 : 0)) * 16 + (ec0 ? atoi(ec0) : 0)) * 16 + (ec1 ? atoi(ec1) : 0);
-  if (A.plan_key == key) return B200ALS_OK;
+  // the plan depends on the rank, the mode and the A/B switches of the environment: cached until any of them changes
+  auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+  const int sig[8] = {k, resident_ok ? 1 : 0, full_g ? 1 : 0, env_int("B200ALS_TILE_SINGLE", 0), env_int("B200ALS_TILE_CLUSTER", -1),
+                      env_int("B200ALS_TILE_CLUSTER_MIN", -1), env_int("B200ALS_GRAM_ROWS", -1), env_int("B200ALS_GRAM_ROWS_MIN", -1)};
+  if (A.plan_key == 0 && std::memcmp(sig, A.plan_sig, sizeof(sig)) == 0) return B200ALS_OK;
   using RC = typename CscDev<T>::RowClass;
   const int kpad = tile_kpad(k);
   int warpsL = 16;   // one CTA per SM: 16 warps (two-stage cross-warp sum); B200ALS_TILE_WARPS_L = 4 | 8 | 16 for A/B runs
   if (const char* e = getenv("B200ALS_TILE_WARPS_L")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16) warpsL = v; }
   const size_t sm_bytes = c.smem_optin + 1024;   // per-SM shared memory (the opt-in per-block limit + the 1 KB reserve)
-  // {warps per CTA, CTAs per SM, CTAs per cluster}: three single-CTA classes, then rows split over clusters of 2 / 4 / 8 CTAs
-  // B200ALS_TILE_SINGLE=1 (experiment): the 4- and 2-CTA/SM classes use ONE tile buffer (twice the rows per class, fewer
-  // warps repeating the CG algebra for a given row length; the other CTAs of the SM cover a row's load)
-  const char* es = getenv("B200ALS_TILE_SINGLE");
-  const int nb12 = (es && es[0] == '1') ? 1 : 2;
-  const int shape[6][4] = {{4, 4, 1, nb12}, {8, 2, 1, nb12}, {warpsL, 1, 1, 2}, {16, 1, 2, 2}, {16, 1, 4, 2}, {16, 1, 8, 2}};
-  int max_cluster = 8;   // B200ALS_TILE_CLUSTER = 1 | 2 | 4 | 8: largest cluster used (1: longer rows go to the streaming kernel)
+  // {warps per CTA, CTAs per SM, CTAs per cluster, tile buffers}.  Measured (profiles/r2/tile_ab.txt): every warp of a
+  // CTA repeats the CG vector algebra, so FEW warps per CTA and MANY CTAs per SM win -- rank 128, rows of 80: 4 warps x 4
+  // CTAs with ONE tile buffer (the other CTAs cover a row's load) 17.4 ms per 1 M rows, 8 warps x 2 CTAs double-buffered
+  // 24.4 ms; where both fit, the double-buffered form of the same shape is 4 % faster.  Hence, by increasing row length:
+  // 4 warps double-buffered, 4 warps single, 8 warps single, 16 warps double (one CTA per SM needs the warps).
+  // Clusters: off unless B200ALS_TILE_CLUSTER >= 2 -- on the heavy-tailed robustness point the streaming kernel beat them
+  // (32.8 vs 40.6 ms); on 1 M uniform rows of 800 entries they won by 8 % (387 vs 421 ms).
+  const int shape[7][4] = {{4, 4, 1, 2}, {4, 4, 1, 1}, {8, 2, 1, 1}, {warpsL, 1, 1, 2}, {16, 1, 2, 2}, {16, 1, 4, 2}, {16, 1, 8, 2}};
+  int max_cluster = 1;   // B200ALS_TILE_CLUSTER = 1 | 2 | 4 | 8: largest cluster used (1: longer rows go to the long-row kernels)
   if (const char* e = getenv("B200ALS_TILE_CLUSTER")) max_cluster = std::max(1, atoi(e));
+  const bool gram_rows = gram_rows_enabled(k);
+  if (gram_rows) max_cluster = 1;   // rank 128: long rows go to the tensor-core Gram kernel, not to clusters
   int min_cluster = 2;   // B200ALS_TILE_CLUSTER_MIN = 2 | 4 | 8: smallest cluster used (rows between one CTA's capacity and
                          // min_cluster / 2 times it go to the streaming kernel)
   if (const char* e = getenv("B200ALS_TILE_CLUSTER_MIN")) min_cluster = std::max(2, atoi(e));
@@ -123,6 +135,18 @@ static int plan_rows(Ctx& c, CscDev<T>& A, int k, bool resident_ok, bool full_g)
     const bool enabled = (C.cluster == 1) || (C.cluster <= max_cluster);
     C.hi = enabled ? std::max(lo - 1, C.cap * C.cluster) : lo - 1;
     lo = C.hi + 1;
+  }
+  if (gram_rows) {
+    if (const char* e = getenv("B200ALS_GRAM_ROWS_MIN")) {
+      const int v = std::max(R.hi + 1, atoi(e));
+      for (int t = 0; t < CscDev<T>::kNumTile; t++) {
+        RC& C = A.cls[CscDev<T>::kClsTile0 + t];
+        if (C.hi < C.lo) continue;
+        if (C.lo >= v) C.hi = C.lo - 1;          // class switched off
+        else if (C.hi >= v) C.hi = v - 1;
+      }
+      lo = std::min(lo, v);
+    }
   }
   RC& Lg = A.cls[CscDev<T>::kClsLong];
   Lg.lo = lo; Lg.hi = std::numeric_limits<int>::max(); Lg.cap = 0; Lg.warps = 0;
@@ -154,7 +178,8 @@ static int plan_rows(Ctx& c, CscDev<T>& A, int k, bool resident_ok, bool full_g)
     if (A.cls[q].count == A.n_cols && A.n_cols > 0) A.plan_single = q;
   }
   A.plan_empty = A.n_cols - total;
-  A.plan_key = key;
+  std::memcpy(A.plan_sig, sig, sizeof(sig));
+  A.plan_key = 0;
   return B200ALS_OK;
 }
 
@@ -214,6 +239,19 @@ static int launch_cg_tile(Ctx& c, TileCgParams P, int warps, int cluster, bool f
     default: B200ALS_TILE_CASE(32, 2); break;
   }
 #undef B200ALS_TILE_CASE
+  LAUNCHED(); CU(cudaGetLastError());
+  *grid_out = grid;
+  return B200ALS_OK;
+}
+
+// launches als_cg_gram_kernel (rank 128, long rows); two CTAs per SM (the occupancy query does not see tensor memory)
+static int launch_cg_gram(Ctx& c, TileCgParams P, int* grid_out) {
+  const size_t smem = sizeof(GramCgSmem);
+  CU(cudaFuncSetAttribute(als_cg_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 2;
+  if (const char* e = getenv("B200ALS_GRAM_ROWS_PER_SM")) per_sm = std::max(1, std::min(2, atoi(e)));
+  const int grid = std::min(c.sm_count * per_sm, std::max(1, P.n_list));
+  als_cg_gram_kernel<<<grid, kGcThreads, smem, c.stream>>>(P);
   LAUNCHED(); CU(cudaGetLastError());
   *grid_out = grid;
   return B200ALS_OK;
@@ -375,7 +413,8 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
     const bool resident_ok = (k == kResK) && (o.kernel != 10);
     const bool full_g = (o.feedback == B200ALS_IMPLICIT) && !diag;
     TRY(plan_rows(c, A, k, resident_ok, full_g));
-    if (sub_range && (A.plan_single < 0 || A.plan_single == CD::kClsLong || A.cls[A.plan_single].stream))
+    const bool gram_rows = gram_rows_enabled(k);
+    if (sub_range && (A.plan_single < 0 || (A.plan_single == CD::kClsLong && !gram_rows) || A.cls[A.plan_single].stream))
       return fail(B200ALS_EINVAL, "row sub-ranges need a block whose rows all fall into one length class");
     if (A.plan_empty > 0) {
       zero_empty_rows_kernel<T><<<(unsigned)(((long long)A.n_cols * k + 255) / 256), 256, 0, c.stream>>>(P.ptr, A.n_cols, k, Y);
@@ -457,7 +496,32 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
       LAUNCHED(); CU(cudaGetLastError());
     }
     const typename CD::RowClass& LC = A.cls[CD::kClsLong];
-    if (LC.count > 0) {
+    if (LC.count > 0 && gram_rows) {
+      TileCgParams TP;
+      TP.ptr = P.ptr;
+      TP.idx = P.idx;
+      TP.val = (const float*)P.val;
+      TP.X = (const float*)X;
+      TP.Y = (float*)Y;
+      TP.diag = diag;
+      TP.G = (const float*)G;
+      TP.k = k;
+      TP.feedback = o.feedback;
+      TP.cg_steps = o.cg_steps;
+      TP.dynamic_lambda = o.dynamic_lambda;
+      TP.lambda = (float)o.lambda;
+      TP.row_list = (A.plan_single == CD::kClsLong) ? nullptr : LC.list.i32();
+      TP.n_list = sub_range ? n_rows_here : LC.count;
+      TP.ptr_base = 0;
+      TP.row_begin = sub_range ? o.row_begin : 0;
+      TP.cap = 0;
+      TP.nbuf = 1;
+      TP.loss_partials = P.loss_partials;
+      int grid = 0;
+      TRY(launch_cg_gram(c, TP, &grid));
+      sum_partials_kernel<<<1, 32, 0, c.stream>>>(P.loss_partials, grid, c.loss_acc.f64(), 1);
+      LAUNCHED(); CU(cudaGetLastError());
+    } else if (LC.count > 0) {
       if (diag && !G) P.diag = (const T*)diag;
       TRY(run_generic_cg(LC.list.i32(), LC.count));
     }

@@ -143,12 +143,14 @@ class Session:
 
     def row_plan(self, which):
         """Rows per kernel of the last CG half-iteration of `which` and the local number of entries."""
-        counts = np.zeros(9, np.int32)
-        caps = np.zeros(8, np.int32)
+        counts = np.zeros(10, np.int32)
+        caps = np.zeros(9, np.int32)
         nnz = C.c_int64(0)
         L.check(L.lib().b200als_row_plan(self._h, which, L.vp(counts), L.vp(caps), C.byref(nnz)))
-        names = ["resident", "tile_4cta", "tile_2cta", "tile_1cta", "cluster2", "cluster4", "cluster8", "streaming", "empty"]
-        return {"rows": dict(zip(names, [int(v) for v in counts])), "longest_row": dict(zip(names[:8], [int(v) for v in caps])),
+        # "long": rows beyond every tile / cluster class -- als_cg_gram_kernel at rank 128, the streaming kernel otherwise
+        names = ["resident", "tile_w4_double", "tile_w4_single", "tile_w8_single", "tile_w16_double", "cluster2", "cluster4",
+                 "cluster8", "long", "empty"]
+        return {"rows": dict(zip(names, [int(v) for v in counts])), "longest_row": dict(zip(names[:9], [int(v) for v in caps])),
                 "nnz_local": int(nnz.value)}
 
     def last_timing(self):

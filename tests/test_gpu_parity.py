@@ -115,11 +115,18 @@ def test_tile_cg_kernel_in_session(name, kernel, cases, golden_half):
     assert np.all(Y[np.diff(c["ptr"]) == 0] == 0)
 
 
-@pytest.mark.parametrize("k,feedback", [(128, "implicit"), (128, "explicit"), (256, "implicit"), (64, "implicit")])
-def test_cluster_tile_kernel_long_rows(k, feedback):
-    """Rows too long for one CTA's tile buffers are solved by thread-block clusters of 2 / 4 / 8 CTAs (slabs of the tile
-    in each CTA's shared memory, per-sweep sums over distributed shared memory); still longer rows by the streaming
-    kernel.  Ragged rows of 1 ... 2399 entries against the fp64 oracle, eigenbasis forced for implicit feedback."""
+@pytest.mark.parametrize("k,feedback,gram_rows", [(128, "implicit", "1"), (128, "explicit", "1"), (128, "implicit", "0"),
+                                                  (128, "explicit", "0"), (256, "implicit", "1"), (64, "implicit", "1")])
+@pytest.mark.parametrize("kernel", [10, 2])
+def test_long_rows_gram_and_cluster_kernels(k, feedback, gram_rows, kernel, monkeypatch):
+    """Rows too long for one CTA's tile buffers.  Rank 128: als_cg_gram_kernel -- the row's 128 x 128 system is formed on
+    tcgen05 in one pass over the tile (3xTF32), then the reference's CG steps run on it.  Other ranks, or with
+    B200ALS_GRAM_ROWS=0: thread-block clusters of 2 / 4 / 8 CTAs (slabs of the tile in each CTA's shared memory, per-sweep
+    sums over distributed shared memory), still longer rows by the streaming kernel.  Ragged rows of 1 ... 2399 entries
+    against the fp64 oracle; kernel = 10: eigenbasis forced for implicit feedback, kernel = 2: full XtX (rank 128)."""
+    if kernel == 2 and k != 128:
+        pytest.skip("kernel = 2 is a rank-128 option")
+    monkeypatch.setenv("B200ALS_GRAM_ROWS", gram_rows)
     n_rows, n_src, lam = 40, 3000, 0.1
     ptr, idx, val = wc.det_csr(n_rows, n_src, 1200, 77 + k, ragged=True, explicit=(feedback == "explicit"))
     X = np.ascontiguousarray(wc.det_factors(n_src, k, 300 + k, 0.1) * (1.0 + np.arange(k, dtype=np.float32)) ** -0.5)
@@ -130,14 +137,17 @@ def test_cluster_tile_kernel_long_rows(k, feedback):
     else:
         cnt = np.bincount(idx, minlength=n_src).astype(np.float64)
         lo = oracle.als_explicit(ptr, idx, val, X64, Yo, cnt, lam, wc.CG, 3, True, 2)
-    s = Session(None, (ptr, idx, val), n_rows, n_src, k, feedback, wc.CG, 3, True, lam, 10)
+    s = Session(None, (ptr, idx, val), n_rows, n_src, k, feedback, wc.CG, 3, True, lam, kernel)
     s.set_factors(L.ITEMS, X)
     s.set_factors(L.USERS, Y0)
     loss = s.half_iteration(L.USERS)
     Y = s.get_factors(L.USERS)
     plan = s.row_plan(L.USERS)["rows"]
     s.close()
-    assert plan["cluster2"] + plan["cluster4"] + plan["cluster8"] > 0, plan
+    if k == 128 and gram_rows == "1":
+        assert plan["long"] > 0 and plan["cluster2"] + plan["cluster4"] + plan["cluster8"] == 0, plan
+    else:
+        assert plan["cluster2"] + plan["cluster4"] + plan["cluster8"] > 0, plan
     assert relF(Y, Yo) < TOL_F32, (relF(Y, Yo), plan)
     assert abs(loss - lo) <= TOL_F32 * abs(lo)
 
