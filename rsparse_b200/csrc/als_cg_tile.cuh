@@ -62,17 +62,18 @@ constexpr int kTileBatch = 4;   // row steps per reduction batch
 // shared-memory carve-up (bytes), shared by host and device
 struct TileCgLayout {
   int kpad, cap, warps, full_g;
-  int nbuf = 2;   // tile buffers: 2 = the next row's tile lands while this one computes; 1 = single buffer (twice the capacity
-                  // per byte of shared memory; the load of a row is then hidden by the OTHER CTAs of the SM)
+  int nbuf = 2;      // tile buffers: 2 = the next row's tile lands while this one computes; 1 = single buffer (twice the capacity
+                     // per byte of shared memory; the load of a row is then hidden by the OTHER CTAs of the SM)
+  int cluster = 0;   // 1: the kernel runs on thread-block clusters (needs the per-CTA partial-sum buffer its peers read)
   __host__ __device__ size_t tile_off(int b) const { return (size_t)b * cap * kpad * 4; }
   __host__ __device__ size_t ybuf_off(int b) const { return tile_off(nbuf) + (size_t)b * kpad * 4; }
   // cross-warp exchange: double-buffered per sweep with <= 4 warps (one barrier per sweep); a single buffer with more
   // warps (the two-stage sum has a second barrier per sweep, which also separates consecutive sweeps)
   __host__ __device__ int n_vbuf() const { return warps > 4 ? 1 : 2; }
-  __host__ __device__ size_t vbuf_off(int b) const { return ybuf_off(2) + (size_t)b * warps * kpad * 4; }
-  __host__ __device__ size_t sum_off() const { return vbuf_off(n_vbuf()); }                                    // [2][kpad] two-stage cross-warp sum
-  __host__ __device__ size_t csum_off() const { return sum_off() + (size_t)2 * kpad * 4; }              // [2][kpad] this CTA's partial, read by its cluster peers
-  __host__ __device__ size_t vec_off() const { return csum_off() + (size_t)2 * kpad * 4; }              // [warps][kpad], kFullG only
+  __host__ __device__ size_t vbuf_off(int b) const { return ybuf_off(nbuf) + (size_t)b * warps * kpad * 4; }
+  __host__ __device__ size_t sum_off() const { return vbuf_off(n_vbuf()); }                              // [2][kpad] two-stage cross-warp sum (> 4 warps)
+  __host__ __device__ size_t csum_off() const { return sum_off() + (warps > 4 ? (size_t)2 * kpad * 4 : 0); }   // [2][kpad] this CTA's partial, read by its cluster peers
+  __host__ __device__ size_t vec_off() const { return csum_off() + (cluster ? (size_t)2 * kpad * 4 : 0); }     // [warps][kpad], kFullG only
   __host__ __device__ size_t idx_off(int s) const { return vec_off() + (full_g ? (size_t)warps * kpad * 4 : 0) + (size_t)s * cap * 4; }
   __host__ __device__ size_t val_off(int s) const { return idx_off(3) + (size_t)s * cap * 4; }
   __host__ __device__ size_t ubuf_off(int b) const { return val_off(3) + (size_t)b * cap * 4; }
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
   const int gi = lane / LPR, gl = lane % LPR;    // lane group within the warp, lane within the group
   const int slot = gl >> SLOT_SHIFT;             // which of a batch's 4 row steps this lane owns after the reduction
   const int k = P.k;
-  const TileCgLayout L{KPAD, P.cap, W, kFullG ? 1 : 0, P.nbuf};
+  const TileCgLayout L{KPAD, P.cap, W, kFullG ? 1 : 0, P.nbuf, kCluster ? 1 : 0};
   const bool single = (P.nbuf == 1);
   auto tile_of = [&](int b) { return reinterpret_cast<float*>(smem_raw + L.tile_off(b)); };
   auto ybuf_of = [&](int b) { return reinterpret_cast<float*>(smem_raw + L.ybuf_off(b)); };

@@ -82,10 +82,10 @@ static bool gram_rows_enabled(int k) {
   return !(e && e[0] == '0');
 }
 static int tile_kpad(int k) { return k <= 16 ? 16 : k <= 32 ? 32 : k <= 64 ? 64 : k <= 128 ? 128 : 256; }
-static int tile_cap_for(int kpad, int warps, size_t budget, bool full_g, int nbuf) {
+static int tile_cap_for(int kpad, int warps, size_t budget, bool full_g, int nbuf, int cluster) {
   int cap = 0;
   for (int cnd = 4; cnd <= 8192; cnd += 4) {
-    const TileCgLayout L{kpad, cnd, warps, full_g ? 1 : 0, nbuf};
+    const TileCgLayout L{kpad, cnd, warps, full_g ? 1 : 0, nbuf, cluster > 1 ? 1 : 0};
     if (L.bytes() > budget) break;
     cap = cnd;
   }
@@ -95,13 +95,15 @@ template <typename T>
 static int plan_rows(Ctx& c, CscDev<T>& A, int k, bool resident_ok, bool full_g) {
   // the plan depends on the rank, the mode and the A/B switches of the environment: cached until any of them changes
   auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
-  const int sig[8] = {k, resident_ok ? 1 : 0, full_g ? 1 : 0, env_int("B200ALS_TILE_SINGLE", 0), env_int("B200ALS_TILE_CLUSTER", -1),
+  const int sig[8] = {k, resident_ok ? 1 : 0, full_g ? 1 : 0, env_int("B200ALS_TILE_WARPS_S", 4) * 100 + env_int("B200ALS_TILE_WARPS_M", 4), env_int("B200ALS_TILE_CLUSTER", -1),
                       env_int("B200ALS_TILE_CLUSTER_MIN", -1), env_int("B200ALS_GRAM_ROWS", -1), env_int("B200ALS_GRAM_ROWS_MIN", -1)};
   if (A.plan_key == 0 && std::memcmp(sig, A.plan_sig, sizeof(sig)) == 0) return B200ALS_OK;
   using RC = typename CscDev<T>::RowClass;
   const int kpad = tile_kpad(k);
   int warpsL = 16;   // one CTA per SM: 16 warps (two-stage cross-warp sum); B200ALS_TILE_WARPS_L = 4 | 8 | 16 for A/B runs
   if (const char* e = getenv("B200ALS_TILE_WARPS_L")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16) warpsL = v; }
+  int warpsS = 4, ctasS = 4;   // B200ALS_TILE_WARPS_S = 2 | 4 (A/B): 2 warps per CTA => up to 8 CTAs per SM in the small classes
+  if (const char* e = getenv("B200ALS_TILE_WARPS_S")) { if (atoi(e) == 2) { warpsS = 2; ctasS = 8; } }
   const size_t sm_bytes = c.smem_optin + 1024;   // per-SM shared memory (the opt-in per-block limit + the 1 KB reserve)
   // {warps per CTA, CTAs per SM, CTAs per cluster, tile buffers}.  Measured (profiles/r2/tile_ab.txt): every warp of a
   // CTA repeats the CG vector algebra, so FEW warps per CTA and MANY CTAs per SM win -- rank 128, rows of 80: 4 warps x 4
@@ -110,7 +112,9 @@ static int plan_rows(Ctx& c, CscDev<T>& A, int k, bool resident_ok, bool full_g)
   // 4 warps double-buffered, 4 warps single, 8 warps single, 16 warps double (one CTA per SM needs the warps).
   // Clusters: off unless B200ALS_TILE_CLUSTER >= 2 -- on the heavy-tailed robustness point the streaming kernel beat them
   // (32.8 vs 40.6 ms); on 1 M uniform rows of 800 entries they won by 8 % (387 vs 421 ms).
-  const int shape[7][4] = {{4, 4, 1, 2}, {4, 4, 1, 1}, {8, 2, 1, 1}, {warpsL, 1, 1, 2}, {16, 1, 2, 2}, {16, 1, 4, 2}, {16, 1, 8, 2}};
+  int warpsM = 4;   // B200ALS_TILE_WARPS_M = 4 | 8: warps of the 2-CTA/SM single-buffered class
+  if (const char* e = getenv("B200ALS_TILE_WARPS_M")) { if (atoi(e) == 8) warpsM = 8; }
+  const int shape[7][4] = {{warpsS, ctasS, 1, 2}, {warpsS, ctasS, 1, 1}, {warpsM, 2, 1, 1}, {warpsL, 1, 1, 2}, {16, 1, 2, 2}, {16, 1, 4, 2}, {16, 1, 8, 2}};
   int max_cluster = 1;   // B200ALS_TILE_CLUSTER = 1 | 2 | 4 | 8: largest cluster used (1: longer rows go to the long-row kernels)
   if (const char* e = getenv("B200ALS_TILE_CLUSTER")) max_cluster = std::max(1, atoi(e));
   const bool gram_rows = gram_rows_enabled(k);
@@ -127,7 +131,7 @@ static int plan_rows(Ctx& c, CscDev<T>& A, int k, bool resident_ok, bool full_g)
     C.warps = shape[t][0];
     C.cluster = shape[t][2];
     C.nbuf = shape[t][3];
-    C.cap = tile_cap_for(kpad, C.warps, sm_bytes / shape[t][1] - 1024, full_g, C.nbuf);
+    C.cap = tile_cap_for(kpad, C.warps, sm_bytes / shape[t][1] - 1024, full_g, C.nbuf, C.cluster);
     C.lo = lo;
     // a cluster of CL CTAs holds CL slabs of ceil(n / CL) <= cap entries each
     // a cluster size below B200ALS_TILE_CLUSTER_MIN keeps its range of row lengths but hands it to the streaming kernel
@@ -186,7 +190,7 @@ static int plan_rows(Ctx& c, CscDev<T>& A, int k, bool resident_ok, bool full_g)
 // launches als_cg_tile_kernel for one length class; *grid_out = CTAs launched (loss partials to sum)
 static int launch_cg_tile(Ctx& c, TileCgParams P, int warps, int cluster, bool full_g, int* grid_out) {
   const int kpad = tile_kpad(P.k);
-  const TileCgLayout L{kpad, P.cap, warps, full_g ? 1 : 0, P.nbuf};
+  const TileCgLayout L{kpad, P.cap, warps, full_g ? 1 : 0, P.nbuf, cluster > 1 ? 1 : 0};
   const size_t smem = L.bytes();
   if (smem > c.smem_optin) return fail(B200ALS_EUNSUPPORTED, "tile kernel: row class does not fit shared memory");
   int per_sm = 1, grid = 1;

@@ -26,6 +26,8 @@ run c3_items_gram_1persm "B200ALS_GRAM_ROWS_PER_SM=1" "--workload c3 --half item
 run c3_ragged "X=1" "--workload c3-ragged"
 run c3_k10 "X=1" "--workload c3 --kernel 10"
 run c5slice "X=1" "--workload c5-slice"
+run c5slice_wm8 "B200ALS_TILE_WARPS_M=8" "--workload c5-slice"
+run ragged_small_wm8 "B200ALS_TILE_WARPS_M=8" "--workload c3-ragged-small"
 run c3k64 "X=1" "--workload c3-k64"
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:als_cg_gram -s 1 -c 1 -f -o $OUT/prof_gram_rows \
     python bench.py --workload c3-small --half items --steps 1 --warmup 3 --no-e2e --no-cpu > $OUT/prof_gram_rows.log 2>&1
