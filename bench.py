@@ -362,7 +362,7 @@ def main():
                     "traffic": None, "kernel_ms": solve_ms}
     else:
         rows = plan["rows"]
-        by = {"als_cg_resident_kernel": rows["resident"], "als_cg_tile_kernel": rows["tile_w4_double"] + rows["tile_w4_single"] + rows["tile_w8_single"] + rows["tile_w16_double"],
+        by = {"als_cg_resident_kernel": rows["resident"], "als_cg_tile_kernel": rows["tile_4cta_double"] + rows["tile_4cta_single"] + rows["tile_2cta_single"] + rows["tile_1cta_double"],
               "als_cg_tile_kernel (thread-block clusters)": rows["cluster2"] + rows["cluster4"] + rows["cluster8"],
               ("als_cg_gram_kernel (per-row Gram on tcgen05)" if (k == 128 and os.environ.get("B200ALS_GRAM_ROWS", "1") != "0") else "als_cg_generic_kernel"): rows["long"]}
         if args.kernel == 1:

@@ -95,7 +95,7 @@ template <typename T>
 static int plan_rows(Ctx& c, CscDev<T>& A, int k, bool resident_ok, bool full_g) {
   // the plan depends on the rank, the mode and the A/B switches of the environment: cached until any of them changes
   auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
-  const int sig[8] = {k, resident_ok ? 1 : 0, full_g ? 1 : 0, env_int("B200ALS_TILE_WARPS_S", 4) * 100 + env_int("B200ALS_TILE_WARPS_M", 4), env_int("B200ALS_TILE_CLUSTER", -1),
+  const int sig[8] = {k, resident_ok ? 1 : 0, full_g ? 1 : 0, env_int("B200ALS_TILE_WARPS_S", 4) * 100 + env_int("B200ALS_TILE_WARPS_M", 0), env_int("B200ALS_TILE_CLUSTER", -1),
                       env_int("B200ALS_TILE_CLUSTER_MIN", -1), env_int("B200ALS_GRAM_ROWS", -1), env_int("B200ALS_GRAM_ROWS_MIN", -1)};
   if (A.plan_key == 0 && std::memcmp(sig, A.plan_sig, sizeof(sig)) == 0) return B200ALS_OK;
   using RC = typename CscDev<T>::RowClass;
@@ -109,11 +109,15 @@ static int plan_rows(Ctx& c, CscDev<T>& A, int k, bool resident_ok, bool full_g)
   // CTA repeats the CG vector algebra, so FEW warps per CTA and MANY CTAs per SM win -- rank 128, rows of 80: 4 warps x 4
   // CTAs with ONE tile buffer (the other CTAs cover a row's load) 17.4 ms per 1 M rows, 8 warps x 2 CTAs double-buffered
   // 24.4 ms; where both fit, the double-buffered form of the same shape is 4 % faster.  Hence, by increasing row length:
-  // 4 warps double-buffered, 4 warps single, 8 warps single, 16 warps double (one CTA per SM needs the warps).
+  // 4 warps x 4 CTAs double-buffered, the same single-buffered, 8 (rank 256: 4) warps x 2 CTAs single-buffered, 16 warps x
+  // 1 CTA double-buffered (one CTA per SM needs the warps).
   // Clusters: off unless B200ALS_TILE_CLUSTER >= 2 -- on the heavy-tailed robustness point the streaming kernel beat them
   // (32.8 vs 40.6 ms); on 1 M uniform rows of 800 entries they won by 8 % (387 vs 421 ms).
-  int warpsM = 4;   // B200ALS_TILE_WARPS_M = 4 | 8: warps of the 2-CTA/SM single-buffered class
-  if (const char* e = getenv("B200ALS_TILE_WARPS_M")) { if (atoi(e) == 8) warpsM = 8; }
+  // warps of the 2-CTA/SM single-buffered class: 8, except at rank 256 where only 4 leave room for rows of 100 entries
+  // (measured: C5 slice 360 ms vs 405 ms for the 16-warp 1-CTA class; rank 128 ragged rows 25.3 ms with 8 vs 26.9 ms with 4).
+  // B200ALS_TILE_WARPS_M = 4 | 8 overrides.
+  int warpsM = (kpad == 256) ? 4 : 8;
+  if (const char* e = getenv("B200ALS_TILE_WARPS_M")) { const int v = atoi(e); if (v == 4 || v == 8) warpsM = v; }
   const int shape[7][4] = {{warpsS, ctasS, 1, 2}, {warpsS, ctasS, 1, 1}, {warpsM, 2, 1, 1}, {warpsL, 1, 1, 2}, {16, 1, 2, 2}, {16, 1, 4, 2}, {16, 1, 8, 2}};
   int max_cluster = 1;   // B200ALS_TILE_CLUSTER = 1 | 2 | 4 | 8: largest cluster used (1: longer rows go to the long-row kernels)
   if (const char* e = getenv("B200ALS_TILE_CLUSTER")) max_cluster = std::max(1, atoi(e));

@@ -148,7 +148,7 @@ class Session:
         nnz = C.c_int64(0)
         L.check(L.lib().b200als_row_plan(self._h, which, L.vp(counts), L.vp(caps), C.byref(nnz)))
         # "long": rows beyond every tile / cluster class -- als_cg_gram_kernel at rank 128, the streaming kernel otherwise
-        names = ["resident", "tile_w4_double", "tile_w4_single", "tile_w8_single", "tile_w16_double", "cluster2", "cluster4",
+        names = ["resident", "tile_4cta_double", "tile_4cta_single", "tile_2cta_single", "tile_1cta_double", "cluster2", "cluster4",
                  "cluster8", "long", "empty"]
         return {"rows": dict(zip(names, [int(v) for v in counts])), "longest_row": dict(zip(names[:9], [int(v) for v in caps])),
                 "nnz_local": int(nnz.value)}

@@ -115,18 +115,20 @@ def test_tile_cg_kernel_in_session(name, kernel, cases, golden_half):
     assert np.all(Y[np.diff(c["ptr"]) == 0] == 0)
 
 
-@pytest.mark.parametrize("k,feedback,gram_rows", [(128, "implicit", "1"), (128, "explicit", "1"), (128, "implicit", "0"),
-                                                  (128, "explicit", "0"), (256, "implicit", "1"), (64, "implicit", "1")])
+@pytest.mark.parametrize("k,feedback,gram_rows,clusters", [(128, "implicit", "1", "1"), (128, "explicit", "1", "1"), (128, "implicit", "0", "8"),
+                                                           (128, "explicit", "0", "8"), (256, "implicit", "1", "8"), (64, "implicit", "1", "8"),
+                                                           (128, "implicit", "0", "1"), (256, "implicit", "1", "1")])
 @pytest.mark.parametrize("kernel", [10, 2])
-def test_long_rows_gram_and_cluster_kernels(k, feedback, gram_rows, kernel, monkeypatch):
+def test_long_rows_gram_and_cluster_kernels(k, feedback, gram_rows, clusters, kernel, monkeypatch):
     """Rows too long for one CTA's tile buffers.  Rank 128: als_cg_gram_kernel -- the row's 128 x 128 system is formed on
     tcgen05 in one pass over the tile (3xTF32), then the reference's CG steps run on it.  Other ranks, or with
-    B200ALS_GRAM_ROWS=0: thread-block clusters of 2 / 4 / 8 CTAs (slabs of the tile in each CTA's shared memory, per-sweep
-    sums over distributed shared memory), still longer rows by the streaming kernel.  Ragged rows of 1 ... 2399 entries
+    B200ALS_GRAM_ROWS=0: the streaming kernel, or with B200ALS_TILE_CLUSTER=8 thread-block clusters of 2 / 4 / 8 CTAs (slabs of
+    the tile in each CTA's shared memory, per-sweep sums over distributed shared memory).  Ragged rows of 1 ... 2399 entries
     against the fp64 oracle; kernel = 10: eigenbasis forced for implicit feedback, kernel = 2: full XtX (rank 128)."""
     if kernel == 2 and k != 128:
         pytest.skip("kernel = 2 is a rank-128 option")
     monkeypatch.setenv("B200ALS_GRAM_ROWS", gram_rows)
+    monkeypatch.setenv("B200ALS_TILE_CLUSTER", clusters)      # clusters are opt-in (profiles/r2/tile_ab.txt)
     n_rows, n_src, lam = 40, 3000, 0.1
     ptr, idx, val = wc.det_csr(n_rows, n_src, 1200, 77 + k, ragged=True, explicit=(feedback == "explicit"))
     X = np.ascontiguousarray(wc.det_factors(n_src, k, 300 + k, 0.1) * (1.0 + np.arange(k, dtype=np.float32)) ** -0.5)
@@ -144,10 +146,11 @@ def test_long_rows_gram_and_cluster_kernels(k, feedback, gram_rows, kernel, monk
     Y = s.get_factors(L.USERS)
     plan = s.row_plan(L.USERS)["rows"]
     s.close()
-    if k == 128 and gram_rows == "1":
-        assert plan["long"] > 0 and plan["cluster2"] + plan["cluster4"] + plan["cluster8"] == 0, plan
+    n_clu = plan["cluster2"] + plan["cluster4"] + plan["cluster8"]
+    if (k == 128 and gram_rows == "1") or clusters == "1":
+        assert plan["long"] > 0 and n_clu == 0, plan          # Gram-rows kernel (rank 128) or the streaming kernel
     else:
-        assert plan["cluster2"] + plan["cluster4"] + plan["cluster8"] > 0, plan
+        assert n_clu > 0, plan
     assert relF(Y, Yo) < TOL_F32, (relF(Y, Yo), plan)
     assert abs(loss - lo) <= TOL_F32 * abs(lo)
 
