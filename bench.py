@@ -62,6 +62,7 @@ WORKLOADS = {
     # robustness points: Zipf(1.0)-like item popularity; the same with log-normal row lengths (sigma 1, mean 80)
     "c3-zipf": _wl(10_000_000, 1_000_000, 80, 128, col_dist=1),
     "c3-ragged": _wl(10_000_000, 1_000_000, 80, 128, col_dist=1, len_dist=1),
+    "c3-items-small": _wl(2_000_000, 200_000, 80, 128),              # ncu capture of the item half: 200 k item rows of ~800 entries
     "c3-ragged-small": _wl(1_000_000, 1_000_000, 80, 128, col_dist=1, len_dist=1),
 }
 # side workload "topk": MatrixFactorizationRecommender$predict's top_product

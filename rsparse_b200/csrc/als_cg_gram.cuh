@@ -273,6 +273,11 @@ __global__ void __launch_bounds__(kGcThreads, 2) als_cg_gram_kernel(TileCgParams
       __syncthreads();
       const float4 y4 = *reinterpret_cast<const float4*>(vb + 4 * lane);
       float l = 0.0f;
+      // 16 gathered rows in flight per warp; their 16 dot products are reduced by a transposing halving reduction
+      // (16 shuffles for 16 rows).  Register s of lane L holds row q + (s ^ slot), slot = L >> 1, which makes every halving
+      // level the same instruction stream for all lanes; after the four levels + one butterfly lanes 2 slot and 2 slot + 1
+      // hold u of row q + slot.
+      const int slot = lane >> 1;
       for (int base = warp * 32; base < n; base += 4 * 32) {          // this warp's groups of 32 gathered rows
         const int cnt = min(32, n - base);
         int my_idx = 0;
@@ -281,24 +286,35 @@ __global__ void __launch_bounds__(kGcThreads, 2) als_cg_gram_kernel(TileCgParams
           my_idx = __ldg(P.idx + p0 + base + lane);
           my_c = __ldg(P.val + p0 + base + lane);
         }
-        for (int q = 0; q < cnt; q += 8) {
-          float4 xv[8];
+        for (int q = 0; q < cnt; q += 16) {
+          float4 xv[16];
 #pragma unroll
-          for (int u = 0; u < 8; u++) {
-            const int src = __shfl_sync(kFull, my_idx, (q + u) & 31);
-            xv[u] = (q + u < cnt) ? ldg_f4(P.X + (size_t)src * K + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int s16 = 0; s16 < 16; s16++) {
+            const int jl = q + (s16 ^ slot);
+            const int src = __shfl_sync(kFull, my_idx, jl & 31);
+            xv[s16] = (jl < cnt) ? ldg_f4(P.X + (size_t)src * K + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
+          float t16[16];
 #pragma unroll
-          for (int u = 0; u < 8; u++) {
-            const float d = warp_sum(dot4(xv[u], y4));
-            const float cj = __shfl_sync(kFull, my_c, (q + u) & 31);
-            if (q + u < cnt) {
-              const float e = implicit ? (1.0f - d) : (cj - d);
-              l += implicit ? e * e * cj : e * e;
-            }
+          for (int s16 = 0; s16 < 16; s16++) t16[s16] = dot4(xv[s16], y4);
+          float t8[8], t4[4], t2[2];
+#pragma unroll
+          for (int v = 0; v < 8; v++) t8[v] = t16[v] + __shfl_xor_sync(kFull, t16[v + 8], 16);
+#pragma unroll
+          for (int v = 0; v < 4; v++) t4[v] = t8[v] + __shfl_xor_sync(kFull, t8[v + 4], 8);
+#pragma unroll
+          for (int v = 0; v < 2; v++) t2[v] = t4[v] + __shfl_xor_sync(kFull, t4[v + 2], 4);
+          float d = t2[0] + __shfl_xor_sync(kFull, t2[1], 2);
+          d += __shfl_xor_sync(kFull, d, 1);
+          const int jo = q + slot;
+          const float cj = __shfl_sync(kFull, my_c, jo & 31);
+          if (jo < cnt && (lane & 1) == 0) {
+            const float e = implicit ? (1.0f - d) : (cj - d);
+            l += implicit ? e * e * cj : e * e;
           }
         }
       }
+      l = warp_sum(l);
       // every lane of a warp carries the same l; the regulariser term once per row
       float tot = block_sum((lane == 0) ? l : 0.0f);
       tot = fmaf(lam_use, block_sum(xr * xr), tot);
