@@ -54,6 +54,7 @@ struct CscDev {
   // double-buffered, then thread-block clusters of 2 / 4 / 8 CTAs
   static constexpr int kClsResident = 0, kClsTile0 = 1, kNumTile = 7, kClsLong = 8, kNumCls = 9;
   RowClass cls[kNumCls];
+  int all_ge1 = -1;           // implicit confidences: 1 = every value >= 1 (the symmetric Gram-rows kernel applies), 0 = not, -1 = unknown
   int plan_key = -1;          // 0: a plan exists (built for plan_sig), -1: none
   int plan_sig[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int plan_empty = 0;
@@ -96,6 +97,7 @@ static int upload_csc(const b200als_csc* A, CscDev<T>& D, cudaStream_t st) {
   }
   D.n_short = -1;
   D.plan_key = -1;
+  D.all_ge1 = -1;
   return B200ALS_OK;
 }
 

@@ -62,6 +62,13 @@ __global__ void classify_rows_kernel(const int32_t* __restrict__ ptr, int n_rows
   else if (n <= max_short) short_list[atomicAdd(&counts[0], 1)] = r;
   else long_list[atomicAdd(&counts[1], 1)] = r;
 }
+// flag[0] |= 1 if any value is below 1 (or NaN)
+__global__ void any_below_one_kernel(const float* __restrict__ v, long long n, int* __restrict__ flag) {
+  bool bad = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    bad |= !(v[i] >= 1.0f);
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
+}
 template <typename T>
 __global__ void zero_empty_rows_kernel(const int32_t* __restrict__ ptr, int n_rows, int k, T* __restrict__ Y) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -560,9 +560,13 @@ static int gather_ranges(b200als_session* s, int which) {
   Ctx& c = ctx();
   // chunked solves (exchange overlapped with the solve) need every row of the block in ONE length class of the CG path
   const bool cg_fast = (s->k % 4 == 0) && (s->k <= 256);
-  if (cg_fast) TRY(plan_rows(c, s->csc[which], s->k, s->k == kResK && s->opt.kernel != 10, false));
+  bool gram_rows = false;
+  if (cg_fast) {
+    TRY(gram_rows_for(c, s->csc[which], s->k, s->opt.feedback, &gram_rows));
+    TRY(plan_rows(c, s->csc[which], s->k, s->k == kResK && s->opt.kernel != 10, false, gram_rows));
+  }
   const bool one_class = cg_fast && s->csc[which].plan_single >= 0 &&
-                         (s->csc[which].plan_single != CscDev<float>::kClsLong || gram_rows_enabled(s->k)) &&
+                         (s->csc[which].plan_single != CscDev<float>::kClsLong || gram_rows) &&
                          !s->csc[which].cls[s->csc[which].plan_single].stream;
   std::vector<int32_t> ranges(3 * g_comm.world);
   DevBuf d;

@@ -81,6 +81,30 @@ static bool gram_rows_enabled(int k) {
   const char* e = getenv("B200ALS_GRAM_ROWS");
   return !(e && e[0] == '0');
 }
+// The Gram-rows kernel forms X_nnz diag(c - 1) X_nnz' as Z Z' with z_j = sqrt(c_j - 1) x_j: implicit confidences must all be
+// >= 1 (checked once per uploaded matrix); explicit feedback has unit weights.
+template <typename T>
+static int gram_rows_for(Ctx& c, CscDev<T>& A, int k, int feedback, bool* ok) {
+  *ok = false;
+  if constexpr (sizeof(T) != 4) return B200ALS_OK;
+  if (!gram_rows_enabled(k)) return B200ALS_OK;
+  if (feedback == B200ALS_EXPLICIT) { *ok = true; return B200ALS_OK; }
+  if (A.all_ge1 < 0) {
+    DevBuf flag;
+    CU(flag.ensure(sizeof(int)));
+    CU(cudaMemsetAsync(flag.p, 0, sizeof(int), c.stream));
+    if (A.nnz > 0) {
+      any_below_one_kernel<<<c.sm_count * 4, 256, 0, c.stream>>>((const float*)A.val.p, (long long)A.nnz, flag.i32());
+      LAUNCHED(); CU(cudaGetLastError());
+    }
+    int h = 0;
+    CU(cudaMemcpyAsync(&h, flag.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    CU(cudaStreamSynchronize(c.stream));
+    A.all_ge1 = h ? 0 : 1;
+  }
+  *ok = (A.all_ge1 == 1);
+  return B200ALS_OK;
+}
 static int tile_kpad(int k) { return k <= 16 ? 16 : k <= 32 ? 32 : k <= 64 ? 64 : k <= 128 ? 128 : 256; }
 static int tile_cap_for(int kpad, int warps, size_t budget, bool full_g, int nbuf, int cluster) {
   int cap = 0;
@@ -92,11 +116,11 @@ static int tile_cap_for(int kpad, int warps, size_t budget, bool full_g, int nbu
   return cap;
 }
 template <typename T>
-static int plan_rows(Ctx& c, CscDev<T>& A, int k, bool resident_ok, bool full_g) {
+static int plan_rows(Ctx& c, CscDev<T>& A, int k, bool resident_ok, bool full_g, bool gram_rows) {
   // the plan depends on the rank, the mode and the A/B switches of the environment: cached until any of them changes
   auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
   const int sig[8] = {k, resident_ok ? 1 : 0, full_g ? 1 : 0, env_int("B200ALS_TILE_WARPS_S", 4) * 100 + env_int("B200ALS_TILE_WARPS_M", 0), env_int("B200ALS_TILE_CLUSTER", -1),
-                      env_int("B200ALS_TILE_CLUSTER_MIN", -1), env_int("B200ALS_GRAM_ROWS", -1), env_int("B200ALS_GRAM_ROWS_MIN", -1)};
+                      env_int("B200ALS_TILE_CLUSTER_MIN", -1), gram_rows ? 1 : 0, env_int("B200ALS_GRAM_ROWS_MIN", -1)};
   if (A.plan_key == 0 && std::memcmp(sig, A.plan_sig, sizeof(sig)) == 0) return B200ALS_OK;
   using RC = typename CscDev<T>::RowClass;
   const int kpad = tile_kpad(k);
@@ -121,7 +145,6 @@ static int plan_rows(Ctx& c, CscDev<T>& A, int k, bool resident_ok, bool full_g)
   const int shape[7][4] = {{warpsS, ctasS, 1, 2}, {warpsS, ctasS, 1, 1}, {warpsM, 2, 1, 1}, {warpsL, 1, 1, 2}, {16, 1, 2, 2}, {16, 1, 4, 2}, {16, 1, 8, 2}};
   int max_cluster = 1;   // B200ALS_TILE_CLUSTER = 1 | 2 | 4 | 8: largest cluster used (1: longer rows go to the long-row kernels)
   if (const char* e = getenv("B200ALS_TILE_CLUSTER")) max_cluster = std::max(1, atoi(e));
-  const bool gram_rows = gram_rows_enabled(k);
   if (gram_rows) max_cluster = 1;   // rank 128: long rows go to the tensor-core Gram kernel, not to clusters
   int min_cluster = 2;   // B200ALS_TILE_CLUSTER_MIN = 2 | 4 | 8: smallest cluster used (rows between one CTA's capacity and
                          // min_cluster / 2 times it go to the streaming kernel)
@@ -420,8 +443,9 @@ static int solve_rows(Ctx& c, CscDev<T>& A, const T* X, T* Y, const T* G, const 
     using CD = CscDev<T>;
     const bool resident_ok = (k == kResK) && (o.kernel != 10);
     const bool full_g = (o.feedback == B200ALS_IMPLICIT) && !diag;
-    TRY(plan_rows(c, A, k, resident_ok, full_g));
-    const bool gram_rows = gram_rows_enabled(k);
+    bool gram_rows = false;
+    TRY(gram_rows_for(c, A, k, o.feedback, &gram_rows));
+    TRY(plan_rows(c, A, k, resident_ok, full_g, gram_rows));
     if (sub_range && (A.plan_single < 0 || (A.plan_single == CD::kClsLong && !gram_rows) || A.cls[A.plan_single].stream))
       return fail(B200ALS_EINVAL, "row sub-ranges need a block whose rows all fall into one length class");
     if (A.plan_empty > 0) {

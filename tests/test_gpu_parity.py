@@ -117,7 +117,8 @@ def test_tile_cg_kernel_in_session(name, kernel, cases, golden_half):
 
 @pytest.mark.parametrize("k,feedback,gram_rows,clusters", [(128, "implicit", "1", "1"), (128, "explicit", "1", "1"), (128, "implicit", "0", "8"),
                                                            (128, "explicit", "0", "8"), (256, "implicit", "1", "8"), (64, "implicit", "1", "8"),
-                                                           (128, "implicit", "0", "1"), (256, "implicit", "1", "1")])
+                                                           (128, "implicit", "0", "1"), (256, "implicit", "1", "1"),
+                                                           (128, "implicit-low", "1", "1")])
 @pytest.mark.parametrize("kernel", [10, 2])
 def test_long_rows_gram_and_cluster_kernels(k, feedback, gram_rows, clusters, kernel, monkeypatch):
     """Rows too long for one CTA's tile buffers.  Rank 128: als_cg_gram_kernel -- the row's 128 x 128 system is formed on
@@ -130,7 +131,11 @@ def test_long_rows_gram_and_cluster_kernels(k, feedback, gram_rows, clusters, ke
     monkeypatch.setenv("B200ALS_GRAM_ROWS", gram_rows)
     monkeypatch.setenv("B200ALS_TILE_CLUSTER", clusters)      # clusters are opt-in (profiles/r2/tile_ab.txt)
     n_rows, n_src, lam = 40, 3000, 0.1
+    low = (feedback == "implicit-low")      # confidences below 1: c - 1 < 0, the symmetric Gram-rows kernel must step aside
+    feedback = "implicit" if low else feedback
     ptr, idx, val = wc.det_csr(n_rows, n_src, 1200, 77 + k, ragged=True, explicit=(feedback == "explicit"))
+    if low:
+        val = val * 0.25
     X = np.ascontiguousarray(wc.det_factors(n_src, k, 300 + k, 0.1) * (1.0 + np.arange(k, dtype=np.float32)) ** -0.5)
     Y0 = wc.det_factors(n_rows, k, 301 + k)
     X64, Yo = X.astype(np.float64), Y0.astype(np.float64)
