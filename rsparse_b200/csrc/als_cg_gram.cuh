@@ -74,6 +74,8 @@ __global__ void __launch_bounds__(kGcThreads, 2) als_cg_gram_kernel(TileCgParams
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = S.tmem_base;
+  for (int e = tid; e < 2 * kTcRows * K / 4; e += kGcThreads)   // raw ring: finite contents from the start (padding rows are read)
+    reinterpret_cast<float4*>(&S.raw[0][0][0])[e] = make_float4(0.f, 0.f, 0.f, 0.f);
   // per operand-tile buffer b (bit b): parity of the next completion to wait for / a commit on that buffer's mbarrier
   // has not been waited for yet (the same values in every thread; each completion is consumed exactly once)
   uint32_t ph_bits = 0, pend_bits = 0;
@@ -157,19 +159,20 @@ __global__ void __launch_bounds__(kGcThreads, 2) als_cg_gram_kernel(TileCgParams
       // ---- stage: warp w transposes the 4-row group w of the chunk into the K-major layout; z = s x, hi / lo split ------
       {
         const int kb = warp;
-        float sv[4], cv[4];
+        // padding rows: their metadata is (index 0, value 0) => c = 0 and s = 0, and the raw buffer holds finite stale data
+        // (zero-filled once per kernel), so no bounds checks are needed here
+        const float4 c4v = *reinterpret_cast<const float4*>(&S.cs[ms][kb * 4]);
+        const float cv[4] = {c4v.x, c4v.y, c4v.z, c4v.w};
+        float sv[4];
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) {
-          const int jl = kb * 4 + kk;
-          const bool ok = (jbase + jl < n);
-          cv[kk] = ok ? S.cs[ms][jl] : 0.0f;
-          sv[kk] = ok ? (implicit ? sqrtf(fmaxf(cv[kk] - 1.0f, 0.0f)) : 1.0f) : 0.0f;
+          // s = sqrt(c - 1) to ~2 ulp (MUFU.RSQ): s^2 differs from c - 1 by ~2e-7 relative, far below the fp32 tolerance
+          const float wgt = implicit ? fmaxf(cv[kk] - 1.0f, 0.0f) : ((jbase + kb * 4 + kk < n) ? 1.0f : 0.0f);
+          sv[kk] = (wgt > 0.0f) ? wgt * __frsqrt_rn(wgt) : 0.0f;
         }
         float4 v[4];
 #pragma unroll
-        for (int kk = 0; kk < 4; kk++)
-          v[kk] = (jbase + kb * 4 + kk < n) ? *reinterpret_cast<const float4*>(&S.raw[ob][kb * 4 + kk][lane * 4])
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int kk = 0; kk < 4; kk++) v[kk] = *reinterpret_cast<const float4*>(&S.raw[ob][kb * 4 + kk][lane * 4]);
         const float col[4][4] = {{v[0].x, v[1].x, v[2].x, v[3].x}, {v[0].y, v[1].y, v[2].y, v[3].y},
                                  {v[0].z, v[1].z, v[2].z, v[3].z}, {v[0].w, v[1].w, v[2].w, v[3].w}};
 #pragma unroll
