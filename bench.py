@@ -378,6 +378,9 @@ def main():
     e2e = None
     if not args.no_e2e:
         from rsparse_b200 import als_implicit
+        if world > 1:
+            # every rank passes the same item matrix: rank 0 uploads it, the others receive it over NVLink
+            os.environ["B200ALS_STATELESS_SHARE_FIXED"] = "1"
         ptr, idx, val = host_csr(L, n_local, n_item, nnz, 42, True, begin)
         Xh = L.pinned_empty((n_item, k), np.float32)
         Yh = L.pinned_empty((n_local, k), np.float32)
@@ -395,10 +398,11 @@ def main():
             t0 = time.perf_counter()
             als_implicit(ptr, idx, val, Xh, Yh, lam, L.CONJUGATE_GRADIENT, cg)
             dt += parallel.max_over_ranks(time.perf_counter() - t0)
-        h2d = ptr.nbytes + idx.nbytes + val.nbytes + Xh.nbytes + Yh.nbytes
+        h2d = ptr.nbytes + idx.nbytes + val.nbytes + Xh.nbytes + Yh.nbytes      # rank 0 (the other ranks: without the item matrix when N > 1)
         e2e = {"value": n_user * args.e2e_steps / dt, "unit": "user-updates/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(Yh.nbytes), "ms_per_step": 1e3 * dt / args.e2e_steps, "steps": args.e2e_steps,
                "h2d_gbs_per_rank": h2d / (dt / args.e2e_steps) / 1e9, "host_binding_rank0": numa,
+               "fixed_matrix": "uploaded by every rank" if world == 1 else "uploaded by rank 0, ncclBroadcast to the others (B200ALS_STATELESS_SHARE_FIXED=1)",
                "api": "b200als_als_implicit_float (stateless, host pointers, CSR values double as in R's dgCMatrix)"}
 
     # ---- CPU baseline (rank 0, N = 1): the oracle timed on this box's host cores -------------------------

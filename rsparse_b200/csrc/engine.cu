@@ -96,9 +96,9 @@ extern "C" int b200als_set_device(int device) {
 // The translation unit is split into parts for readability only; they are textually included in this order.
 #include "engine_helpers.inl"   // small device helpers: DevBuf, conversion / reduction / bias-layout / synthetic-data kernels
 #include "engine_context.inl"   // device context, CSC upload, XtX dispatch
+#include "engine_comm.inl"   // 3. communicator (NCCL bound with dlopen)
 #include "engine_solve.inl"   // half-iteration dispatch: kernel selection for CG / Cholesky / NNLS, loss
 #include "engine_stateless.inl"   // 1. stateless calls (the reference-shaped entry points), pipelined call, initialize_biases, XtX, host helpers
 #include "engine_topk.inl"   // top-k recommendation (top_product)
-#include "engine_comm.inl"   // 3. communicator (NCCL bound with dlopen)
 #include "engine_session.inl"   // 2. session: device-resident fit, format ingest, exchange of solved rows, transform
 #include "engine_synth.inl"   // 4. synthetic workloads

@@ -686,6 +686,7 @@ __global__ void set_col_kernel(float* __restrict__ M, int ld, int col, int n, fl
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < n) M[(size_t)r * ld + col] = v;
 }
+__global__ void status_to_double_kernel(const int* __restrict__ status, double* __restrict__ out) { out[0] = (status[0] != 0) ? 1.0 : 0.0; }
 __global__ void finalize_gram_kernel(double* __restrict__ G64, float* __restrict__ G, int k, double lambda) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= k * k) return;
@@ -849,19 +850,33 @@ static int session_half(b200als_session* s, int which, int solver, float* Yout, 
   nvtxRangePop();
   NvtxRange nv_loss("b200als/loss");
   // loss: local row sums -> global
-  double rows_sum = 0.0;
-  {
-    double h = 0.0;
-    if (g_comm.world > 1) {
-      NC(g_nccl.AllReduce(c.loss_acc.p, c.loss_acc.p, 1, ncclDouble, ncclSum, g_comm.comm, c.stream));
-      // a non-SPD row on ONE rank must fail the call on EVERY rank (the others would otherwise run ahead into the next collective)
-      NC(g_nccl.AllReduce(c.status.p, c.status.p, 1, ncclInt32, ncclMax, g_comm.comm, c.stream));
+  if (g_comm.world > 1) {
+    // One all-reduce carries the row sums, the regulariser (each rank squares its 1 / world slice of the fixed matrix instead of
+    // every rank reading all of it) and the status word (a non-SPD row on ONE rank must fail the call on EVERY rank).  With
+    // the peer-memory exchange it is also the completion barrier of the pushes (see above).
+    const long long b = n_fixed * g_comm.rank / g_comm.world, e = n_fixed * (g_comm.rank + 1) / g_comm.world;
+    CU(cudaMemsetAsync(c.loss_acc.f64() + 1, 0, sizeof(double), c.stream));
+    if (o.lambda > 0 && e > b) {
+      const bool weighted = (o.feedback == B200ALS_EXPLICIT) && o.dynamic_lambda;
+      const int grid = c.sm_count * 2;
+      CU(c.reg_partials.ensure(sizeof(double) * (size_t)grid));
+      sqnorm_kernel<float><<<grid, 256, 0, c.stream>>>(X + (size_t)b * s->k, s->k, e - b, weighted ? s->cnt[fixed].f32() + b : nullptr,
+                                                     c.reg_partials.f64());
+      LAUNCHED(); CU(cudaGetLastError());
+      sum_partials_kernel<<<1, 32, 0, c.stream>>>(c.reg_partials.f64(), grid, c.loss_acc.f64() + 1, 0);
+      LAUNCHED(); CU(cudaGetLastError());
     }
-    CU(cudaMemcpyAsync(&h, c.loss_acc.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    status_to_double_kernel<<<1, 1, 0, c.stream>>>(c.status.i32(), c.loss_acc.f64() + 2);
+    LAUNCHED(); CU(cudaGetLastError());
+    NC(g_nccl.AllReduce(c.loss_acc.p, c.loss_acc.p, 3, ncclDouble, ncclSum, g_comm.comm, c.stream));
+    double h[3] = {0, 0, 0};
+    CU(cudaMemcpyAsync(h, c.loss_acc.p, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
     CU(cudaStreamSynchronize(c.stream));
-    rows_sum = h;
+    if (h[2] != 0.0) return fail(B200ALS_ENOTSPD, "a per-row system was not positive definite (Cholesky pivot <= 0) on some rank");
+    if (loss) *loss = (double)(float)((h[0] + o.lambda * h[1]) / (double)s->nnz_global[which]);
+  } else {
+    TRY(finish_loss<float>(c, X, s->k, n_fixed, s->cnt[fixed].f32(), o, s->nnz_global[which], 0.0, false, loss));
   }
-  TRY(finish_loss<float>(c, X, s->k, n_fixed, s->cnt[fixed].f32(), o, s->nnz_global[which], rows_sum, true, loss));
   cudaEventElapsedTime(&s->t_gram, s->ev[0], s->ev[1]);
   cudaEventElapsedTime(&s->t_prep, s->ev[1], s->ev[2]);
   cudaEventElapsedTime(&s->t_solve, s->ev[2], s->ev[3]);

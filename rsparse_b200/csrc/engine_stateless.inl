@@ -226,7 +226,17 @@ static int stateless_pipelined(const b200als_csc* A, const float* X, float* Y, c
   // ---- fixed matrix, Gram, eigenbasis (compute stream) ----
   const size_t xbytes = sizeof(float) * (size_t)k * (size_t)A->n_rows;
   CU(pc.X.ensure(xbytes));
-  CU(cudaMemcpyAsync(pc.X.p, X, xbytes, cudaMemcpyHostToDevice, c.stream));
+  // One process per GPU, every rank calling with its own block of rows and the SAME fixed matrix: with
+  // B200ALS_STATELESS_SHARE_FIXED=1 only rank 0 uploads it and the others receive it over NVLink (ncclBroadcast) --
+  // on a host whose memory system, not PCIe, bounds N concurrent uploads that removes (N - 1) x the matrix from the host path.
+  // Opt-in: the caller asserts that all ranks pass identical X (the engine cannot check it).
+  const char* esh = getenv("B200ALS_STATELESS_SHARE_FIXED");
+  if (g_comm.world > 1 && g_comm.comm && esh && esh[0] == '1') {
+    if (g_comm.rank == 0) CU(cudaMemcpyAsync(pc.X.p, X, xbytes, cudaMemcpyHostToDevice, c.stream));
+    NC(g_nccl.Broadcast(pc.X.p, pc.X.p, (size_t)k * (size_t)A->n_rows, ncclFloat, 0, g_comm.comm, c.stream));
+  } else {
+    CU(cudaMemcpyAsync(pc.X.p, X, xbytes, cudaMemcpyHostToDevice, c.stream));
+  }
   const float* diag = nullptr;
   const float* Glong = nullptr;
   if (implicit) {
