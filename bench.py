@@ -374,6 +374,20 @@ def main():
                     "traffic": traffic_per_launch(args.workload if not items_half else args.workload + "-items", world),
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": solve_ms,
                     "fp32_tflops": (cg + 1) * (4 * nnz_local * k + 2 * k * k * rows_local) / (solve_ms / 1e3) / 1e12}
+    if solver == L.CHOLESKY:
+        # rank 128: the per-row Gram (2nk^2 of the flops) runs on tcgen05 as 3xTF32 => effective tensor peak = TF32 dense / 3
+        # = measured bf16 sustained / 2 / 3; rank 64: fp32 FFMA2 kernel => nominal fp32 peak (148 SMs x 128 lanes x 2 x clock)
+        try:
+            pk16 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
+        except Exception:
+            pk16 = 1364.4
+        if k == 128 and args.kernel != 4:
+            pk, src = pk16 / 6.0, "3xTF32 effective = measured bf16 sustained / 2 (TF32 rate) / 3 (split passes)"
+        else:
+            roofline["bound"] = "fp32"
+            pk, src = 148 * 128 * 2 * 1.965e9 / 1e12, "nominal fp32 FMA peak (148 SMs x 128 lanes x 2 flop x 1.965 GHz)"
+        roofline["peak"], roofline["frac"], roofline["peak_source"] = pk, roofline["achieved"] / pk, src
+        roofline["gram_share_of_flops"] = 2 * nnz * k * k / fl
     # ---- e2e: stateless C-ABI call, host buffers, copies inside the timed region -----------------------
     e2e = None
     if not args.no_e2e:
