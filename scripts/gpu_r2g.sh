@@ -1,6 +1,7 @@
 #!/bin/bash
 # round 2, call G (1 GPU): full GPU suite; A/B of the tile kernel's switches (clusters off / >= 4 / all; single-buffered
 # small classes) on the ragged robustness point, the item half, C3 forced onto the tile kernel and rank 64.
+# (B200ALS_TILE_SINGLE was the experiment switch of this call; its outcome is now the default class layout, engine_solve.inl)
 TAG=${1:-r2g}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
