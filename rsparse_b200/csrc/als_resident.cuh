@@ -21,8 +21,11 @@
 //     of XtX from L1/L2 and the slabs are summed by the same cross-warp reduction;
 //   * the loss term X_nnz' y is obtained from the u vectors already computed
 //     (X_nnz' y = X_nnz' x0 + sum_k alpha_k X_nnz' p_k) instead of a fifth sweep;
-//   * alpha = rsold / p'Ap and beta are formed by fp32 division (the reference divides in double and
-//     rounds to T, wrmf_implicit.hpp:18,23,28); rounding-level difference, covered by the fp32 tolerance.
+//   * alpha = rsold / p'Ap and beta are formed by the fp32 hardware reciprocal, <= 2 ulp (the reference divides
+//     in double and rounds to T, wrmf_implicit.hpp:18,23,28); rounding-level difference, covered by the fp32
+//     tolerance;
+//   * p'XtX p rides in the per-warp scalar of the cross-warp exchange and the loss terms are summed per lane in
+//     fp64, so a CG step has ONE warp-wide scalar reduction that is not overlapped with a sweep (|r|^2).
 // Algorithmic HBM bytes per row: 4nk + 8n + 4 + 4k + 4k  (42,628 B at n = 80, k = 128).
 #pragma once
 #include "common.cuh"
@@ -242,10 +245,21 @@ __global__ void __launch_bounds__(kResThreads, kCtas) als_cg_resident_kernel(Res
       if (my_j < n) bulk_g2s(my_tile + slot * kResK, P.X + (size_t)my_idx * kResK, kResRowBytes, my_bar);
       if (lane == 0) bulk_g2s(my_tile + kResIPW * kResK, P.Y + (size_t)row * kResK, kResRowBytes, my_bar);
     } else {
+      const float* xl = P.X + lane * 4;
+      float* tl = my_tile + lane * 4;
+      if (n == kResMaxN) {
 #pragma unroll
-      for (int q = 0; q < kResIPW; q++) {
-        const int src = __shfl_sync(kFull, my_idx, resident_owner_lane(q));
-        if (w + kResWarps * q < n) cp_async_16(my_tile + q * kResK + lane * 4, P.X + (size_t)src * kResK + lane * 4);
+        for (int q = 0; q < kResIPW; q++) {
+          const int src = __shfl_sync(kFull, my_idx, resident_owner_lane(q));
+          cp_async_16(tl + q * kResK, xl + (size_t)src * kResK);
+        }
+      } else {
+        const int nw = (n > w) ? (n - w + kResWarps - 1) / kResWarps : 0;
+#pragma unroll
+        for (int q = 0; q < kResIPW; q++) {
+          const int src = __shfl_sync(kFull, my_idx, resident_owner_lane(q));
+          if (q < nw) cp_async_16(tl + q * kResK, xl + (size_t)src * kResK);
+        }
       }
       cp_async_16(my_tile + kResIPW * kResK + lane * 4, P.Y + (size_t)row * kResK + lane * 4);
       cp_async_mbar_arrive_noinc(my_bar);
@@ -285,19 +299,31 @@ __global__ void __launch_bounds__(kResThreads, kCtas) als_cg_resident_kernel(Res
   float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
   if (!kFullG && implicit) dg = ldg_f4(P.diag + lane * 4);
   const float4 ndg = neg4(dg);
-  double warp_loss = 0.0;
+  double lane_loss = 0.0;   // summed over this lane's rows in fp64; one block reduction at the end
   int sweep = 0;
 
   for (int i = 0; valid(i); i++) {
     const int n = n0;
     // ---- my 20 rows: shared memory -> registers ----------------------------------------------------------
     mbar_wait(my_bar, (uint32_t)(i & 1));
+    // Register q = 10 h1 + 5 h2 + r2 holds gathered row w + 4 nat with nat = 10 (h1 ^ b4) + 5 (h2 ^ b3) + r2 (see
+    // Halver / resident_natural_slot): four lane-dependent block bases, compile-time offsets inside a block.
     float4 xt[kResIPW];
+    {
+      const float* tb = my_tile + lane * 4;
+      const int o1 = ((lane >> 4) & 1) * 10, o2 = ((lane >> 3) & 1) * 5;
+      const int nb[4] = {o1 + o2, o1 + (5 - o2), (10 - o1) + o2, (10 - o1) + (5 - o2)};   // first slot of block (h1, h2)
+      if (n == kResMaxN) {   // full tile: no padding anywhere
 #pragma unroll
-    for (int q = 0; q < kResIPW; q++) {
-      const int nat = resident_natural_slot(q, lane);   // register q holds gathered row w + 4*nat (see Halver)
-      xt[q] = (w + kResWarps * nat < n) ? *reinterpret_cast<const float4*>(my_tile + nat * kResK + lane * 4)
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < kResIPW; q++)
+          xt[q] = *reinterpret_cast<const float4*>(tb + (nb[q / 5] + q % 5) * kResK);
+      } else {
+        const int nw = (n > w) ? (n - w + kResWarps - 1) / kResWarps : 0;   // slots of this warp that hold a row
+#pragma unroll
+        for (int q = 0; q < kResIPW; q++)
+          xt[q] = (q % 5 < nw - nb[q / 5]) ? *reinterpret_cast<const float4*>(tb + (nb[q / 5] + q % 5) * kResK)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
     float4 x = *reinterpret_cast<const float4*>(my_tile + kResIPW * kResK + lane * 4);
     __syncwarp();  // my slot is free again
@@ -331,20 +357,20 @@ __global__ void __launch_bounds__(kResThreads, kCtas) als_cg_resident_kernel(Res
     }
     float4 p = r;
     float rsold = warp_sum(dot4(r, r));
+    u_p = sweep_dots(xt, p);   // issued with the |r|^2 reduction, not after the branch on its result
     // Guard the reference does not have (wrmf_implicit.hpp:23 computes rsold / (p'Ap) = 0/0 -> NaN once a row
     // has converged exactly, e.g. when the same half-iteration is repeated): a zero residual skips the loop.
     const int n_steps = (rsold > 0.0f) ? P.cg_steps : 0;
-    if (n_steps > 0) u_p = sweep_dots(xt, p);
+#pragma unroll 1
     for (int it = 0; it < n_steps; it++) {
-      // p' XtX p without the tile part (independent of the sweep below => overlaps with it)
-      float pGp = 0.0f;
-      if (implicit) {
-        if (!kFullG) pGp = warp_sum(dot4(p, make_float4(dg.x * p.x, dg.y * p.y, dg.z * p.z, dg.w * p.w)));
-      } else {
-        pGp = lam_use * warp_sum(dot4(p, p));
-      }
+      // p' XtX p without the tile part: every warp holds the whole p, so each adds a QUARTER of its lanes' terms to
+      // the per-warp scalar that the cross-warp exchange sums anyway -- one warp reduction per step instead of two,
+      // interleaved with the sweep below instead of ahead of it.
+      float gterm;
+      if (implicit) gterm = kFullG ? 0.0f : 0.25f * dot4(p, fma4(dg, p, make_float4(0.f, 0.f, 0.f, 0.f)));
+      else gterm = (0.25f * lam_use) * dot4(p, p);
       const float cw = implicit ? (cq - 1.0f) : 1.0f;
-      const float spart = warp_sum(mine ? cw * u_p * u_p : 0.0f);
+      const float spart = warp_sum((mine ? cw * u_p * u_p : 0.0f) + gterm);
       float ssum;
       v = sweep_apply<kFullG>(xt, cw * u_p, slot, p, (kFullG && implicit) ? 2 : 0, S, sweep++, P.G, spart, ssum);
       float4 Ap;
@@ -354,8 +380,11 @@ __global__ void __launch_bounds__(kResThreads, kCtas) als_cg_resident_kernel(Res
       } else {
         Ap = axpy4(lam_use, p, v);
       }
-      const float pAp = pGp + ssum;
-      const float a = (pAp != 0.0f) ? __fdiv_rn(rsold, pAp) : 0.0f;
+      const float pAp = ssum;
+      // rsold / pAp and rsnew / rsold by the hardware reciprocal (div.approx, <= 2 ulp; the reference divides in
+      // double and rounds, wrmf_implicit.hpp:18,23,28): two instructions instead of the exact-division chain with
+      // its slow-path branch on the critical path of every step
+      const float a = (pAp != 0.0f) ? __fdividef(rsold, pAp) : 0.0f;
       x = axpy4(a, p, x);
       r = axpy4(-a, Ap, r);
       uy = fmaf(a, u_p, uy);
@@ -363,22 +392,21 @@ __global__ void __launch_bounds__(kResThreads, kCtas) als_cg_resident_kernel(Res
       const float rsnew = warp_sum(dot4(r, r));           // in flight ...
       const float u_r = sweep_dots(xt, r);                // ... while the next sweep's row dots run
       if (rsnew < (float)B200ALS_CG_TOL) break;           // identical in all four warps (same data, same order)
-      const float bt = __fdiv_rn(rsnew, rsold);
+      const float bt = __fdividef(rsnew, rsold);
       p = axpy4(bt, p, r);
       u_p = fmaf(bt, u_p, u_r);
       rsold = rsnew;
     }
     if (w == 0) *reinterpret_cast<float4*>(P.Y + (size_t)rid0 * kResK + lane * 4) = x;
     // ---- loss ---------------------------------------------------------------------------------------------
-    {
+    {   // per-lane terms: owner lanes add their rating's term, warp 0 adds its features' share of lambda |y|^2
       float l = 0.0f;
       if (my_j < n) {
         const float d = implicit ? (1.0f - uy) : (cq - uy);
         l = implicit ? d * d * cq : d * d;
       }
-      l = warp_sum(l);
-      if (w == 0) l = fmaf(lam_use, warp_sum(dot4(x, x)), l);
-      warp_loss += (double)l;
+      if (w == 0) l = fmaf(lam_use, dot4(x, x), l);
+      lane_loss += (double)l;
     }
     // ---- advance the pipeline ------------------------------------------------------------------------------
     n0 = n1; cq = val1; rid0 = rid1;
@@ -386,7 +414,7 @@ __global__ void __launch_bounds__(kResThreads, kCtas) als_cg_resident_kernel(Res
     p2 = p3 - P.ptr_base; n2 = p3e - p3; rid2 = rid3;
     rid3 = rid4;
   }
-  const double tot = block_sum_double((lane == 0) ? warp_loss : 0.0, S.red);
+  const double tot = block_sum_double(lane_loss, S.red);
   if (tid == 0) P.loss_partials[blockIdx.x] = tot;
 }
 
