@@ -4,12 +4,15 @@
 // Reference semantics: cg_solver_implicit (inst/include/wrmf_implicit.hpp:8-32), cg_solver_explicit
 // (inst/include/wrmf_explicit.hpp:8-31) and the surrounding column loop (wrmf_implicit.hpp:175-282,
 // wrmf_explicit.hpp:71-146).  What is different from the reference's shape:
-//   * one CTA of 4 warps owns a row; warp w holds gathered rows j = w, w+4, ... (<= 20 of them), lane l
-//     holds features 4l..4l+3 of each as one float4 => the 40 KB tile X_nnz is read from HBM exactly
-//     once per row and then lives in 80 registers/thread for all 2(s+1) mat-vecs;
+//   * one CTA of 4 warps owns a row; warp w holds gathered rows j = w, w+4, ... (<= 20 of them) as 10 register
+//     GROUPS x 2 half-warps: lane (g = lane >> 4, l = lane & 15) keeps, for each group, 8 features of ONE row
+//     (two float4) => the 40 KB tile X_nnz is read from HBM exactly once per row and then lives in 80
+//     registers/thread for all 2(s+1) mat-vecs;
 //   * the two mat-vecs of a CG step are fused into one sweep over the registers:
-//       u_j = x_j . p   (4 FMA/lane + one transposing halving reduction per warp: 21 SHFL for 20 rows)
-//       w_j = (c_j - 1) u_j ;  acc += w_j x_j   (80 FMA/lane), then a 4-way cross-warp sum in smem;
+//       u_j = x_j . p   (8 FMA/lane per row, then a transposing halving reduction over the 16 lanes of the
+//                        half-warp: 11 SHFL for its 10 rows -- the other half-warp reduces its own 10 at the same time)
+//       w_j = (c_j - 1) u_j ;  acc += w_j x_j   (80 FMA/lane), one exchange between the two half-warps (4 SHFL),
+//       then a 4-way cross-warp sum in smem;
 //   * the NEXT row's tile (and its warm-start y) is prefetched while this row computes: every warp stages
 //     its own 20 gathered rows with one 512-byte cp.async.bulk (TMA engine, SASS UBLKCP) per owner lane
 //     into its own 10.5 KB shared-memory slot, completion by a per-warp mbarrier (complete_tx); the CSR
@@ -35,7 +38,8 @@ namespace b200als {
 constexpr int kResK = 128;       // rank handled by this kernel
 constexpr int kResWarps = 4;
 constexpr int kResThreads = kResWarps * 32;
-constexpr int kResIPW = 20;      // gathered rows per warp
+constexpr int kResIPW = 20;      // gathered rows per warp (= float4 registers per lane)
+constexpr int kResGroups = 10;   // register groups per lane: group q of half-warp g holds tile slot 2 qn + g
 constexpr int kResMaxN = kResWarps * kResIPW;  // 80
 constexpr int kResRowBytes = kResK * 4;        // 512
 
@@ -64,7 +68,7 @@ struct __align__(128) ResidentSmem {
   float tile[kResWarps][(kResIPW + 1) * kResK];
   float vbuf[2][kResWarps][kResK];         // cross-warp partial sums (double buffered per sweep)
   float sbuf[2][kResWarps];                // per-warp scalar partials riding the same exchange (p'Ap terms)
-  float2 wbuf[kResWarps][32];              // per-warp (w_j, w_j) broadcast: 4 blocks of 5 pairs, each padded to 8
+  float wbuf[kResWarps][32];               // per-warp w_j broadcast: [half-warp][block of 5, padded to 8]
   uint64_t bar[kResWarps];                 // one mbarrier per warp slot
   double red[32];
 };
@@ -72,7 +76,7 @@ struct __align__(128) ResidentSmem {
 // Transposing halving reduction: on entry lane L holds t[0..N) partial dot products, on exit the lane
 // whose bits select slot q holds the full 32-lane sum of t[q]; returns it (0 for padding lanes).
 // Levels with kSwapFree = true assume the registers of lanes whose bit M is set were LOADED with their two
-// halves swapped (see resident_natural_slot), so "keep the low registers, send the high registers" is the
+// halves swapped (see the layout note above resident_owner_group), so "keep the low registers, send the high registers" is the
 // same instruction stream for every lane -- no selects.  Odd-sized levels fall back to selects.
 template <int N>
 struct Halver {
@@ -101,24 +105,26 @@ struct Halver {
     }
   }
 };
-// slot owned by a lane after Halver<20>::run<16>: 20 -> 10 -> 5 -> 3 -> 2 -> 1
-__device__ __forceinline__ int resident_owner_slot(int lane) {
-  const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1, b0 = lane & 1;
+// Layout of a warp's 20 tile slots (slot s = gathered row w + 4 s of the CSR row, 512 B each in shared memory):
+// half-warp g = lane >> 4 holds the slots of its parity, s = 2 qn + g, qn = 0..9.  Register group q = 5 h + r of a
+// lane holds NATURAL group qn = 5 (h ^ b3) + r (b3 = lane bit 3: the first halving level 10 -> 5 is select-free
+// because lanes with bit 3 set keep their two blocks of five swapped), as two float4: register c of the group is
+// the 16-byte chunk (c ^ g) * 16 + l of the row (l = lane & 15), so that "keep register 0, send register 1" in the
+// exchange between the half-warps leaves lane L with chunk L of the sum -- the natural layout of x, r, p.
+//
+// group (within its half-warp) owned by a lane after Halver<10>::run<8, 1>: 10 -> 5 -> 3 -> 2 -> 1 over lane bits 3..0
+__device__ __forceinline__ int resident_owner_group(int lane, int& in5_out) {
+  const int b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1, b0 = lane & 1;
   const int in3 = 2 * b1 + b0;          // index within the group of 3 (valid < 3)
   const int in5 = 3 * b2 + in3;         // index within the group of 5 (valid < 5)
+  in5_out = in5;
   if (in3 >= 3 || in5 >= 5) return -1;
-  return 10 * b4 + 5 * b3 + in5;
+  return 5 * b3 + in5;
 }
-// lane that owns slot q (inverse of resident_owner_slot)
-__host__ __device__ constexpr int resident_owner_lane(int q) {
-  const int b4 = q / 10, r = q % 10, b3 = r / 5, in5 = r % 5, b2 = in5 / 3, in3 = in5 % 3;
-  return 16 * b4 + 8 * b3 + 4 * b2 + 2 * (in3 / 2) + (in3 % 2);
-}
-// Which gathered-row slot lane L keeps in register q: the two halving levels 20->10 and 10->5 are select-free
-// because lanes with bit 4 (bit 3) set hold the two halves (quarters) of their registers swapped.
-__device__ __forceinline__ int resident_natural_slot(int q, int lane) {
-  const int h1 = q / 10, r1 = q % 10, h2 = r1 / 5, r2 = r1 % 5;
-  return 10 * (h1 ^ ((lane >> 4) & 1)) + 5 * (h2 ^ ((lane >> 3) & 1)) + r2;
+// lane (within a half-warp) that owns natural group qn (inverse of resident_owner_group)
+__host__ __device__ constexpr int resident_group_owner_lane(int qn) {
+  const int b3 = qn / 5, in5 = qn % 5, b2 = in5 / 3, in3 = in5 % 3;
+  return 8 * b3 + 4 * b2 + 2 * (in3 / 2) + (in3 % 2);
 }
 
 // Packed fp32 math (Blackwell FFMA2 / FMUL2 / FADD2: one instruction per register PAIR): the float4 held per
@@ -145,46 +151,53 @@ __device__ __forceinline__ float4 add4(const float4& a, const float4& b) {
 __device__ __forceinline__ float4 neg4(const float4& a) { return make_float4(-a.x, -a.y, -a.z, -a.w); }
 
 // ---- one CG sweep, in two halves -------------------------------------------------------------------------
-// (A) u_j = x_j . vec for this warp's 20 rows; the owner lane of slot q returns the full sum (0 on padding lanes)
+// (A) u_j = x_j . vec for this warp's 20 rows; the owner lane of a slot returns the full sum (0 on padding lanes).
+//     vec is in the natural layout (lane L holds chunk L); register 1 of a group needs the chunk of lane L ^ 16.
 __device__ __forceinline__ float sweep_dots(const float4 (&xt)[kResIPW], const float4& vec) {
-  float t[kResIPW];
+  const float4 vo = make_float4(__shfl_xor_sync(kFull, vec.x, 16), __shfl_xor_sync(kFull, vec.y, 16),
+                                __shfl_xor_sync(kFull, vec.z, 16), __shfl_xor_sync(kFull, vec.w, 16));
+  float t[kResGroups];
 #pragma unroll
-  for (int q = 0; q < kResIPW; q++) t[q] = dot4(xt[q], vec);
-  return Halver<kResIPW>::template run<16, 2>(t, lane_id());
+  for (int q = 0; q < kResGroups; q++) {
+    float2 m = __fmul2_rn(lo2(xt[2 * q]), lo2(vec));
+    m = __ffma2_rn(hi2(xt[2 * q]), hi2(vec), m);
+    m = __ffma2_rn(lo2(xt[2 * q + 1]), lo2(vo), m);
+    m = __ffma2_rn(hi2(xt[2 * q + 1]), hi2(vo), m);
+    t[q] = m.x + m.y;
+  }
+  return Halver<kResGroups>::template run<8, 1>(t, lane_id());
 }
 // (B) acc = sum_j wq_j x_j over the warp's rows (+ this warp's slab of XtX * vec when kFullG), 4-way cross-warp
 //     sum through shared memory; `spart` (a per-warp scalar, identical in all lanes) is summed across the four
 //     warps on the way and returned in `ssum`.
 template <bool kFullG>
-__device__ __forceinline__ float4 sweep_apply(const float4 (&xt)[kResIPW], float wq, int slot, const float4& vec,
+__device__ __forceinline__ float4 sweep_apply(const float4 (&xt)[kResIPW], float wq, int wpos, const float4& vec,
                                               int gmode /* 0: none, 1: acc - G vec, 2: acc + G vec */,
                                               ResidentSmem& S, int sweep, const float* __restrict__ G, float spart,
                                               float& ssum) {
   const int lane = lane_id(), w = warp_id();
-  if (slot >= 0) S.wbuf[w][(slot / 5) * 8 + (slot % 5)] = make_float2(wq, wq);
+  if (wpos >= 0) S.wbuf[w][wpos] = wq;
   __syncwarp();
-  // two independent accumulator sets (even / odd rows)
+  // four independent accumulator chains: (register 0 | register 1 of a group) x (low | high pair)
   float2 a0l = make_float2(0.f, 0.f), a0h = a0l, a1l = a0l, a1h = a0l;
-  const int bsel = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);  // this lane's register blocks hold natural blocks blk ^ bsel
 #pragma unroll
-  for (int blk = 0; blk < 4; blk++) {
-    const float2* wp = &S.wbuf[w][(blk ^ bsel) * 8];
-    const float4 w01 = *reinterpret_cast<const float4*>(wp);
-    const float4 w23 = *reinterpret_cast<const float4*>(wp + 2);
-    const float2 ws[5] = {lo2(w01), hi2(w01), lo2(w23), hi2(w23), wp[4]};
+  for (int h = 0; h < 2; h++) {
+    const float* wp = &S.wbuf[w][(lane & 24) ^ (h * 8)];   // my half-warp's block of natural groups 5 (h ^ b3) ..
+    const float4 w03 = *reinterpret_cast<const float4*>(wp);
+    const float ws[5] = {w03.x, w03.y, w03.z, w03.w, wp[4]};
 #pragma unroll
-    for (int i = 0; i < 5; i++) {
-      const float4& x = xt[blk * 5 + i];
-      if (((blk * 5 + i) & 1) == 0) {
-        a0l = __ffma2_rn(ws[i], lo2(x), a0l);
-        a0h = __ffma2_rn(ws[i], hi2(x), a0h);
-      } else {
-        a1l = __ffma2_rn(ws[i], lo2(x), a1l);
-        a1h = __ffma2_rn(ws[i], hi2(x), a1h);
-      }
+    for (int r = 0; r < 5; r++) {
+      const int q = 5 * h + r;
+      const float2 s2 = make_float2(ws[r], ws[r]);
+      a0l = __ffma2_rn(s2, lo2(xt[2 * q]), a0l);
+      a0h = __ffma2_rn(s2, hi2(xt[2 * q]), a0h);
+      a1l = __ffma2_rn(s2, lo2(xt[2 * q + 1]), a1l);
+      a1h = __ffma2_rn(s2, hi2(xt[2 * q + 1]), a1h);
     }
   }
-  float4 acc = join4(__fadd2_rn(a0l, a1l), __fadd2_rn(a0h, a1h));
+  // the other half-warp's rows: keep register 0 (chunk L), send register 1 (chunk L ^ 16)
+  float4 acc = join4(__fadd2_rn(a0l, make_float2(__shfl_xor_sync(kFull, a1l.x, 16), __shfl_xor_sync(kFull, a1l.y, 16))),
+                     __fadd2_rn(a0h, make_float2(__shfl_xor_sync(kFull, a1h.x, 16), __shfl_xor_sync(kFull, a1h.y, 16))));
   __syncwarp();
   if constexpr (kFullG) {
     // this warp's slab of XtX * vec: columns j in [32w, 32w+32); vec_j lives in lane j/4 (component j%4)
@@ -224,7 +237,10 @@ __global__ void __launch_bounds__(kResThreads, kCtas) als_cg_resident_kernel(Res
   const int lane = lane_id(), w = warp_id(), tid = threadIdx.x;
   const bool implicit = (P.feedback == 0);
   const int stride = gridDim.x;
-  const int slot = resident_owner_slot(lane);      // gathered-row slot this lane owns after the halving reduce
+  int in5;
+  const int og = resident_owner_group(lane, in5);  // natural group (within my half-warp) this lane owns after the halving reduce
+  const int slot = (og >= 0) ? 2 * og + (lane >> 4) : -1;             // ... = this tile slot of the warp
+  const int wpos = (og >= 0) ? (lane & 24) + in5 : -1;                // where its w_j goes in S.wbuf[w]
   const int my_j = (slot >= 0) ? (w + kResWarps * slot) : (1 << 30);  // its position within the CSR row
   float* my_tile = &S.tile[w][0];
   uint64_t* my_bar = &S.bar[w];
@@ -245,20 +261,26 @@ __global__ void __launch_bounds__(kResThreads, kCtas) als_cg_resident_kernel(Res
       if (my_j < n) bulk_g2s(my_tile + slot * kResK, P.X + (size_t)my_idx * kResK, kResRowBytes, my_bar);
       if (lane == 0) bulk_g2s(my_tile + kResIPW * kResK, P.Y + (size_t)row * kResK, kResRowBytes, my_bar);
     } else {
-      const float* xl = P.X + lane * 4;
-      float* tl = my_tile + lane * 4;
+      // half-warp g copies the slots of its parity: 16 lanes x 16 B = one half of a 512-byte row per instruction
+      const float* xl = P.X + (lane & 15) * 4;
+      float* tl = my_tile + (lane >> 4) * kResK + (lane & 15) * 4;
       if (n == kResMaxN) {
 #pragma unroll
-        for (int q = 0; q < kResIPW; q++) {
-          const int src = __shfl_sync(kFull, my_idx, resident_owner_lane(q));
-          cp_async_16(tl + q * kResK, xl + (size_t)src * kResK);
+        for (int qn = 0; qn < kResGroups; qn++) {
+          const int src = __shfl_sync(kFull, my_idx, resident_group_owner_lane(qn) | (lane & 16));
+          cp_async_16(tl + qn * 2 * kResK, xl + (size_t)src * kResK);
+          cp_async_16(tl + qn * 2 * kResK + 64, xl + (size_t)src * kResK + 64);
         }
       } else {
         const int nw = (n > w) ? (n - w + kResWarps - 1) / kResWarps : 0;
+        const int nwh = (nw - (lane >> 4) + 1) >> 1;   // slots 2 qn + g < nw
 #pragma unroll
-        for (int q = 0; q < kResIPW; q++) {
-          const int src = __shfl_sync(kFull, my_idx, resident_owner_lane(q));
-          if (q < nw) cp_async_16(tl + q * kResK, xl + (size_t)src * kResK);
+        for (int qn = 0; qn < kResGroups; qn++) {
+          const int src = __shfl_sync(kFull, my_idx, resident_group_owner_lane(qn) | (lane & 16));
+          if (qn < nwh) {
+            cp_async_16(tl + qn * 2 * kResK, xl + (size_t)src * kResK);
+            cp_async_16(tl + qn * 2 * kResK + 64, xl + (size_t)src * kResK + 64);
+          }
         }
       }
       cp_async_16(my_tile + kResIPW * kResK + lane * 4, P.Y + (size_t)row * kResK + lane * 4);
@@ -306,23 +328,31 @@ __global__ void __launch_bounds__(kResThreads, kCtas) als_cg_resident_kernel(Res
     const int n = n0;
     // ---- my 20 rows: shared memory -> registers ----------------------------------------------------------
     mbar_wait(my_bar, (uint32_t)(i & 1));
-    // Register q = 10 h1 + 5 h2 + r2 holds gathered row w + 4 nat with nat = 10 (h1 ^ b4) + 5 (h2 ^ b3) + r2 (see
-    // Halver / resident_natural_slot): four lane-dependent block bases, compile-time offsets inside a block.
+    // register c of group q = 5 h + r: chunk (c ^ g) * 16 + l of tile slot 2 (5 (h ^ b3) + r) + g  (see the layout
+    // note above resident_owner_group): four lane-dependent bases, compile-time offsets from there
     float4 xt[kResIPW];
     {
-      const float* tb = my_tile + lane * 4;
-      const int o1 = ((lane >> 4) & 1) * 10, o2 = ((lane >> 3) & 1) * 5;
-      const int nb[4] = {o1 + o2, o1 + (5 - o2), (10 - o1) + o2, (10 - o1) + (5 - o2)};   // first slot of block (h1, h2)
+      const int g = lane >> 4, l = lane & 15, ob = ((lane >> 3) & 1) * 5;
+      const float* tb = my_tile + g * kResK;
+      const float* cb[2] = {tb + (g * 16 + l) * 4, tb + ((g ^ 1) * 16 + l) * 4};
+      const int nb[2] = {ob, 5 - ob};   // first natural group of block h
       if (n == kResMaxN) {   // full tile: no padding anywhere
 #pragma unroll
-        for (int q = 0; q < kResIPW; q++)
-          xt[q] = *reinterpret_cast<const float4*>(tb + (nb[q / 5] + q % 5) * kResK);
+        for (int q = 0; q < kResGroups; q++)
+#pragma unroll
+          for (int c = 0; c < 2; c++)
+            xt[2 * q + c] = *reinterpret_cast<const float4*>(cb[c] + (nb[q / 5] + q % 5) * 2 * kResK);
       } else {
         const int nw = (n > w) ? (n - w + kResWarps - 1) / kResWarps : 0;   // slots of this warp that hold a row
+        const int nwh = (nw - g + 1) >> 1;                                  // ... of my half-warp's parity
 #pragma unroll
-        for (int q = 0; q < kResIPW; q++)
-          xt[q] = (q % 5 < nw - nb[q / 5]) ? *reinterpret_cast<const float4*>(tb + (nb[q / 5] + q % 5) * kResK)
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < kResGroups; q++) {
+          const bool ok = (q % 5 < nwh - nb[q / 5]);
+#pragma unroll
+          for (int c = 0; c < 2; c++)
+            xt[2 * q + c] = ok ? *reinterpret_cast<const float4*>(cb[c] + (nb[q / 5] + q % 5) * 2 * kResK)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
     }
     float4 x = *reinterpret_cast<const float4*>(my_tile + kResIPW * kResK + lane * 4);
@@ -346,7 +376,7 @@ __global__ void __launch_bounds__(kResThreads, kCtas) als_cg_resident_kernel(Res
     float dummy;
     float u_p = sweep_dots(xt, x);   // u_x = X_nnz' x0 (owner lanes)
     float uy = u_p;                  // running X_nnz' y for the loss
-    float4 v = sweep_apply<kFullG>(xt, implicit ? (cq - (cq - 1.0f) * u_p) : (cq - u_p), slot, x,
+    float4 v = sweep_apply<kFullG>(xt, implicit ? (cq - (cq - 1.0f) * u_p) : (cq - u_p), wpos, x,
                                    (kFullG && implicit) ? 1 : 0, S, sweep++, P.G, 0.0f, dummy);
     float4 r;
     if (implicit) {
@@ -372,7 +402,7 @@ __global__ void __launch_bounds__(kResThreads, kCtas) als_cg_resident_kernel(Res
       const float cw = implicit ? (cq - 1.0f) : 1.0f;
       const float spart = warp_sum((mine ? cw * u_p * u_p : 0.0f) + gterm);
       float ssum;
-      v = sweep_apply<kFullG>(xt, cw * u_p, slot, p, (kFullG && implicit) ? 2 : 0, S, sweep++, P.G, spart, ssum);
+      v = sweep_apply<kFullG>(xt, cw * u_p, wpos, p, (kFullG && implicit) ? 2 : 0, S, sweep++, P.G, spart, ssum);
       float4 Ap;
       if (implicit) {
         if (kFullG) Ap = v;
