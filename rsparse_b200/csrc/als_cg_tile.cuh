@@ -162,15 +162,25 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
     }
   };
   auto issue_tile = [&](int buf, int sl, int row, int n) {   // gathered rows + warm-start y -> shared (16-byte cp.async)
+    // A warp instruction copies CW consecutive 16-byte chunks of RP gathered rows: one index load and one 64-bit
+    // address per (row, lane) instead of per chunk (the per-chunk loop was 24 % of the kernel's instructions at rank 256).
     const int* si = idx_of(sl);
     float* tl = tile_of(buf);
     constexpr int CPR = KPAD / 4;                            // 16-byte chunks per padded row (power of two)
-    const int total = n * CPR;
-    for (int q = tid; q < total; q += T) {
-      const int j = q / CPR, c4 = q % CPR;
-      if (4 * c4 < k) cp_async_16(tl + (size_t)j * KPAD + 4 * c4, P.X + (size_t)si[j] * k + 4 * c4);
+    constexpr int CW = (CPR < 32) ? CPR : 32;                // chunks of one row per warp instruction
+    constexpr int RP = 32 / CW;                              // rows per warp instruction
+    constexpr int NC = CPR / CW;                             // instructions per row (2 at rank > 128)
+    const int cl = lane % CW;
+#pragma unroll 4
+    for (int j = w * RP + lane / CW; j < n; j += W * RP) {
+      const float* src = P.X + (size_t)si[j] * k + 4 * cl;
+      float* dst = tl + (size_t)j * KPAD + 4 * cl;
+#pragma unroll
+      for (int cc = 0; cc < NC; cc++)
+        if (4 * (cl + cc * CW) < k) cp_async_16(dst + cc * CW * 4, src + cc * CW * 4);
     }
-    if (tid < CPR && 4 * tid < k) cp_async_16(ybuf_of(buf) + 4 * tid, P.Y + (size_t)row * k + 4 * tid);
+    constexpr int CPRy = CPR;
+    if (tid < CPRy && 4 * tid < k) cp_async_16(ybuf_of(buf) + 4 * tid, P.Y + (size_t)row * k + 4 * tid);
   };
 
   // ---- pipeline prologue ----------------------------------------------------------------------------------
