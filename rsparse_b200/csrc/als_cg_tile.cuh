@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
 #pragma unroll
   for (int c = 0; c < C; c++)
     dg[c] = (!kFullG && implicit && fvalid[c]) ? ldg_f4(P.diag + foff[c]) : make_float4(0.f, 0.f, 0.f, 0.f);
-  double warp_loss = 0.0;
+  double lane_loss = 0.0;
   int sweep = 0;
 
   // dot over the k features of two replicated vectors (every lane of the CTA ends with the same value)
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
     const int buf = single ? 0 : (i & 1), sl = i % 3;
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();   // tile i and the metadata of row i+1 have landed; every warp is done with row i-1
-    if (single) {      // one buffer: this row's tile is fetched now (its metadata landed a row ago), other CTAs cover the wait
+    if (single && i == 0) {   // one buffer: the first row's tile is fetched now; later ones right after the previous row's last sweep
       issue_tile(0, sl, rid0, n);
       asm volatile("cp.async.wait_all;" ::: "memory");
       __syncthreads();
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
         else Ap[c] = axpy4(lam_use, p[c], v[c]);                              // X_nnz X_nnz' p + lambda p       (:21)
       }
       const float pAp = vdot(p, Ap);
-      const float a = (pAp != 0.0f) ? __fdiv_rn(rsold, pAp) : 0.0f;
+      const float a = (pAp != 0.0f) ? __fdividef(rsold, pAp) : 0.0f;   // hardware reciprocal, <= 2 ulp (as in als_resident.cuh)
 #pragma unroll
       for (int c = 0; c < C; c++) {
         x[c] = axpy4(a, p[c], x[c]);
@@ -423,11 +423,14 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
       if (it + 1 == n_cg) break;
       const float rsnew = vdot(r, r);
       if (rsnew < (float)B200ALS_CG_TOL) break;                          // identical in every warp
-      const float bt = __fdiv_rn(rsnew, rsold);
+      const float bt = __fdividef(rsnew, rsold);
 #pragma unroll
       for (int c = 0; c < C; c++) p[c] = axpy4(bt, p[c], r[c]);
       rsold = rsnew;
     }
+    // One buffer: nobody reads the tile after the last sweep (every warp has passed its closing barrier), and the next
+    // row's metadata landed a row ago -- its copies run under the store of y, the loss pass and the next row's set-up.
+    if (single && valid(i + 1)) issue_tile(0, (i + 1) % 3, rid1, slab_cnt(n1));
     if (w == 0 && gi == 0 && crank == 0) {
 #pragma unroll
       for (int c = 0; c < C; c++)
@@ -441,9 +444,13 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
         const float d = implicit ? (1.0f - uy[j]) : (cj - uy[j]);
         l += implicit ? d * d * cj : d * d;
       }
-      l = warp_sum(l);
-      if (w == 0 && crank == 0) l = fmaf(lam_use, vdot(x, x), l);
-      if (lane == 0) warp_loss += (double)l;
+      // per-lane fp64 sums (one block reduction at the end of the kernel): lane group 0 of warp 0 adds lambda |y|^2
+      if (w == 0 && gi == 0 && crank == 0) {
+        float yy = dot4(x[0], x[0]);
+        if constexpr (C == 2) yy += dot4(x[1], x[1]);
+        l = fmaf(lam_use, yy, l);
+      }
+      lane_loss += (double)l;
     }
     // ---- advance the pipeline ----
     n0 = n1; rid0 = rid1;
@@ -453,7 +460,7 @@ __global__ void __launch_bounds__(512) als_cg_tile_kernel(TileCgParams P) {
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   if constexpr (kCluster) cluster_sync_all();   // no CTA leaves while a peer may still read its shared memory
-  const double tot = block_sum_double((lane == 0) ? warp_loss : 0.0, red);
+  const double tot = block_sum_double(lane_loss, red);
   if (tid == 0) P.loss_partials[blockIdx.x] = tot;
 }
 

@@ -11,3 +11,5 @@ for WL in "c5-slice" "c3-ragged" "c3 --kernel 10" "c3-k64" "c3 --half items"; do
 import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']/1e6,2),'M/s', round(d['ms_per_step'],2),'ms', d.get('step_breakdown_ms'), 'frac', d['roofline']['frac'])"
 done
 ls $OUT
+echo "== A/B: c5-slice with 8 warps in the 2-CTA class"; B200ALS_TILE_WARPS_M=8 timeout 300 python bench.py --workload c5-slice --steps 3 --no-e2e --no-cpu 2>&1 | tail -1 | tee $OUT/bench_c5slice_w8.json | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']/1e6,2),'M/s', round(d['ms_per_step'],2),'ms', d.get('step_breakdown_ms'), 'frac', d['roofline']['frac'])"
