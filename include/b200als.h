@@ -145,7 +145,7 @@ int b200als_gram_float(const float* X, int rank, int64_t n, double lambda, float
  * outputs are n_user x top_k column-major, `glob_mean` is added to every score.  Scores are accumulated in double
  * like the reference (which converts float factors to double, R/utils.R:35-36).  user_emb is rank x n_user
  * (what transform_ produces before R's t()); not_recommend is a CSR over users with ascending 0-based column
- * indices (the @p / @j slots of a dgRMatrix) or NULL.  Limits of this engine: rank <= 128, top_k <= 128. */
+ * indices (the @p / @j slots of a dgRMatrix) or NULL.  Limits of this engine: rank <= 256, top_k <= 128. */
 int b200als_top_product(const float* user_emb, int64_t n_user, const float* item_emb, int32_t n_item, int rank,
                         int top_k, const int32_t* not_recommend_ptr, const int32_t* not_recommend_idx,
                         const int32_t* exclude, int n_exclude, double glob_mean, int32_t* idx_out,

@@ -11,7 +11,7 @@ __global__ void set_bits_kernel(const int32_t* __restrict__ ids_1based, int n, i
 static int run_topk(Ctx& c, const float* dX, long long n_user, const float* dY, int n_item, int rank, int top_k,
                     const int32_t* h_nr_ptr, const int32_t* h_nr_idx, const int32_t* h_exclude, int n_exclude,
                     double glob_mean, int32_t* h_idx_out, double* h_scores_out) {
-  if (rank > kTopMaxRank) return fail(B200ALS_EUNSUPPORTED, "top_product: rank > 128 is not supported");
+  if (rank > kTopMaxRank) return fail(B200ALS_EUNSUPPORTED, "top_product: rank > 256 is not supported");
   if (top_k < 1 || top_k > kTopMaxK) return fail(B200ALS_EUNSUPPORTED, "top_product: k must be in 1..128");
   if (n_user <= 0) return B200ALS_OK;
   DevBuf nr_ptr, nr_idx, excl, bits, d_idx, d_sc;

@@ -6,7 +6,8 @@
 //   pairs with the STRICT replacement rule `q.top().first < val`, emit indices (1-based) by decreasing (score, index).
 // Here: one CTA = 32 users, items streamed in tiles of 64.  Scores are accumulated in DOUBLE like the reference
 // (float x float products are exact in double), so the ranking does not depend on fp32 rounding:
-//   * user block and item tile are staged transposed in shared memory as doubles (xs[f][u], ys[f][i]);
+//   * user block and item tile are staged transposed in shared memory as doubles (xs[f][u], ys[f][i]); ranks above
+//     128 (up to 256) stage the item tile in two passes of 128 features into the same accumulators;
 //   * 256 threads, thread tile 2 users x 4 items, per feature 3 x LDS.128 + 8 DFMA;
 //   * selection: warp w owns users 4w..4w+3; a score becomes a candidate only if it beats the user's current k-th
 //     score (strictly) -- only candidates pay for the exclusion tests (bitmap; binary search in the user's sorted
@@ -20,11 +21,12 @@ namespace b200als {
 constexpr int kTopUB = 32;      // users per CTA
 constexpr int kTopIT = 64;      // items per tile
 constexpr int kTopMaxK = 128;   // top_k limit (list storage)
-constexpr int kTopMaxRank = 128;
+constexpr int kTopMaxRank = 256;   // the user block is staged whole
+constexpr int kTopFC = 128;        // features of an item tile staged at a time (rank > 128: two passes, same accumulators)
 
 struct TopkSmem {
-  alignas(16) double xs[kTopMaxRank][kTopUB];       // 32 KB
-  alignas(16) double ys[kTopMaxRank][kTopIT];       // 64 KB
+  alignas(16) double xs[kTopMaxRank][kTopUB];       // 64 KB
+  alignas(16) double ys[kTopFC][kTopIT];            // 64 KB
   alignas(16) double sc[kTopUB][kTopIT + 2];        // scores of the current tile
   double lscore[kTopUB][kTopMaxK];                  // per-user sorted lists
   int lidx[kTopUB][kTopMaxK];
@@ -73,22 +75,25 @@ __global__ void __launch_bounds__(256) topk_kernel(TopkParams P) {
   const int tu = (tid >> 4) * 2;      // this thread's 2 users  (16 thread-rows x 2)
   const int ti = (tid & 15) * 4;      // this thread's 4 items  (16 thread-cols x 4)
   for (int i0 = 0; i0 < P.n_item; i0 += kTopIT) {
-    __syncthreads();   // previous tile's scores consumed, xs ready
-    for (int e = tid; e < kTopIT * rank; e += 256) {
-      const int i = e / rank, f = e - i * rank;
-      S.ys[f][i] = (i0 + i < P.n_item) ? (double)__ldg(P.y + (size_t)(i0 + i) * rank + f) : 0.0;
-    }
-    __syncthreads();
     double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    for (int f0 = 0; f0 < rank; f0 += kTopFC) {   // features in ascending order, as one pass would take them
+      const int fc = min(kTopFC, rank - f0);
+      __syncthreads();   // previous tile's scores (first pass) / previous feature chunk consumed, xs ready
+      for (int e = tid; e < kTopIT * fc; e += 256) {
+        const int i = e / fc, f = e - i * fc;
+        S.ys[f][i] = (i0 + i < P.n_item) ? (double)__ldg(P.y + (size_t)(i0 + i) * rank + f0 + f) : 0.0;
+      }
+      __syncthreads();
 #pragma unroll 4
-    for (int f = 0; f < rank; f++) {
-      const double2 xv = *reinterpret_cast<const double2*>(&S.xs[f][tu]);
-      const double2 y01 = *reinterpret_cast<const double2*>(&S.ys[f][ti]);
-      const double2 y23 = *reinterpret_cast<const double2*>(&S.ys[f][ti + 2]);
-      acc[0][0] = fma(xv.x, y01.x, acc[0][0]); acc[0][1] = fma(xv.x, y01.y, acc[0][1]);
-      acc[0][2] = fma(xv.x, y23.x, acc[0][2]); acc[0][3] = fma(xv.x, y23.y, acc[0][3]);
-      acc[1][0] = fma(xv.y, y01.x, acc[1][0]); acc[1][1] = fma(xv.y, y01.y, acc[1][1]);
-      acc[1][2] = fma(xv.y, y23.x, acc[1][2]); acc[1][3] = fma(xv.y, y23.y, acc[1][3]);
+      for (int f = 0; f < fc; f++) {
+        const double2 xv = *reinterpret_cast<const double2*>(&S.xs[f0 + f][tu]);
+        const double2 y01 = *reinterpret_cast<const double2*>(&S.ys[f][ti]);
+        const double2 y23 = *reinterpret_cast<const double2*>(&S.ys[f][ti + 2]);
+        acc[0][0] = fma(xv.x, y01.x, acc[0][0]); acc[0][1] = fma(xv.x, y01.y, acc[0][1]);
+        acc[0][2] = fma(xv.x, y23.x, acc[0][2]); acc[0][3] = fma(xv.x, y23.y, acc[0][3]);
+        acc[1][0] = fma(xv.y, y01.x, acc[1][0]); acc[1][1] = fma(xv.y, y01.y, acc[1][1]);
+        acc[1][2] = fma(xv.y, y23.x, acc[1][2]); acc[1][3] = fma(xv.y, y23.y, acc[1][3]);
+      }
     }
 #pragma unroll
     for (int a = 0; a < 2; a++)
